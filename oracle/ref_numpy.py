@@ -1,0 +1,448 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the reference's matrix-product hot path.
+
+This is the parity ORACLE for the CUDA path.  It restates, on the CPU, what
+antoine311200/Syngular's `syngular.tensor` does (citations `file:line` are relative to the
+reference root), with exactly ONE generalisation: the *natural clamp* -- the width kept by
+the QR-truncation step is min(q, rows(L)) (= Q.shape[1]); the reference crashes in `reshape`
+when that is < q.  Wherever the reference runs, this agrees with it:
+pinned by tests/golden/*.npz, which oracle/gen_golden.py produced from the unmodified reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this file.
+
+Conventions (tensor/matrix_product_state.py:54-56, tensor/matrix_product_operator.py:49-60):
+  MPS core k : (l_k, d_k, r_k)            C-contiguous, l_0 = r_{N-1} = 1
+  MPO core k : (l_k, in_k, out_k, r_k)
+  dense MPO tensor is given as (in_0..in_{N-1}, out_0..out_{N-1}) and interleaved internally.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------------------
+# elementary steps
+# --------------------------------------------------------------------------------------
+def qrt(L, q):
+    """The reference truncation step (matrix_product_state.py:443-446, matrix_product_operator.py:555-558,
+    and decompose :307-311 / :436-440): complete QR, keep the first q columns of Q and rows of R.
+    Equivalent to projecting L on the span of its own first q columns.  Natural clamp: the kept
+    width is min(q, L.shape[0])."""
+    Q, R = np.linalg.qr(L, mode="complete")
+    return Q[:, :q], R[:q, :]
+
+
+def site_mpo_mps(X, W):
+    """K1, matrix_product_operator.py:184-190:  C[(a,l), o, (b,r)] = sum_i X[a,i,b] W[l,i,o,r]."""
+    a, i, b = X.shape
+    l, i2, o, r = W.shape
+    assert i == i2
+    C = np.einsum("aib,lior->alobr", X, W)
+    return C.reshape(a * l, o, b * r)
+
+
+def site_mpo_mpo(A, B):
+    """K2, matrix_product_operator.py:280-287: C[(lA,lB), iA, oB, (rA,rB)] = sum_x A[lA,iA,x,rA] B[lB,x,oB,rB]."""
+    la, ia, xa, ra = A.shape
+    lb, xb, ob, rb = B.shape
+    assert xa == xb
+    C = np.einsum("aixb,cxod->aciobd", A, B)
+    return C.reshape(la * lb, ia, ob, ra * rb)
+
+
+def site_add(A, B, first, last):
+    """K9, matrix_product_state.py:82-96 / matrix_product_operator.py:90-106: direct sum of the bond spaces
+    (self's block first); first core concatenates on r, last core on l.  Always float64 (np.zeros)."""
+    la, ra = A.shape[0], A.shape[-1]
+    lb, rb = B.shape[0], B.shape[-1]
+    phys = A.shape[1:-1]
+    out = np.zeros(((la if first else la + lb),) + phys + ((ra if last else ra + rb),))
+    if first and last:
+        # single-site chain: the reference's `wing_left` branch wins (np.block([A, B]) cannot fit) -> crash there;
+        # here: plain sum is the only meaningful reading, but we keep the reference's behaviour out of scope.
+        raise Exception("single-site addition is not defined by the reference")
+    if first:
+        out[..., :ra] = A
+        out[..., ra:] = B
+    elif last:
+        out[:la] = A
+        out[la:] = B
+    else:
+        out[:la, ..., :ra] = A
+        out[la:, ..., ra:] = B
+    return out
+
+
+def site_kron(A, B):
+    """K10, matrix_product_operator.py:140-152: per (in,out) Kronecker product of the bond matrices."""
+    la, i, o, ra = A.shape
+    lb, _, _, rb = B.shape
+    C = np.einsum("aiob,ciod->aciobd", A, B)
+    return C.reshape(la * lb, i, o, ra * rb)
+
+
+def _flat3(core):
+    """View a core as (l, phys, r) with all physical legs flattened."""
+    return core.reshape(core.shape[0], -1, core.shape[-1])
+
+
+# --------------------------------------------------------------------------------------
+# sweeps on bare core lists
+# --------------------------------------------------------------------------------------
+def round_qr(cores, q):
+    """The strict `>>` sweep (matrix_product_state.py:432-468, matrix_product_operator.py:544-580) on a list of
+    cores; returns new cores.  No canonicalisation before or after."""
+    cores = [np.array(c, copy=True) for c in cores]
+    n = len(cores)
+    for k in range(n - 1):
+        cur, nxt = cores[k], cores[k + 1]
+        phys = cur.shape[1:-1]
+        L = cur.reshape(-1, cur.shape[-1])
+        Q, S = qrt(L, q)
+        kept = Q.shape[1]
+        W = S @ nxt.reshape(nxt.shape[0], -1)
+        cores[k] = Q.reshape((cur.shape[0],) + phys + (kept,))
+        cores[k + 1] = W.reshape((kept,) + nxt.shape[1:])
+    return cores
+
+
+def left_orthonormalize(cores):
+    """matrix_product_state.py:554-566 / matrix_product_operator.py:673-694: reduced QR sweep, left to right."""
+    cores = [np.array(c, copy=True) for c in cores]
+    for k in range(len(cores) - 1):
+        cur, nxt = cores[k], cores[k + 1]
+        L = cur.reshape(-1, cur.shape[-1])
+        U, B = np.linalg.qr(L)
+        W = B @ nxt.reshape(nxt.shape[0], -1)
+        cores[k] = U.reshape(cur.shape[:-1] + (U.shape[1],))
+        cores[k + 1] = W.reshape((U.shape[1],) + nxt.shape[1:])
+    return cores
+
+
+def right_orthonormalize(cores):
+    """matrix_product_state.py:568-580 / matrix_product_operator.py:696-719: QR of R^T, right to left."""
+    cores = [np.array(c, copy=True) for c in cores]
+    for k in range(len(cores) - 1, 0, -1):
+        cur, prv = cores[k], cores[k - 1]
+        R = cur.reshape(cur.shape[0], -1)
+        V, U = np.linalg.qr(R.T)
+        W = prv.reshape(-1, prv.shape[-1]) @ U.T
+        cores[k] = V.T.reshape((V.shape[1],) + cur.shape[1:])
+        cores[k - 1] = W.reshape(prv.shape[:-1] + (V.shape[1],))
+    return cores
+
+
+def overlap(A, B):
+    """`A | B`, matrix_product_state.py:116-129: bilinear (NO conjugation) transfer-matrix contraction."""
+    E = np.ones((1, 1), dtype=np.result_type(A[0].dtype, B[0].dtype))
+    for a, b in zip(A, B):
+        a3, b3 = _flat3(a), _flat3(b)
+        T = np.tensordot(E, a3, axes=(0, 0))            # (lb, d, ra)
+        E = np.tensordot(T, b3, axes=([0, 1], [0, 1]))  # (ra, rb)
+    return E.reshape(1)[0]
+
+
+def to_dense(cores):
+    """Dense tensor of a chain: MPS -> (d_0..d_{N-1}); MPO -> (in_0..in_{N-1}, out_0..out_{N-1}).
+    Same numbers as the reference's per-index `retrieve` loops (matrix_product_state.py:265-273, :546-551;
+    matrix_product_operator.py:405-416, :663-670), evaluated by one left-to-right chain."""
+    T = cores[0].reshape(-1, cores[0].shape[-1])
+    dims = list(cores[0].shape[1:-1])
+    for c in cores[1:]:
+        T = T @ c.reshape(c.shape[0], -1)
+        T = T.reshape(-1, c.shape[-1])
+        dims += list(c.shape[1:-1])
+    T = T.reshape(dims)
+    if cores[0].ndim == 4:
+        n = len(cores)
+        T = T.transpose(list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
+    return T
+
+
+def retrieve(cores, idx_in, idx_out=None):
+    """One amplitude as the product of the sliced bond matrices (matrix_product_state.py:546-551,
+    matrix_product_operator.py:663-670); returns a (1,1) array like the reference."""
+    M = None
+    for k, c in enumerate(cores):
+        m = c[:, idx_in[k], :] if idx_out is None else c[:, idx_in[k], idx_out[k], :]
+        M = m if M is None else M @ m
+    return M
+
+
+def decompose_left(T, shapes):
+    """TT decomposition by the qrt step, left to right (matrix_product_state.py:298-319,
+    matrix_product_operator.py:430-450).  `T` is the (interleaved, for an MPO) dense tensor and `shapes` the
+    declared core shapes; the rank kept at bond k is shapes[k][-1] (clamped)."""
+    cores = []
+    n = len(shapes)
+    l = 1
+    for k in range(n - 1):
+        phys = int(np.prod(shapes[k][1:-1]))
+        L = T.reshape(l * phys, -1)
+        Q, R = qrt(L, shapes[k][-1])
+        kept = Q.shape[1]
+        cores.append(Q.reshape((l,) + tuple(shapes[k][1:-1]) + (kept,)))
+        T, l = R, kept
+    cores.append(T.reshape((l,) + tuple(shapes[n - 1][1:-1]) + (1,)))
+    return cores
+
+
+def decompose_right(T, shapes):
+    """MPS-only right-to-left variant (matrix_product_state.py:324-347): QR of the transposed right unfolding."""
+    n = len(shapes)
+    cores = [None] * n
+    r = 1
+    for k in range(n - 1, 0, -1):
+        phys = int(np.prod(shapes[k][1:-1]))
+        L = T.reshape(-1, phys * r).T
+        Q, R = qrt(L, shapes[k][0])
+        kept = Q.shape[1]
+        cores[k] = Q.T.reshape((kept,) + tuple(shapes[k][1:-1]) + (r,))
+        T, r = R.T, kept
+    cores[0] = T.reshape((1,) + tuple(shapes[0][1:-1]) + (r,))
+    return cores
+
+
+# --------------------------------------------------------------------------------------
+# the two container types, with the reference's metadata rules
+# --------------------------------------------------------------------------------------
+class _Chain:
+    """Shared behaviour of the two containers.  Metadata rules restated from the reference:
+      * `from_sites` derives shape / input_shape / bond_shape from the cores (MPS :191-214, MPO :357-380);
+      * the result of `>>` keeps the PRE-truncation `bond_shape` (stale) while `.shape` is updated
+        (MPS :433-468; MPO :545-580) -- later `min_bond` computations and `>>` guards depend on it;
+      * `>>` with q >= min(bond_shape) returns the operand itself (MPS :367-368; MPO :473-474).
+    Not replicated: the MPO copy()/from_sites list aliasing that overwrites the source."""
+
+    PHYS = 1
+
+    def __init__(self):
+        self.sites = []
+        self.sites_number = 0
+        self.shape = []
+        self.bond_shape = ()
+        self.input_shape = ()
+        self.decomposed = False
+        self.orthonormalized = None
+        self.parameters_number = 0
+        self.real_parameters_number = 0
+        self.verbose = 0
+
+    @classmethod
+    def from_sites(cls, sites, orthogonality=None, real_parameters_number=None):
+        mp = cls()
+        mp.sites = list(sites)
+        mp.sites_number = len(sites)
+        mp.decomposed = True
+        mp.orthonormalized = orthogonality
+        mp.parameters_number = int(sum(int(np.prod(s.shape)) for s in sites))
+        mp.real_parameters_number = real_parameters_number
+        mp.shape = [tuple(s.shape) for s in sites]
+        mp.input_shape = tuple(s.shape[1] for s in sites)
+        if cls.PHYS == 2:
+            mp.output_shape = tuple(s.shape[2] for s in sites)
+        mp.bond_shape = tuple(s.shape[-1] for s in sites[:-1])
+        return mp
+
+    def copy(self):
+        return type(self).from_sites(self.sites)
+
+    # `>>`
+    def __rshift__(self, dim):
+        if not isinstance(dim, int):
+            raise Exception("dimension should be an integer")
+        return self.compress(dim, strict=True)
+
+    def compress(self, dim, mode="left", strict=False):
+        if dim >= min(self.bond_shape):
+            return self
+        if strict:
+            that = self.copy()                       # bond_shape of `that` = actual bonds before truncation
+            that.sites = round_qr(self.sites, dim)
+            that.shape = [tuple(s.shape) for s in that.sites]
+            that.parameters_number = int(sum(int(np.prod(s.shape)) for s in that.sites))
+            return that
+        # non-strict: canonicalise first, then the same qrt sweep from that side, in place
+        # (MPS :370-430; MPO :480-541).  Returns None like the reference.
+        if self.PHYS == 2:
+            self.bond_shape = (dim,) * (self.sites_number - 1)      # MPO :477
+        if mode == "left":
+            if self.orthonormalized != "left":
+                self.left_orthonormalization()
+            self.sites = round_qr(self.sites, dim)
+        elif mode == "right":
+            if self.orthonormalized != "right":
+                self.right_orthonormalization()
+            rev = [np.swapaxes(_flat3(s), 0, 2) for s in reversed(self.sites)]
+            # right sweep uses the *reduced* QR of R^T (MPS :410, MPO :520) -- same projection as qrt
+            out = round_qr(rev, dim)
+            shapes = [s.shape for s in self.sites]
+            new = []
+            for s, ref_shape in zip(reversed(out), shapes):
+                t = np.swapaxes(s, 0, 2)
+                new.append(t.reshape((t.shape[0],) + tuple(ref_shape[1:-1]) + (t.shape[2],)))
+            self.sites = new
+        self.shape = [tuple(s.shape) for s in self.sites]
+        self.parameters_number = int(sum(int(np.prod(s.shape)) for s in self.sites))
+        return None
+
+    def left_orthonormalization(self):
+        self.sites = left_orthonormalize(self.sites)
+        self.shape = [tuple(s.shape) for s in self.sites]
+        self.orthonormalized = "left"
+        return self if self.PHYS == 2 else None
+
+    def right_orthonormalization(self):
+        self.sites = right_orthonormalize(self.sites)
+        self.shape = [tuple(s.shape) for s in self.sites]
+        self.orthonormalized = "right"
+        return self if self.PHYS == 2 else None
+
+    def left_orthogonality(self, k):
+        L = self.sites[k].reshape(-1, self.sites[k].shape[-1])
+        return L.T @ L
+
+    def right_orthogonality(self, k):
+        R = self.sites[k].reshape(self.sites[k].shape[0], -1)
+        return R @ R.T
+
+    def to_tensor(self):
+        return to_dense(self.sites)
+
+
+class MPS(_Chain):
+    PHYS = 1
+
+    @classmethod
+    def dense(cls, tensor, bond_shape, mode="left"):
+        """`MatrixProductState(tensor, bond_shape).decompose(mode)` (matrix_product_state.py:30-61, :296-350)."""
+        tensor = np.asarray(tensor)
+        n = len(bond_shape) + 1
+        if tensor.ndim != n:
+            raise Exception("dimensions of bond indices do not match order - 1")
+        b = (1,) + tuple(bond_shape) + (1,)
+        shapes = [(b[k], tensor.shape[k], b[k + 1]) for k in range(n)]
+        cores = decompose_left(tensor, shapes) if mode == "left" else decompose_right(tensor, shapes)
+        mp = cls.from_sites(cores, real_parameters_number=int(np.prod(tensor.shape)))
+        mp.bond_shape = tuple(bond_shape)            # declared, not derived (matrix_product_state.py:38)
+        mp.shape = shapes
+        mp.input_shape = tuple(tensor.shape)
+        return mp
+
+    @classmethod
+    def zeros(cls, input_shape, bond_shape):
+        n = len(input_shape)
+        b = (1,) + tuple(bond_shape) + (1,)
+        return cls.from_sites([np.zeros((b[k], input_shape[k], b[k + 1])) for k in range(n)])
+
+    def __add__(self, other):
+        if not (self.decomposed and other.decomposed):
+            raise Exception("Both Matrix Product Operator must be in canonical form (use .decompose()")
+        n = self.sites_number
+        return MPS.from_sites([site_add(self.sites[k], other.sites[k], k == 0, k == n - 1) for k in range(n)])
+
+    def __or__(self, other):
+        if not isinstance(other, MPS):
+            raise Exception("right-hand site must be a MatrixProductState")
+        return overlap(self.sites, other.sites)
+
+    def dot(self):
+        return np.sqrt(self | self)
+
+    def normalize(self):
+        """matrix_product_state.py:252-256: divide the LAST core by its Frobenius norm, in place."""
+        self.sites[-1] = self.sites[-1] / np.linalg.norm(self.sites[-1].reshape(self.sites[-1].shape[0], -1))
+        return self
+
+    def __getitem__(self, key):
+        if len(key) != self.sites_number:
+            raise Exception("input indices do not match the number of sites")
+        return retrieve(self.sites, key)
+
+
+class MPO(_Chain):
+    PHYS = 2
+
+    @classmethod
+    def dense(cls, tensor, bond_shape):
+        """`MatrixProductOperator(tensor, bond_shape).decompose()` (matrix_product_operator.py:25-64, :418-467)."""
+        tensor = np.asarray(tensor)
+        bond_shape = tuple(bond_shape)
+        n = len(bond_shape) + 1
+        inp, out = tuple(tensor.shape[:n]), tuple(tensor.shape[n:])
+        if len(inp) != len(out):
+            raise Exception("input_shape and output_shape of the tensor must have the same length")
+        if len(inp) != n:
+            raise Exception("dimensions of bond indices do not match input dimension - 1")
+        if bond_shape == ():
+            mp = cls.from_sites([tensor.reshape(1, inp[0], out[0], 1)])
+            return mp
+        inter = tensor.transpose(sum(zip(range(n), range(n, 2 * n)), ()))
+        b = (1,) + bond_shape + (1,)
+        shapes = [(b[k], inp[k], out[k], b[k + 1]) for k in range(n)]
+        cores = decompose_left(inter, shapes)
+        mp = cls.from_sites(cores, real_parameters_number=int(np.prod(tensor.shape)))
+        mp.bond_shape = bond_shape
+        mp.shape = shapes
+        return mp
+
+    @classmethod
+    def zeros(cls, input_shape, output_shape, bond_shape):
+        n = len(input_shape)
+        b = (1,) + tuple(bond_shape) + (1,)
+        return cls.from_sites([np.zeros((b[k], input_shape[k], output_shape[k], b[k + 1])) for k in range(n)])
+
+    def __add__(self, other):
+        m = min(min(self.bond_shape), min(other.bond_shape))          # matrix_product_operator.py:80 (metadata!)
+        if not (self.decomposed and other.decomposed):
+            raise Exception("Both Matrix Product Operator must be in canonical form (use .decompose()")
+        n = self.sites_number
+        sites = [site_add(self.sites[k], other.sites[k], k == 0, k == n - 1) for k in range(n)]
+        return MPO.from_sites(sites) >> m
+
+    def __mul__(self, other):
+        m = min(min(self.bond_shape), min(other.bond_shape))          # :128
+        if not isinstance(other, MPO):
+            raise Exception("left hand-side must be either a MatrixProductState or a MatrixProductOperator")
+        sites = [site_kron(a, b) for a, b in zip(self.sites, other.sites)]
+        return MPO.from_sites(sites) >> m
+
+    def __matmul__(self, other):
+        m = min(min(self.bond_shape), min(other.bond_shape))          # :176 (metadata!)
+        if isinstance(other, MPS):
+            sites = [site_mpo_mps(x, w) for x, w in zip(other.sites, self.sites)]
+            return MPS.from_sites(sites) >> m                          # :192
+        if isinstance(other, MPO):
+            sites = [site_mpo_mpo(a, b) for a, b in zip(self.sites, other.sites)]
+            return MPO.from_sites(sites) >> m                          # :289
+        return None
+
+    def __getitem__(self, key):
+        kin, kout = key
+        if len(kin) != self.sites_number:
+            raise Exception("input indices do not match the number of sites")
+        if len(kout) != self.sites_number:
+            raise Exception("output indices do not match the number of sites")
+        return retrieve(self.sites, kin, kout)
+
+
+def mul(op1, op2, mode="standard"):
+    """`syn.mul`, tensor/utils.py:8-73.  NOTE (MPO,MPO) contracts op2's OUTPUT with op1's INPUT (:62) --
+    the reverse of `@` -- with op2's bond major."""
+    if op1.sites_number != op2.sites_number:
+        raise Exception("both operator do not have the same number of sites")
+    m = min(min(op1.bond_shape), min(op2.bond_shape))
+    if mode != "standard":
+        return None
+    if isinstance(op1, MPS) and isinstance(op2, MPO):
+        if not op1.decomposed or not op2.decomposed:
+            raise Exception("Operators and States must be decomposed")
+        return MPS.from_sites([site_mpo_mps(x, w) for x, w in zip(op1.sites, op2.sites)]) >> m
+    if isinstance(op1, MPO) and isinstance(op2, MPS):
+        if not op1.decomposed or not op2.decomposed:
+            raise Exception("Operators and States must be decomposed")
+        return MPS.from_sites([site_mpo_mps(x, w) for x, w in zip(op2.sites, op1.sites)]) >> m
+    if isinstance(op1, MPS) and isinstance(op2, MPS):
+        return op1 | op2
+    if isinstance(op1, MPO) and isinstance(op2, MPO):
+        return MPO.from_sites([site_mpo_mpo(b, a) for a, b in zip(op1.sites, op2.sites)]) >> m
+    raise Exception("`syn.mul` should be provided MatrixProductState or MatrixProductOperator objects only")
