@@ -1,0 +1,84 @@
+"""Build libsyngular_b200.so IN-TREE with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m syngular_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libsyngular_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+    "-Xptxas", "-v",
+]
+# --use_fast_math only affects FP32 intrinsics; all arithmetic of this library is FP64.
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "syngular_b200.h")]
+    stamp = os.path.join(OBJ, "stamp.txt")
+    digest = _digest(sources + headers)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB
+    hdr_digest = _digest(headers)
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        tag = os.path.join(OBJ, os.path.basename(src)[:-3] + ".tag")
+        d = _digest([src]) + hdr_digest
+        if not force and os.path.exists(obj) and os.path.exists(tag) and open(tag).read() == d:
+            return obj, ""
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        open(tag, "w").write(d)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        results = list(ex.map(compile_one, sources))
+    objs = [o for o, _ in results]
+    log = "\n".join(l for _, l in results if l)
+    open(os.path.join(OBJ, "ptxas.log"), "a").write(log)
+    if verbose and log:
+        print(log)
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    open(stamp, "w").write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

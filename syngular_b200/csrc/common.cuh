@@ -1,0 +1,76 @@
+// Shared helpers for the sm_100a kernels of libsyngular_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/syngular_b200.h"
+
+namespace syn {
+
+// ---- error channel (never throw across the C ABI) -------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SYN_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return ::syn::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SYN_REQUIRE(cond, ...)                    \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::syn::set_error(__VA_ARGS__);        \
+            return 2;                             \
+        }                                         \
+    } while (0)
+
+inline int launch_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what, __FILE__, __LINE__);
+    return 0;
+}
+
+int sm_count();
+
+// ---- device helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t idx2(const syn_index_t& ix, int x) {
+    // two-level index: (x / div) * outer + (x % div) * inner ; div >= extent collapses to x * inner
+    unsigned q = (unsigned)x / (unsigned)ix.div;
+    unsigned r = (unsigned)x - q * (unsigned)ix.div;
+    return (int64_t)q * ix.outer + (int64_t)r * ix.inner;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    // D(8x8) += A(8x4,row) * B(4x8,col); SASS: DMMA.8x8x4
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src, bool pred) {
+    // LDGSTS with zero-fill when !pred (src-size 0)
+    uint32_t d = smem_u32(smem_dst);
+    int sz = pred ? BYTES : 0;
+    if constexpr (BYTES == 16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz));
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(sz));
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace syn

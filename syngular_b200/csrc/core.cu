@@ -1,0 +1,37 @@
+// Library lifecycle + error channel of libsyngular_b200.so.
+#include "common.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace syn {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return 1;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace syn
+
+extern "C" int syn_version(void) { return 100; }
+extern "C" const char* syn_last_error(void) { return syn::g_error; }
+extern "C" int syn_device_sm_count(void) { return syn::sm_count(); }

@@ -1,0 +1,309 @@
+// Strided tensor-contraction GEMM on the FP64 tensor pipe (DMMA.8x8x4), sm_100a.
+//
+//   C[m,n] = alpha * sum_k A[m,k] * B[k,n] + beta * C[m,n]      (batched)
+//
+// Every logical index (m, n, k, batch) of every operand is a two-level strided index (syn_index_t), so the
+// per-site contractions of the matrix-product hot path -- which in the reference are opt_einsum/np.tensordot
+// calls on reshaped, permuted cores (matrix_product_operator.py:184,280; tensor/utils.py:35,49,62) and the
+// `S @ R`, `B @ R`, `L @ U.T` products of the sweeps (matrix_product_state.py:448,561,575;
+// matrix_product_operator.py:560,682,705) -- run without any transposition copy.
+//
+// Design (B200): Blackwell's tcgen05 has no FP64 kind; FP64 matrix math runs on DMMA (measured 37.1 TFLOP/s on
+// this part, tools/microbench).  One DMMA.8x8x4 occupies an SM sub-partition for 16 cycles, so the pipe is fed
+// comfortably from shared memory: operands are staged by a 4-stage cp.async (LDGSTS) ring, 16-byte chunks along
+// whichever logical dimension is contiguous in HBM; tiles are stored in shared memory in the orientation they
+// arrive in, padded so that the 64-bit fragment loads of a half-warp hit 16 distinct 8-byte bank pairs.
+#include "common.cuh"
+
+namespace syn {
+
+template <int BM_, int BN_, int BK_, int WM_, int WN_, int STAGES_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_;
+    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+    static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+    static constexpr int MT = WM / 8, NT = WN / 8;
+    static constexpr int PAD = 4;   // strides = 4 (mod 16) doubles -> conflict-free DMMA fragment loads
+};
+
+// Loader for one operand tile of ROWS x BK logical elements (ROWS = BM for A, BN for B).
+//   ROW_MAJOR_IN_HBM == false : contiguous along k  -> smem [row][k]   (stride BK+PAD)
+//   ROW_MAJOR_IN_HBM == true  : contiguous along row-> smem [k][row]   (stride ROWS+PAD)
+template <class C, int ROWS, bool ALONG_ROWS, int VEC>
+struct OperandLoader {
+    static constexpr int T = C::THREADS;
+    static constexpr int STRIDE = ALONG_ROWS ? (ROWS + C::PAD) : (C::BK + C::PAD);
+    static constexpr int TILE_ELEMS = ALONG_ROWS ? C::BK * STRIDE : ROWS * STRIDE;
+    // chunks along the contiguous dimension
+    static constexpr int CH = (ALONG_ROWS ? ROWS : C::BK) / VEC;       // chunks per line
+    static constexpr int LINES = ALONG_ROWS ? C::BK : ROWS;            // number of lines
+    static constexpr int LINES_PER_PASS = T / CH;
+    static constexpr int PASSES = LINES / LINES_PER_PASS;
+    static_assert(T % CH == 0, "thread count must be a multiple of chunks per line");
+    static_assert(LINES % LINES_PER_PASS == 0, "lines must divide evenly");
+
+    int pos;            // position along the contiguous dimension (element index within tile)
+    int line0;          // first line handled by this thread
+    // ALONG_ROWS: one fixed row chunk, PASSES k-lines per tile.  else: one fixed k chunk, PASSES rows.
+    int64_t fixed_off;  // ALONG_ROWS: offset of the row chunk
+    bool fixed_ok;
+    int64_t row_off[ALONG_ROWS ? 1 : PASSES];
+    unsigned row_ok;
+
+    __device__ __forceinline__ void init(const syn_index_t& rows_ix, int row0, int nrows, int tid) {
+        pos = (tid % CH) * VEC;
+        line0 = tid / CH;
+        if constexpr (ALONG_ROWS) {
+            int r = row0 + pos;
+            fixed_ok = r < nrows;
+            fixed_off = fixed_ok ? idx2(rows_ix, r) : 0;
+            row_ok = 0;
+        } else {
+            row_ok = 0;
+#pragma unroll
+            for (int i = 0; i < PASSES; i++) {
+                int r = row0 + line0 + i * LINES_PER_PASS;
+                bool ok = r < nrows;
+                row_off[i] = ok ? idx2(rows_ix, r) : 0;
+                row_ok |= (ok ? 1u : 0u) << i;
+            }
+            fixed_ok = true;
+            fixed_off = 0;
+        }
+    }
+
+    __device__ __forceinline__ void load(double* smem, const double* base, const syn_index_t& k_ix, int k0, int K) const {
+        if constexpr (ALONG_ROWS) {
+#pragma unroll
+            for (int i = 0; i < PASSES; i++) {
+                int kl = line0 + i * LINES_PER_PASS;
+                int k = k0 + kl;
+                bool ok = fixed_ok && (k < K);
+                const double* src = base + (ok ? (fixed_off + idx2(k_ix, k)) : 0);
+                cp_async<VEC * 8>(smem + kl * STRIDE + pos, src, ok);
+            }
+        } else {
+            int k = k0 + pos;
+            bool kok = k < K;
+            int64_t koff = kok ? idx2(k_ix, k) : 0;
+#pragma unroll
+            for (int i = 0; i < PASSES; i++) {
+                int rl = line0 + i * LINES_PER_PASS;
+                bool ok = kok && ((row_ok >> i) & 1u);
+                const double* src = base + (ok ? (row_off[i] + koff) : 0);
+                cp_async<VEC * 8>(smem + rl * STRIDE + pos, src, ok);
+            }
+        }
+    }
+};
+
+template <class C, bool A_ALONG_M, bool B_ALONG_N, int VEC>
+__global__ void __launch_bounds__(C::THREADS)
+gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const double* __restrict__ B,
+                double* __restrict__ Cmat, int tiles_n, int c_vec) {
+    using LA = OperandLoader<C, C::BM, A_ALONG_M, VEC>;
+    using LB = OperandLoader<C, C::BN, B_ALONG_N, VEC>;
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;
+    double* sB = smem + C::STAGES * LA::TILE_ELEMS;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp / C::WARPS_N) * C::WM;
+    const int wn0 = (warp % C::WARPS_N) * C::WN;
+
+    const int tile = blockIdx.x;
+    const int m0 = (tile / tiles_n) * C::BM;
+    const int n0 = (tile % tiles_n) * C::BN;
+    const int batch = blockIdx.y + gridDim.y * blockIdx.z;
+    if (batch >= d.batch) return;
+
+    A += idx2(d.a_b, batch);
+    B += idx2(d.b_b, batch);
+    Cmat += idx2(d.c_b, batch);
+
+    LA la;
+    LB lb;
+    la.init(d.a_m, m0, d.M, tid);
+    lb.init(d.b_n, n0, d.N, tid);
+
+    const int KT = (d.K + C::BK - 1) / C::BK;
+
+    double acc[C::MT][C::NT][2];
+#pragma unroll
+    for (int i = 0; i < C::MT; i++)
+#pragma unroll
+        for (int j = 0; j < C::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < C::STAGES - 1; s++) {
+        if (s < KT) {
+            la.load(sA + s * LA::TILE_ELEMS, A, d.a_k, s * C::BK, d.K);
+            lb.load(sB + s * LB::TILE_ELEMS, B, d.b_k, s * C::BK, d.K);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<C::STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + C::STAGES - 1;
+            if (nk < KT) {
+                int s = nk % C::STAGES;
+                la.load(sA + s * LA::TILE_ELEMS, A, d.a_k, nk * C::BK, d.K);
+                lb.load(sB + s * LB::TILE_ELEMS, B, d.b_k, nk * C::BK, d.K);
+            }
+            cp_async_commit();
+        }
+        const double* a_s = sA + (kt % C::STAGES) * LA::TILE_ELEMS;
+        const double* b_s = sB + (kt % C::STAGES) * LB::TILE_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < C::BK; kk += 4) {
+            double af[C::MT], bf[C::NT];
+#pragma unroll
+            for (int i = 0; i < C::MT; i++) {
+                int r = wm0 + i * 8 + g;
+                af[i] = A_ALONG_M ? a_s[(kk + t) * LA::STRIDE + r] : a_s[r * LA::STRIDE + kk + t];
+            }
+#pragma unroll
+            for (int j = 0; j < C::NT; j++) {
+                int c = wn0 + j * 8 + g;
+                bf[j] = B_ALONG_N ? b_s[(kk + t) * LB::STRIDE + c] : b_s[c * LB::STRIDE + kk + t];
+            }
+#pragma unroll
+            for (int i = 0; i < C::MT; i++)
+#pragma unroll
+                for (int j = 0; j < C::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread owns C[row = g][col = 2t, 2t+1] of every 8x8 tile
+    const double alpha = d.alpha, beta = d.beta;
+#pragma unroll
+    for (int i = 0; i < C::MT; i++) {
+        int m = m0 + wm0 + i * 8 + g;
+        if (m >= d.M) continue;
+        int64_t mo = idx2(d.c_m, m);
+#pragma unroll
+        for (int j = 0; j < C::NT; j++) {
+            int n = n0 + wn0 + j * 8 + 2 * t;
+            if (n >= d.N) continue;
+            double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+            int64_t o0 = mo + idx2(d.c_n, n);
+            if (c_vec && (n + 1 < d.N)) {
+                double2* p = reinterpret_cast<double2*>(Cmat + o0);
+                if (beta != 0.0) {
+                    double2 old = *p;
+                    v0 += beta * old.x;
+                    v1 += beta * old.y;
+                }
+                *p = make_double2(v0, v1);
+            } else {
+                if (beta != 0.0) v0 += beta * Cmat[o0];
+                Cmat[o0] = v0;
+                if (n + 1 < d.N) {
+                    int64_t o1 = mo + idx2(d.c_n, n + 1);
+                    if (beta != 0.0) v1 += beta * Cmat[o1];
+                    Cmat[o1] = v1;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+using CfgL = GemmCfg<128, 128, 16, 64, 32, 4>;   // 256 threads, 1 CTA/SM, 160 KB smem
+using CfgS = GemmCfg<64, 64, 16, 32, 32, 4>;     // 128 threads, 80 KB smem, up to 2 CTAs/SM
+
+template <class C, bool AM, bool BN, int VEC>
+static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, int c_vec, cudaStream_t st) {
+    using LA = OperandLoader<C, C::BM, AM, VEC>;
+    using LB = OperandLoader<C, C::BN, BN, VEC>;
+    constexpr size_t smem = (size_t)C::STAGES * (LA::TILE_ELEMS + LB::TILE_ELEMS) * sizeof(double);
+    auto kern = gemm_f64_kernel<C, AM, BN, VEC>;
+    static bool configured = false;
+    if (!configured) {
+        SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int tiles_m = (d.M + C::BM - 1) / C::BM, tiles_n = (d.N + C::BN - 1) / C::BN;
+    long long tiles = (long long)tiles_m * tiles_n;
+    SYN_REQUIRE(tiles < (1ll << 31), "syn_gemm_f64: too many tiles");
+    int by = d.batch < 65535 ? d.batch : 65535;
+    int bz = (d.batch + by - 1) / by;
+    dim3 grid((unsigned)tiles, by, bz);
+    kern<<<grid, C::THREADS, smem, st>>>(d, A, B, Cm, tiles_n, c_vec);
+    return launch_status("gemm_f64_kernel");
+}
+
+template <class C>
+static int dispatch_layout(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, bool am, bool bn, int vec,
+                           int c_vec, cudaStream_t st) {
+#define SYN_GEMM_CASE(AM, BN)                                                                  \
+    if (am == AM && bn == BN) {                                                                \
+        return vec == 2 ? launch_gemm<C, AM, BN, 2>(d, A, B, Cm, c_vec, st)                    \
+                        : launch_gemm<C, AM, BN, 1>(d, A, B, Cm, c_vec, st);                   \
+    }
+    SYN_GEMM_CASE(false, false)
+    SYN_GEMM_CASE(false, true)
+    SYN_GEMM_CASE(true, false)
+    SYN_GEMM_CASE(true, true)
+#undef SYN_GEMM_CASE
+    return 2;
+}
+
+static inline bool even64(int64_t v) { return (v & 1) == 0; }
+
+// can a 16-byte chunk run along logical index `ix` (extent `ext`)?
+static bool vec_ok_along(const syn_index_t& ix, int ext) {
+    if (ix.inner != 1) return false;
+    if (ix.div >= ext) return even64(ext);               // single level: tiles start at even offsets, extent even
+    return even64(ix.div) && even64(ix.outer) && even64(ext);
+}
+static bool other_even(const syn_index_t& ix, int ext) {
+    // every offset produced by this index must be even (16-byte alignment of chunk starts)
+    if (ext <= 1) return true;
+    if (ix.div >= ext) return even64(ix.inner);
+    return even64(ix.inner) && even64(ix.outer);
+}
+
+int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double* C, cudaStream_t st) {
+    SYN_REQUIRE(d.M >= 0 && d.N >= 0 && d.K >= 0 && d.batch >= 0, "syn_gemm_f64: negative extent");
+    if (d.M == 0 || d.N == 0 || d.batch == 0) return 0;
+    const syn_index_t* all[] = {&d.a_m, &d.a_k, &d.a_b, &d.b_k, &d.b_n, &d.b_b, &d.c_m, &d.c_n, &d.c_b};
+    for (auto* ix : all) SYN_REQUIRE(ix->div >= 1, "syn_gemm_f64: index div must be >= 1");
+    SYN_REQUIRE(A && B && C, "syn_gemm_f64: null operand");
+
+    // orientation: which logical dimension is contiguous in HBM (neither -> scalar loads, k-major tile)
+    bool a_along_m = (d.a_m.inner == 1) && (d.a_k.inner != 1 || d.K == 1);
+    bool b_along_n = (d.b_n.inner == 1) && (d.b_k.inner != 1 || d.K == 1);
+
+    bool a_vec = a_along_m ? (vec_ok_along(d.a_m, d.M) && other_even(d.a_k, d.K))
+                           : (vec_ok_along(d.a_k, d.K) && other_even(d.a_m, d.M));
+    bool b_vec = b_along_n ? (vec_ok_along(d.b_n, d.N) && other_even(d.b_k, d.K))
+                           : (vec_ok_along(d.b_k, d.K) && other_even(d.b_n, d.N));
+    a_vec = a_vec && other_even(d.a_b, d.batch) && (((uintptr_t)A & 15) == 0);
+    b_vec = b_vec && other_even(d.b_b, d.batch) && (((uintptr_t)B & 15) == 0);
+    int vec = (a_vec && b_vec) ? 2 : 1;
+    int c_vec = (vec_ok_along(d.c_n, d.N) && other_even(d.c_m, d.M) && other_even(d.c_b, d.batch) &&
+                 (((uintptr_t)C & 15) == 0)) ? 1 : 0;
+
+    // tile choice: the large tile when it still fills the machine, else the small one
+    long long big_tiles = (long long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch;
+    bool use_large = (d.M > 64 && d.N > 64) && big_tiles >= (long long)sm_count();
+    if (use_large) return dispatch_layout<CfgL>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+}
+
+}  // namespace syn
+
+extern "C" int syn_gemm_f64(const syn_gemm_desc_t* desc, const double* A, const double* B, double* C, void* stream) {
+    if (!desc) {
+        syn::set_error("syn_gemm_f64: null descriptor");
+        return 2;
+    }
+    return syn::gemm_f64(*desc, A, B, C, (cudaStream_t)stream);
+}
