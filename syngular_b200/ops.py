@@ -36,3 +36,163 @@ def matmul(a, b, out=None, alpha=1.0, beta=0.0):
         out = torch.empty((nb, M, N), dtype=torch.float64, device=a.device)
     return gemm(a, b, out, M, N, K, a.stride(1), a.stride(2), b.stride(1), b.stride(2), out.stride(1), out.stride(2),
                 batch=nb, a_b=a.stride(0), b_b=b.stride(0), c_b=out.stride(0), alpha=alpha, beta=beta)
+
+
+# ---------------------------------------------------------------------------------------------------------
+_i64, _i32, _sz, _dbl = ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t, ctypes.c_double
+lib.syn_qrt_workspace_f64.restype = ctypes.c_size_t
+lib.syn_qrt_workspace_f64.argtypes = [_i32, _i32, _i32, _i32]
+lib.syn_jacobi_ctrl_bytes.restype = ctypes.c_size_t
+lib.syn_jacobi_ctrl_bytes.argtypes = [_i32, _i32]
+
+_workspaces = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    """A cached, 256-byte aligned scratch buffer owned by PyTorch (the library never allocates)."""
+    key = (tag, device)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((int(nbytes) + 7) // 8 + 32, dtype=torch.float64, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def qrt(A, q, Q=None, S=None, want_S=True):
+    """The reference truncation step on a 2-D (or batched 3-D) strided view A (m x n):
+    Q (m x qk) = orthonormal basis of span(A[:, :q]) (completed when q > n), S = Q^T A (qk x n), qk = min(q, m).
+    Replaces np.linalg.qr(L, mode="complete") + slicing (MPS:443-446, MPO:555-558) and the reduced QRs (MPS:560,574)."""
+    require_cuda_f64(A)
+    batched = A.dim() == 3
+    A3 = A if batched else A.unsqueeze(0)
+    nb, m, n = A3.shape
+    qk = min(int(q), m)
+    if Q is None:
+        Q = torch.empty((nb, m, qk) if batched else (m, qk), dtype=torch.float64, device=A.device)
+    if S is None and want_S:
+        S = torch.empty((nb, qk, n) if batched else (qk, n), dtype=torch.float64, device=A.device)
+    Q3 = Q if batched else Q.unsqueeze(0)
+    S3 = None if S is None else (S if batched else S.unsqueeze(0))
+    wsb = lib.syn_qrt_workspace_f64(m, n, int(q), nb)
+    ws = workspace(wsb, A.device)
+    qk_out = ctypes.c_int(0)
+    rc = lib.syn_qrt_f64(ptr(A3), _i64(A3.stride(1)), _i64(A3.stride(2)), _i64(A3.stride(0)), _i32(m), _i32(n), _i32(int(q)), _i32(nb),
+                         ptr(Q3), _i64(Q3.stride(1)), _i64(Q3.stride(2)), _i64(Q3.stride(0)),
+                         ptr(S3) if S3 is not None else None,
+                         _i64(S3.stride(1) if S3 is not None else 0), _i64(S3.stride(2) if S3 is not None else 0),
+                         _i64(S3.stride(0) if S3 is not None else 0),
+                         ptr(ws), _sz(ws.numel() * 8), ctypes.byref(qk_out), stream_ptr())
+    check(rc, "syn_qrt_f64")
+    return Q, S
+
+
+def qr_r(A, R=None):
+    """Upper-triangular R factor (n x n) of a tall strided view A (m x n, m >= n)."""
+    require_cuda_f64(A)
+    batched = A.dim() == 3
+    A3 = A if batched else A.unsqueeze(0)
+    nb, m, n = A3.shape
+    if R is None:
+        R = torch.empty((nb, n, n) if batched else (n, n), dtype=torch.float64, device=A.device)
+    R3 = R if batched else R.unsqueeze(0)
+    ws = workspace(lib.syn_qrt_workspace_f64(m, n, n, nb), A.device)
+    rc = lib.syn_qr_r_f64(ptr(A3), _i64(A3.stride(1)), _i64(A3.stride(2)), _i64(A3.stride(0)), _i32(m), _i32(n), _i32(nb),
+                          ptr(R3), _i64(R3.stride(1)), _i64(R3.stride(2)), _i64(R3.stride(0)), ptr(ws), _sz(ws.numel() * 8), stream_ptr())
+    check(rc, "syn_qr_r_f64")
+    return R
+
+
+def copy_strided(src, out=None):
+    """out (contiguous) = src (any 2-D / batched 3-D strided view); a tiled transpose when src is a .T view."""
+    require_cuda_f64(src)
+    batched = src.dim() == 3
+    s3 = src if batched else src.unsqueeze(0)
+    nb, m, n = s3.shape
+    if out is None:
+        out = torch.empty(tuple(src.shape), dtype=torch.float64, device=src.device)
+    assert out.is_contiguous()
+    rc = lib.syn_copy_strided_f64(ptr(s3), _i64(s3.stride(1)), _i64(s3.stride(2)), _i64(s3.stride(0)), ptr(out), _i64(m * n),
+                                  _i32(m), _i32(n), _i32(nb), stream_ptr())
+    check(rc, "syn_copy_strided_f64")
+    return out
+
+
+def jacobi_tol(n):
+    return 4.0 * (float(n) ** 0.5) * 1.1102230246251565e-16
+
+
+def jacobi_rows(G, max_sweeps=40, tol=None):
+    """In place: G (n x n contiguous, or batched) <- J G with mutually orthogonal rows (one-sided Jacobi)."""
+    require_cuda_f64(G)
+    batched = G.dim() == 3
+    G3 = G if batched else G.unsqueeze(0)
+    nb, n, n2 = G3.shape
+    assert n == n2 and G3.stride(2) == 1
+    cb = lib.syn_jacobi_ctrl_bytes(nb, max_sweeps)
+    ctrl = workspace(cb, G.device, tag="jacobi_ctrl")
+    rc = lib.syn_jacobi_rows_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(ctrl), _sz(ctrl.numel() * 8),
+                                 _i32(max_sweeps), _dbl(tol if tol is not None else jacobi_tol(n)), stream_ptr())
+    check(rc, "syn_jacobi_rows_f64")
+    return G
+
+
+def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False):
+    """Sort / normalise / cut the rows produced by jacobi_rows.  Returns (Ut, sigma, info[int32: keep, n], winfo[f64: discarded, s0])
+    -- all DEVICE tensors; the caller decides when to synchronise on `info`."""
+    require_cuda_f64(G)
+    batched = G.dim() == 3
+    G3 = G if batched else G.unsqueeze(0)
+    nb, n, _ = G3.shape
+    Ut = torch.empty((nb, n, n), dtype=torch.float64, device=G.device)
+    sigma = torch.empty((nb, n), dtype=torch.float64, device=G.device)
+    info = torch.empty((nb, 2), dtype=torch.int32, device=G.device)
+    winfo = torch.empty((nb, 2), dtype=torch.float64, device=G.device)
+    rc = lib.syn_jacobi_finalize_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(Ut), _i64(n), _i64(n * n),
+                                     ptr(sigma), _i64(n), ptr(info), ptr(winfo), _i32(int(chi_max)), _dbl(cutoff), _dbl(rank_tol),
+                                     _i32(1 if sqrt_mode else 0), stream_ptr())
+    check(rc, "syn_jacobi_finalize_f64")
+    if not batched:
+        return Ut[0], sigma[0], info[0], winfo[0]
+    return Ut, sigma, info, winfo
+
+
+def add_site(A, B, first, last):
+    """Block assembly of `A + B` for one site (MPS:82-96, MPO:90-106).  Cores contiguous, physical legs flattened by the kernel."""
+    require_cuda_f64(A, B)
+    A, B = A.contiguous(), B.contiguous()
+    la, ra, lb, rb = A.shape[0], A.shape[-1], B.shape[0], B.shape[-1]
+    phys = 1
+    for d in A.shape[1:-1]:
+        phys *= d
+    out = torch.empty(((la if first else la + lb),) + tuple(A.shape[1:-1]) + ((ra if last else ra + rb),), dtype=torch.float64, device=A.device)
+    check(lib.syn_add_site_f64(ptr(A), ptr(B), ptr(out), _i32(la), _i32(ra), _i32(lb), _i32(rb), _i32(phys), _i32(int(first)), _i32(int(last)),
+                               stream_ptr()), "syn_add_site_f64")
+    return out
+
+
+def kron_site(A, B):
+    """Per-(in,out) Kronecker product of the bond matrices (MPO:140-152)."""
+    require_cuda_f64(A, B)
+    A, B = A.contiguous(), B.contiguous()
+    la, ra, lb, rb = A.shape[0], A.shape[-1], B.shape[0], B.shape[-1]
+    phys = 1
+    for d in A.shape[1:-1]:
+        phys *= d
+    out = torch.empty((la * lb,) + tuple(A.shape[1:-1]) + (ra * rb,), dtype=torch.float64, device=A.device)
+    check(lib.syn_kron_site_f64(ptr(A), ptr(B), ptr(out), _i32(la), _i32(ra), _i32(lb), _i32(rb), _i32(phys), stream_ptr()), "syn_kron_site_f64")
+    return out
+
+
+def sumsq(x):
+    require_cuda_f64(x)
+    x = x.contiguous()
+    out = torch.empty((1,), dtype=torch.float64, device=x.device)
+    check(lib.syn_sumsq_f64(ptr(x), _i64(x.numel()), ptr(out), stream_ptr()), "syn_sumsq_f64")
+    return out
+
+
+def scale_rsqrt_(x, ss):
+    require_cuda_f64(x, ss)
+    assert x.is_contiguous()
+    check(lib.syn_scale_rsqrt_f64(ptr(x), _i64(x.numel()), ptr(ss), stream_ptr()), "syn_scale_rsqrt_f64")
+    return x
