@@ -1,0 +1,351 @@
+"""Host-side sweep algorithms of the matrix-product hot path, on lists of CUDA float64 cores.
+
+Pure orchestration: every arithmetic step is a call into libsyngular_b200.so through `syngular_b200.ops`
+(strided DMMA GEMM, Householder qrt, one-sided Jacobi, block assembly).  PyTorch only provides device buffers
+and views.  Citations are to the reference (MPS = tensor/matrix_product_state.py, MPO = tensor/matrix_product_operator.py).
+"""
+import numpy as np
+import torch
+
+from syngular_b200 import ops
+
+F64 = torch.float64
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise ops._lib.SynError("syngular_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def as_core(x):
+    """numpy array / torch tensor -> contiguous CUDA float64 tensor (host arrays are uploaded)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if np.iscomplexobj(a):
+            if np.max(np.abs(a.imag)) > 0:
+                raise NotImplementedError("complex cores are not supported by the FP64 library yet")
+            a = a.real
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    if t.dtype != F64:
+        t = t.to(F64)
+    if not t.is_cuda:
+        t = t.to(device())
+    return t.contiguous()
+
+
+def empty(*shape):
+    return torch.empty(shape, dtype=F64, device=device())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# site contractions (K1 / K2 of SURVEY section 2.4) as single strided GEMMs
+# ---------------------------------------------------------------------------------------------------------
+def site_mpo_mps(X, W):
+    """C[(a,l), o, (b,r)] = sum_i X[a,i,b] W[l,i,o,r]   (MPO:184-190; MPS bond major, MPO bond minor)."""
+    a, i, b = X.shape
+    l, i2, o, r = W.shape
+    assert i == i2, (X.shape, W.shape)
+    out = empty(a * l, o, b * r)
+    ops.gemm(X, W, out, M=b, N=o * r, K=i,
+             a_m=1, a_k=b, b_k=o * r, b_n=1,
+             c_m=r, c_n=(b * r, 1, r),
+             batch=a * l, a_b=(i * b, 0, l), b_b=(0, i * o * r, l), c_b=o * b * r)
+    return out
+
+
+def site_mpo_mpo(A, B):
+    """C[(lA,lB), iA, oB, (rA,rB)] = sum_x A[lA,iA,x,rA] B[lB,x,oB,rB]   (MPO:280-287; A acts first)."""
+    la, ia, xa, ra = A.shape
+    lb, xb, ob, rb = B.shape
+    assert xa == xb, (A.shape, B.shape)
+    out = empty(la * lb, ia, ob, ra * rb)
+    ops.gemm(A, B, out, M=ia * ra, N=ob * rb, K=xa,
+             a_m=(xa * ra, 1, ra), a_k=ra, b_k=ob * rb, b_n=1,
+             c_m=(ob * ra * rb, rb, ra), c_n=(ra * rb, 1, rb),
+             batch=la * lb, a_b=(ia * xa * ra, 0, lb), b_b=(0, xb * ob * rb, lb), c_b=ia * ob * ra * rb)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference-semantic sweeps
+# ---------------------------------------------------------------------------------------------------------
+def round_qr(sites, dim):
+    """Strict `>>` sweep (MPS:432-468, MPO:544-580): QR-truncation left to right, no canonicalisation.
+    Natural clamp: kept width = min(dim, rows)."""
+    out = list(sites)
+    for k in range(len(out) - 1):
+        cur, nxt = out[k], out[k + 1]
+        L = cur.reshape(-1, cur.shape[-1])
+        Q, S = ops.qrt(L, dim)
+        kept = Q.shape[1]
+        Wn = ops.matmul(S, nxt.reshape(nxt.shape[0], -1))
+        out[k] = Q.reshape(tuple(cur.shape[:-1]) + (kept,))
+        out[k + 1] = Wn.reshape((kept,) + tuple(nxt.shape[1:]))
+    return out
+
+
+def left_orthonormalize(sites):
+    """MPS:554-566 / MPO:673-694 (reduced QR, left to right)."""
+    out = list(sites)
+    for k in range(len(out) - 1):
+        cur, nxt = out[k], out[k + 1]
+        L = cur.reshape(-1, cur.shape[-1])
+        Q, S = ops.qrt(L, min(L.shape))
+        kept = Q.shape[1]
+        Wn = ops.matmul(S, nxt.reshape(nxt.shape[0], -1))
+        out[k] = Q.reshape(tuple(cur.shape[:-1]) + (kept,))
+        out[k + 1] = Wn.reshape((kept,) + tuple(nxt.shape[1:]))
+    return out
+
+
+def right_orthonormalize(sites):
+    """MPS:568-580 / MPO:696-719: QR of R^T right to left; the transposed factor is written straight into the core."""
+    out = list(sites)
+    for k in range(len(out) - 1, 0, -1):
+        cur, prv = out[k], out[k - 1]
+        R = cur.reshape(cur.shape[0], -1)                  # (l, d*r)
+        kept = min(R.shape)
+        core = empty(kept, R.shape[1])
+        _, S = ops.qrt(R.t(), kept, Q=core.t())            # Q = core^T ; S = Q^T R^T  (kept x l)
+        Lp = prv.reshape(-1, prv.shape[-1])
+        Wp = ops.matmul(Lp, S.t())
+        out[k] = core.reshape((kept,) + tuple(cur.shape[1:]))
+        out[k - 1] = Wp.reshape(tuple(prv.shape[:-1]) + (kept,))
+    return out
+
+
+def overlap(A, B):
+    """`A | B` (MPS:116-129): bilinear transfer-matrix contraction, two GEMMs per site.  Returns a (1,1) device tensor."""
+    E = torch.ones((1, 1), dtype=F64, device=A[0].device)
+    for a, b in zip(A, B):
+        la, lb = a.shape[0], b.shape[0]
+        T = ops.matmul(E.t(), a.reshape(la, -1))           # (lb, d*ra')
+        ra, rb = a.shape[-1], b.shape[-1]
+        E = ops.matmul(T.reshape(-1, ra).t(), b.reshape(-1, rb))   # (ra', rb')
+    return E
+
+
+def to_dense(sites):
+    """Dense tensor by one left-to-right chain of GEMMs (the reference loops over every index: MPS:265-273, MPO:405-416)."""
+    T = sites[0].reshape(-1, sites[0].shape[-1])
+    dims = list(sites[0].shape[1:-1])
+    for c in sites[1:]:
+        T = ops.matmul(T, c.reshape(c.shape[0], -1)).reshape(-1, c.shape[-1])
+        dims += list(c.shape[1:-1])
+    T = T.reshape(dims)
+    if sites[0].dim() == 4:
+        n = len(sites)
+        T = T.permute(list(range(0, 2 * n, 2)) + list(range(1, 2 * n, 2)))
+    return T
+
+
+def retrieve(sites, idx_in, idx_out=None):
+    """One amplitude = product of the sliced bond matrices (MPS:546-551, MPO:663-670); (1,1) device tensor."""
+    v = None
+    for k, c in enumerate(sites):
+        m = c[:, int(idx_in[k]), :] if idx_out is None else c[:, int(idx_in[k]), int(idx_out[k]), :]
+        v = m if v is None else ops.matmul(v, m)
+    return v
+
+
+def decompose_left(T, shapes):
+    """TT decomposition by the qrt step (MPS:298-319, MPO:430-450)."""
+    cores, l, n = [], 1, len(shapes)
+    T = T.reshape(-1)
+    for k in range(n - 1):
+        phys = int(np.prod(shapes[k][1:-1]))
+        L = T.reshape(l * phys, -1)
+        Q, S = ops.qrt(L, int(shapes[k][-1]))
+        kept = Q.shape[1]
+        cores.append(Q.reshape((l,) + tuple(shapes[k][1:-1]) + (kept,)))
+        T, l = S, kept
+    cores.append(T.reshape((l,) + tuple(shapes[n - 1][1:-1]) + (1,)))
+    return cores
+
+
+def decompose_right(T, shapes):
+    """MPS-only right-to-left variant (MPS:324-347)."""
+    n = len(shapes)
+    cores, r = [None] * n, 1
+    T = T.reshape(-1)
+    for k in range(n - 1, 0, -1):
+        phys = int(np.prod(shapes[k][1:-1]))
+        Rm = T.reshape(-1, phys * r)                        # (rest, d*r)
+        rest = Rm.shape[0]
+        kept = min(int(shapes[k][0]), phys * r)
+        core = empty(kept, phys * r)
+        Snext = empty(rest, kept)                           # S^T, so the remainder stays (rest, kept) row-major
+        ops.qrt(Rm.t(), kept, Q=core.t(), S=Snext.t())
+        cores[k] = core.reshape((kept,) + tuple(shapes[k][1:-1]) + (r,))
+        T, r = Snext, kept
+    cores[0] = T.reshape((1,) + tuple(shapes[0][1:-1]) + (r,))
+    return cores
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused MPO x MPS application: the product core (a*l, o, b*r) is never materialised
+# ---------------------------------------------------------------------------------------------------------
+def contract_carry(T, X, W):
+    """M[s, o, (b,r)] = sum_{a,l,i} T[s,l,a] X[a,i,b] W[l,i,o,r].
+    `T` is the carry of the sweep, stored (s, l, a) -- MPO bond major -- so that both GEMMs read unit-stride operands;
+    the output columns are in the reference's product order (b major, r minor), which the QR truncation depends on."""
+    s, l, a = T.shape
+    a2, i, b = X.shape
+    l2, i2, o, r = W.shape
+    assert a == a2 and l == l2 and i == i2, (T.shape, X.shape, W.shape)
+    T1 = empty(s, l, i, b)
+    # T1[s,l,(i,b)] = sum_a T[s,l,a] X[a,(i,b)]      batch over l
+    ops.gemm(T, X, T1, M=s, N=i * b, K=a, a_m=l * a, a_k=1, b_k=i * b, b_n=1, c_m=l * i * b, c_n=1,
+             batch=l, a_b=a, b_b=0, c_b=i * b)
+    M = empty(s, o, b * r)
+    # M[(s,b),(o,r)] = sum_{(l,i)} T1[s,(l,i),b] W[(l,i),(o,r)]
+    ops.gemm(T1, W, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
+             c_m=(o * b * r, r, b), c_n=(b * r, 1, r))
+    return M
+
+
+def _carry_from(Ut_or_Q, L, kept, b, r, transposed_basis):
+    """T_next[kept, r, b] = basis^T L with the columns of L (b major) re-ordered to (r, b) on the fly."""
+    rows = L.shape[0]
+    Tn = empty(kept, r, b)
+    if transposed_basis:     # basis given as (kept, rows) rows
+        ops.gemm(Ut_or_Q, L, Tn, M=kept, N=b * r, K=rows, a_m=Ut_or_Q.stride(0), a_k=Ut_or_Q.stride(1), b_k=L.stride(0), b_n=L.stride(1),
+                 c_m=r * b, c_n=(1, b, r))
+    else:                    # basis given as (rows, kept) columns
+        ops.gemm(Ut_or_Q, L, Tn, M=kept, N=b * r, K=rows, a_m=Ut_or_Q.stride(1), a_k=Ut_or_Q.stride(0), b_k=L.stride(0), b_n=L.stride(1),
+                 c_m=r * b, c_n=(1, b, r))
+    return Tn
+
+
+def apply_round_qr(X, W, dim):
+    """`W @ X` followed by `>> dim` with the reference's semantics (MPO:181-192 + MPS:432-468), fused: identical numbers
+    to site_mpo_mps + round_qr (same projections, same column order), without the D = chi*chi_W product cores."""
+    n = len(X)
+    out = []
+    T = torch.ones((1, 1, 1), dtype=F64, device=X[0].device)
+    for k in range(n - 1):
+        M = contract_carry(T, X[k], W[k])
+        s, o, _ = M.shape
+        b, r = X[k].shape[2], W[k].shape[3]
+        L = M.reshape(s * o, b * r)
+        Q, _ = ops.qrt(L, dim, want_S=False)
+        kept = Q.shape[1]
+        out.append(Q.reshape(s, o, kept))
+        T = _carry_from(Q, L, kept, b, r, transposed_basis=False)
+    M = contract_carry(T, X[-1], W[-1])
+    out.append(M)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SVD rounding (north_star; absent from the reference -- oracle/svd_numpy.py)
+# ---------------------------------------------------------------------------------------------------------
+class Truncation:
+    """Per-bond record of an SVD rounding sweep (device tensors; .host() synchronises)."""
+
+    def __init__(self):
+        self.sigma, self.keep, self.discarded = [], [], []
+
+    def host(self):
+        return ([s.detach().cpu().numpy() for s in self.sigma], list(self.keep), [float(d) for d in self.discarded])
+
+
+def _svd_basis(M, chi_max, cutoff, trunc):
+    """Left singular basis of the unfolding M (m x c): returns (core2d (m x keep) contiguous, keep)."""
+    m, c = M.shape
+    if m <= c:
+        G = ops.qr_r(M.t())                                 # R factor of M^T (m x m); rows rotate to sigma_i u_i^T
+        ops.jacobi_rows(G)
+        Ut, sigma, info, winfo = ops.jacobi_finalize(G, chi_max, cutoff, rank_tol=1e-14)
+        keep = int(info[0].item())
+        core2d = ops.copy_strided(Ut[:keep].t())
+    else:
+        Gt = empty(c, c)
+        Q1, _ = ops.qrt(M, c, S=Gt.t())                     # Gt = R1^T ; rows rotate to sigma_i u1_i^T
+        ops.jacobi_rows(Gt)
+        Ut, sigma, info, winfo = ops.jacobi_finalize(Gt, chi_max, cutoff, rank_tol=1e-14)
+        keep = int(info[0].item())
+        core2d = ops.matmul(Q1, Ut[:keep].t())
+    trunc.sigma.append(sigma)
+    trunc.keep.append(keep)
+    trunc.discarded.append(winfo[0].item())
+    return core2d, keep
+
+
+def round_svd(sites, chi_max, cutoff=0.0, canonicalize=True):
+    """Textbook rounding: right-to-left QR canonicalisation, then left-to-right truncated SVD with S V^T absorbed into the
+    next core (oracle/svd_numpy.round_svd).  The SVD is Householder reduction + one-sided Jacobi on the device; the cutoff and
+    chi_max selection happen in the finalize kernel, the host only reads the kept rank back."""
+    out = right_orthonormalize(sites) if canonicalize else list(sites)
+    trunc = Truncation()
+    for k in range(len(out) - 1):
+        cur, nxt = out[k], out[k + 1]
+        M = cur.reshape(-1, cur.shape[-1])
+        core2d, keep = _svd_basis(M, chi_max, cutoff, trunc)
+        carry = ops.matmul(core2d.t(), M)                   # U^T M = S V^T  (keep x c)
+        Wn = ops.matmul(carry, nxt.reshape(nxt.shape[0], -1))
+        out[k] = core2d.reshape(tuple(cur.shape[:-1]) + (keep,))
+        out[k + 1] = Wn.reshape((keep,) + tuple(nxt.shape[1:]))
+    return out, trunc
+
+
+def right_environments(X, W):
+    """E[k] = Gram matrix of the product chain to the right of bond k (D_k x D_k, index (b,r) b-major), k = 1..n-1,
+    without forming product cores: four strided GEMMs per site (finished form of MPO:193-260)."""
+    n = len(X)
+    E = [None] * (n + 1)
+    E[n] = torch.ones((1, 1), dtype=F64, device=X[0].device)
+    for k in range(n - 1, 0, -1):
+        Xk, Wk, En = X[k], W[k], E[k + 1]
+        a, i, b = Xk.shape
+        l, _, o, r = Wk.shape
+        D = b * r
+        # P1[(a,i),(r,y)] = sum_b X[(a,i),b] E[b,(r,y)]
+        P1 = empty(a, i, r, D)
+        ops.gemm(Xk, En, P1, M=a * i, N=r * D, K=b, a_m=b, a_k=1, b_k=r * D, b_n=1, c_m=r * D, c_n=1)
+        # P2[a,(l,o),y] = sum_{(i,r)} W[l,i,o,r] P1[a,(i,r),y]       batch over a
+        P2 = empty(a, l, o, D)
+        ops.gemm(Wk, P1, P2, M=l * o, N=D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=1, c_m=D, c_n=1,
+                 batch=a, a_b=0, b_b=i * r * D, c_b=l * o * D)
+        # Z[(a,l), l', i', b'] = sum_{(o,r')} P2[(a,l), o, b', r'] W[l', i', o, r']      batch over (a,l)
+        Z = empty(a * l, l, i, b)
+        ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=r, a_k=(b * r, 1, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
+                 batch=a * l, a_b=o * D, b_b=0, c_b=l * i * b)
+        # E[(a,l),(a',l')] = sum_{(i',b')} Z[(a,l), l', (i',b')] X[a',(i',b')]           batch over l'
+        Ek = empty(a * l, a * l)
+        ops.gemm(Z, Xk, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=l,
+                 batch=l, a_b=i * b, b_b=0, c_b=1)
+        E[k] = Ek
+    return E
+
+
+def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=1e-7):
+    """`W @ X` + optimal (SVD) rounding by the density-matrix algorithm: right environments, then a left-to-right sweep that
+    diagonalises M E M^T (one-sided Jacobi) -- mathematically the truncation of round_svd(site_mpo_mps(...)) but every matrix
+    stays <= (chi d) x D.  Eigenvalues are squared singular values, so values below ~1e-8 sigma_0 are noise: rank_tol."""
+    n = len(X)
+    E = right_environments(X, W)
+    trunc = Truncation()
+    out = []
+    T = torch.ones((1, 1, 1), dtype=F64, device=X[0].device)
+    for k in range(n - 1):
+        M = contract_carry(T, X[k], W[k])
+        s, o, D = M.shape
+        b, r = X[k].shape[2], W[k].shape[3]
+        M2 = M.reshape(s * o, D)
+        ME = ops.matmul(M2, E[k + 1])
+        A = ops.matmul(ME, M2.t())
+        nA = s * o
+        if nA > 1024:
+            raise NotImplementedError("density-matrix rounding needs chi*d <= 1024 (got %d)" % nA)
+        ops.jacobi_rows(A)
+        Ut, sigma, info, winfo = ops.jacobi_finalize(A, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True)
+        keep = int(info[0].item())
+        trunc.sigma.append(sigma); trunc.keep.append(keep); trunc.discarded.append(winfo[0].item())
+        out.append(ops.copy_strided(Ut[:keep].t()).reshape(s, o, keep))
+        T = _carry_from(Ut[:keep], M2, keep, b, r, transposed_basis=True)
+    out.append(contract_carry(T, X[-1], W[-1]))
+    return out, trunc

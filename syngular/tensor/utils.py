@@ -1,0 +1,30 @@
+"""`syn.mul` -- functional alias of `@` / `|` (reference: tensor/utils.py:8-99)."""
+from syngular.tensor import _sweeps as sw
+from syngular.tensor.matrix_product_operator import MatrixProductOperator, _apply_to_state
+from syngular.tensor.matrix_product_state import MatrixProductState
+
+
+def mul(op1, op2, mode="standard"):
+    n, m = op1.sites_number, op2.sites_number
+    min_bond = min(min(op1.bond_shape), min(op2.bond_shape))                 # utils.py:12
+    if n != m:
+        raise Exception("both operator do not have the same number of sites")
+    if mode == "standard":
+        if isinstance(op1, MatrixProductState) and isinstance(op2, MatrixProductOperator):
+            if not op1.decomposed or not op2.decomposed:
+                raise Exception("Operators and States must be decomposed")
+            return _apply_to_state(op2, op1, min_bond)                       # utils.py:30-43
+        if isinstance(op1, MatrixProductOperator) and isinstance(op2, MatrixProductState):
+            if not op1.decomposed or not op2.decomposed:
+                raise Exception("Operators and States must be decomposed")
+            return _apply_to_state(op1, op2, min_bond)                       # utils.py:44-57
+        if isinstance(op1, MatrixProductState) and isinstance(op2, MatrixProductState):
+            return op1 | op2                                                 # utils.py:58-59
+        if isinstance(op1, MatrixProductOperator) and isinstance(op2, MatrixProductOperator):
+            # utils.py:60-71: op2's OUTPUT is contracted with op1's INPUT (the reverse of `@`), op2's bond major
+            sites = [sw.site_mpo_mpo(b, a) for a, b in zip(op1.sites, op2.sites)]
+            return MatrixProductOperator.from_sites(sites) >> min_bond
+        raise Exception("`syn.mul` should be provided MatrixProductState or MatrixProductOperator objects only")
+    if mode in ("variational", "optimized", "fitup"):
+        return None                                                          # empty stubs in the reference (utils.py:76-99)
+    return None
