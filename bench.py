@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: MPO x MPS apply + SVD-round sweeps/s on BASELINE.json configs[1]
+(single chain N=64, d=2, chi=256, MPO chi_W=16, rounded back to chi=256, FP64), one chain per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full sweep of the hot path over one synthetic chain: apply the MPO and round back to chi=256 with
+optimal (SVD) truncation.  Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+
+  value     device-resident inputs, CUDA-event timed, max over ranks (one independent chain per rank: "replicas only")
+  e2e       the same sweep through the public API `syn.mul(W, X, mode="optimized", bond=256)` with HOST (pinned) cores:
+            H2D of every input core and D2H of every output core inside the timed region
+  roofline  the strided DMMA GEMM (dominant kernel): algorithmic FLOPs of all its launches in one sweep / their summed
+            CUDA-event durations, against the cuBLAS DGEMM rate measured in the same process (MEASURED_PEAKS.json
+            has no FP64 entry)
+  cpu_baseline / --impl reference
+            the oracle's textbook apply + right-QR + left-SVD rounding (numpy/LAPACK, all host threads) on a bounded
+            sample of plateau sites, scaled to a sweep by the textbook flop model
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SITES, D_PHYS, CHI, CHI_W = 64, 2, 256, 16
+METRIC = "mpo_mps_apply_svd_round_sweeps_per_s"
+UNIT = "sweeps/s"
+WORKLOAD = "C2 single chain: N=64 d=2 random MPS chi=256 x random MPO chi_W=16, apply + SVD-round to chi=256, FP64"
+
+
+def capped_bonds(n, d_eff, chi):
+    return [1] + [int(min(chi, d_eff ** min(k, n - k, 40))) for k in range(1, n)] + [1]
+
+
+def make_chain(seed, n=N_SITES, d=D_PHYS, chi=CHI, chiw=CHI_W):
+    """SURVEY 8(d) C2 inputs: cores ~ N(0, 1/(l d)) drawn on the host so CPU and GPU see identical bits."""
+    rng = np.random.default_rng(seed)
+    bx = capped_bonds(n, d, chi)
+    bw = capped_bonds(n, d * d, chiw)
+    X = [rng.normal(size=(bx[k], d, bx[k + 1])) / np.sqrt(bx[k] * d) for k in range(n)]
+    W = [rng.normal(size=(bw[k], d, d, bw[k + 1])) / np.sqrt(bw[k] * d) for k in range(n)]
+    return X, W
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# flop models: only what the executed algorithm needs
+# ---------------------------------------------------------------------------------------------------------------------
+def textbook_site_flops(a, l, i, o, b, r, s_left):
+    """Flops of the textbook algorithm at one site: materialise, absorb the right carry, QR of the right unfolding (factor +
+    form Q), absorb the left carry, SVD of the left unfolding (dominant terms; LAPACK conventions)."""
+    Dl, Dr = a * l, b * r
+    mat = 2.0 * a * l * i * o * b * r
+    absorb_r = 2.0 * (Dl * o) * Dr * Dr
+    m, n = o * Dr, Dl
+    k = min(m, n)
+    qr = 2.0 * (2.0 * m * n * k - (2.0 / 3.0) * k ** 3) if m >= n else 2.0 * (2.0 * n * m * k - (2.0 / 3.0) * k ** 3)
+    absorb_l = 2.0 * s_left * k * (o * Dr)
+    rows = s_left * o
+    p, q = max(rows, Dr), min(rows, Dr)
+    svd = 4.0 * p * q * q + 22.0 * q ** 3               # thin SVD with both factors (Golub & Van Loan)
+    return mat + absorb_r + qr + absorb_l + svd
+
+
+def chain_dims(X, W, chi):
+    dims, s = [], 1
+    for x, w in zip(X, W):
+        a, i, b = x.shape
+        l, _, o, r = w.shape
+        dims.append((a, l, i, o, b, r, s))
+        s = min(chi, s * o, b * r)
+    return dims
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: oracle textbook algorithm on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_textbook_sample(X, W, chi, sites):
+    """Run the textbook steps at FULL size on `sites` and return (seconds, flops of the sample by the model above).
+    The carries entering a site are replaced by identity-like matrices of the right shape: every step is a dense
+    BLAS/LAPACK call whose cost does not depend on the data."""
+    from oracle import ref_numpy as R
+    dims = chain_dims(X, W, chi)
+    t0 = time.perf_counter()
+    flops = 0.0
+    for k in sites:
+        a, l, i, o, b, r, s = dims[k]
+        C = R.site_mpo_mps(X[k], W[k])                                  # K1: (Dl, o, Dr)
+        Dl, Dr = C.shape[0], C.shape[2]
+        U = np.eye(Dr)
+        C2 = (C.reshape(Dl * o, Dr) @ U.T).reshape(Dl, o * Dr)          # absorb the carry coming from the right
+        V, Un = np.linalg.qr(C2.T)                                      # right-QR step (ref_numpy.right_orthonormalize)
+        carry = np.eye(s, V.shape[1])
+        M = (carry @ V.T).reshape(s * o, Dr)                            # absorb the carry coming from the left
+        Uu, S, Vt = np.linalg.svd(M, full_matrices=False)               # left-SVD step (svd_numpy.round_svd)
+        keep = min(chi, len(S))
+        _ = S[:keep, None] * Vt[:keep]
+        flops += textbook_site_flops(a, l, i, o, b, r, s)
+    return time.perf_counter() - t0, flops
+
+
+def cpu_sweeps_per_s(X, W, chi, sites, repeats=1):
+    dims = chain_dims(X, W, chi)
+    total = sum(textbook_site_flops(*d) for d in dims)
+    best, fl = None, None
+    for _ in range(repeats):
+        sec, fl = cpu_textbook_sample(X, W, chi, sites)
+        best = sec if best is None else min(best, sec)
+    est = best * total / fl
+    return 1.0 / est, best, total, fl
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, W = make_chain(2)
+    sites = [31]                                         # one plateau site per step (a few seconds of LAPACK)
+    for _ in range(args.warmup):
+        cpu_textbook_sample(X, W, CHI, sites)
+    dims = chain_dims(X, W, CHI)
+    total = sum(textbook_site_flops(*d) for d in dims)
+    secs, fl = [], None
+    for _ in range(args.steps):
+        s, fl = cpu_textbook_sample(X, W, CHI, sites)
+        secs.append(s)
+    per_sweep = float(np.mean(secs)) * total / fl
+    value = 1.0 / per_sweep
+    sample = ("oracle textbook steps (materialise product core, QR of its right unfolding + carry GEMM, SVD of the left unfolding "
+              "+ carry GEMM; numpy/LAPACK) at full size on plateau site 31 per step, scaled to the 64-site sweep by the "
+              "textbook flop model (x%.1f)" % (total / fl))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_sweep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "algorithm": "textbook right-QR + left-SVD rounding of the materialised product (oracle/svd_numpy.py)",
+                   "note": "the reference has no SVD rounding and cannot run d=2 chains with dim>2 (SURVEY fact 4): this is the oracle port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import syngular as syn
+    from syngular.tensor import MatrixProductOperator as MPO, MatrixProductState as MPS, _sweeps as sw
+    from syngular_b200 import ops
+
+    dev = torch.device("cuda", local)
+    Xh, Wh = make_chain(2 + rank)
+    Xp = [torch.from_numpy(x).pin_memory() for x in Xh]
+    Wp = [torch.from_numpy(w).pin_memory() for w in Wh]
+    Xd = [t.to(dev) for t in Xp]
+    Wd = [t.to(dev) for t in Wp]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return sw.apply_round_dm(Xd, Wd, CHI)
+
+    def step_e2e(out_host):
+        X = MPS.from_sites(Xp)                          # H2D from pinned host memory
+        Wm = MPO.from_sites(Wp)
+        Y = syn.mul(Wm, X, mode="optimized", bond=CHI)
+        for k, s in enumerate(Y.sites):                 # D2H of the result cores
+            out_host[k][: s.numel()].copy_(s.reshape(-1), non_blocking=True)
+        return Y
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # warm-up (also sizes every cached workspace)
+    for _ in range(max(args.warmup, 3)):
+        out, trunc = step_device()
+    # parity guard inside the bench: the state must be left-canonical and normalisation-consistent
+    L0 = out[20].reshape(-1, out[20].shape[-1])
+    gram_err = float((ops.matmul(L0.t(), L0) - torch.eye(L0.shape[1], dtype=torch.float64, device=dev)).abs().max().item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.lib.syn_launch_count()
+    ms = timed(step_device, args.steps)
+    launches = (ops.lib.syn_launch_count() - launches0) / float(args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.steps / (ms * 1e-3)
+
+    # end to end through the public API with host buffers
+    out_host = [torch.empty(CHI * D_PHYS * CHI, dtype=torch.float64).pin_memory() for _ in range(N_SITES)]
+    step_e2e(out_host)
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e = timed(lambda: step_e2e(out_host), e2e_steps)
+    e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
+    h2d = int(sum(t.numel() for t in Xp + Wp) * 8)
+    d2h = int(sum(int(np.prod(s.shape)) for s in out) * 8)
+
+    # secondary: the reference-semantic (QR truncation) sweep on the same chain
+    def step_qr():
+        return sw.apply_round_qr(Xd, Wd, CHI)
+    for _ in range(2):
+        step_qr()
+    ms_qr = timed(step_qr, max(2, min(args.steps, 5)))
+    qr_value = world * max(2, min(args.steps, 5)) / (ms_qr * 1e-3)
+
+    line = None
+    if rank == 0:
+        # roofline of the dominant kernel: profile one sweep with per-launch CUDA events on the launching stream
+        ops.GEMM_PROFILE = []
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); step_device(); t1.record()
+        torch.cuda.synchronize()
+        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        g_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in prof)
+        g_fl = sum(f for _, _, f, _, _ in prof)
+        g_by = sum(by for _, _, _, by, _ in prof)
+        sweep_ms = t0.elapsed_time(t1)
+        # FP64 peak measured here: cuBLAS DGEMM 8192^3 (burst, best of 5)
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        best = 1e30
+        for _ in range(6):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(); torch.matmul(a, b); p1.record(); torch.cuda.synchronize()
+            best = min(best, p0.elapsed_time(p1))
+        del a, b
+        peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+        achieved = g_fl / (g_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this process (MEASURED_PEAKS.json has no FP64 entry); DMMA pipe microbench: 37.1",
+                    "launches_per_sweep": len(prof), "flops_per_sweep": g_fl, "algorithmic_bytes_per_sweep": g_by,
+                    "kernel_ms_per_sweep": g_ms, "share_of_step": g_ms / sweep_ms}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, sec, total, fl = cpu_sweeps_per_s(Xh, Wh, CHI, [31, 32])
+            cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                   "sample": "oracle textbook apply + right-QR + left-SVD steps at full size on plateau sites 31-32 (%.1f s), scaled to the "
+                             "64-site sweep by the textbook flop model (x%.1f)" % (sec, total / fl)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rounding": "SVD truncation by the density-matrix algorithm (Gram environments + one-sided Jacobi)",
+                       "l2": "inputs larger than L2: 63 right environments of up to 134 MB (8.5 GB) are streamed every sweep",
+                       "multi_gpu": "replicas only: one independent chain per rank, no collective on the data path",
+                       "left_gram_err_site20": gram_err},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "syn.mul(W, X, mode='optimized', bond=256) on pinned host cores, result cores copied back"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "extra": {"qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),
+                      "qr_round_note": "reference-semantic `>>` (QR truncation, fused apply+round) on the same chain"},
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,7 @@ extern "C" {
 int         syn_version(void);
 const char* syn_last_error(void);
 int         syn_device_sm_count(void);
+long long   syn_launch_count(void);      /* kernels launched by the library so far (this process) */
 
 /* ---- strided tensor-contraction GEMM (FP64 DMMA) ------------------------------------------------------ */
 /* C[m,n] = alpha * sum_k A[m,k] B[k,n] + beta * C[m,n], batched.  Every logical index may be split in two
@@ -49,6 +50,51 @@ typedef struct {
 } syn_gemm_desc_t;
 
 int syn_gemm_f64(const syn_gemm_desc_t* desc, const double* A, const double* B, double* C, void* stream);
+
+/* ---- Householder QR truncation step (batched, arbitrary row/column/batch strides) ------------------------- */
+/* qrt(A (m x n), q):  Q (m x qk) = orthonormal basis of span(A[:, :q]) (completed with further orthonormal columns when
+ * q > n), S = Q^T A (qk x n), qk = min(q, m) written to *qk_out.  S may be NULL.
+ * Replaces  Q, R = np.linalg.qr(L, mode="complete"); Q[:, :q]; R[:q, :]   -- the `>>` / decompose truncation step
+ *   (MPS:307-311, 332-336, 443-446; MPO:436-440, 555-558; also the non-strict sweeps MPS:378-381,410-413, MPO:488-491,520-523)
+ * and the reduced QRs np.linalg.qr(L), np.linalg.qr(R.T) of the canonicalisation sweeps with q = min(m, n)
+ *   (MPS:560, 574; MPO:680, 703).  Pass a transposed view (row stride 1) to factor R^T or to write Q^T in place.
+ * Workspace: syn_qrt_workspace_f64(m, n, q, batch) bytes, 16-byte aligned, owned by the caller. */
+size_t syn_qrt_workspace_f64(int m, int n, int q, int batch);
+int syn_qrt_f64(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int m, int n, int q, int batch,
+                double* Q, int64_t q_rs, int64_t q_cs, int64_t q_bs,
+                double* S, int64_t s_rs, int64_t s_cs, int64_t s_bs,
+                void* ws, size_t ws_bytes, int* qk_out, void* stream);
+/* R factor only (n x n upper triangular) of a tall A (m >= n); reduces an unfolding before the Jacobi SVD. */
+int syn_qr_r_f64(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int m, int n, int batch,
+                 double* R, int64_t r_rs, int64_t r_cs, int64_t r_bs, void* ws, size_t ws_bytes, void* stream);
+/* dst (contiguous m x n per batch) = strided src; a tiled transpose when src is a transposed view
+ * (np.reshape / .T of cores: MPS:596-622, MPO:735-769). */
+int syn_copy_strided_f64(const double* src, int64_t s_rs, int64_t s_cs, int64_t s_bs, double* dst, int64_t d_bs,
+                         int m, int n, int batch, void* stream);
+
+/* ---- one-sided Jacobi SVD (north_star "truncated SVD of each bond matrix"; no live counterpart in the reference:
+ *      its only SVD/eigh are dead code -- trash/mpo.py:59-190, experimental/layers.py:241-325, MPO:228) ------------- */
+/* In place: rows of G (n x n, row-major ld, n <= 1024) are rotated until mutually orthogonal: row_i -> sigma_i u_i^T. */
+size_t syn_jacobi_ctrl_bytes(int batch, int max_sweeps);
+int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes,
+                        int max_sweeps, double tol, void* stream);
+/* Sort sigma descending, normalise rows into Ut, apply chi_max / relative cutoff on the device.
+ * info[2*b] = kept rank, winfo[2*b] = discarded weight sum_{k>=kept} sigma_k^2, winfo[2*b+1] = sigma_0.
+ * sqrt_mode = 1 when G was a Gram matrix M E M^T (rows are lambda_i u_i^T, sigma_i = sqrt(lambda_i)). */
+int syn_jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs,
+                            double* sigma, int64_t sbs, int* info, double* winfo, int chi_max, double cutoff,
+                            double rank_tol, int sqrt_mode, void* stream);
+
+/* ---- block assembly and elementwise kernels ---------------------------------------------------------------- */
+/* `A + B` site: direct sum of the bond spaces, self's block first; cores as (l, phys, r) with the physical legs flattened
+ * (np.block / scipy.linalg.block_diag loops of MPS:82-96 and MPO:90-106). */
+int syn_add_site_f64(const double* A, const double* B, double* out, int la, int ra, int lb, int rb, int phys,
+                     int first, int last, void* stream);
+/* `A * B` site: out[(la,lb), p, (ra,rb)] = A[la,p,ra] * B[lb,p,rb]  (np.kron loop of MPO:140-152). */
+int syn_kron_site_f64(const double* A, const double* B, double* out, int la, int ra, int lb, int rb, int phys, void* stream);
+/* out[0] = sum x_i^2 ; x *= 1/sqrt(sumsq[0])   (normalize: np.linalg.norm + in-place divide, MPS:252-256) */
+int syn_sumsq_f64(const double* x, int64_t n, double* out, void* stream);
+int syn_scale_rsqrt_f64(double* x, int64_t n, const double* sumsq, void* stream);
 
 #ifdef __cplusplus
 }

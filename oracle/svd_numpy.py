@@ -90,3 +90,48 @@ def apply_round_density_matrix(X, W, chi_max, cutoff=0.0):
     C = prod[n - 1]
     out.append(np.tensordot(carry, C, axes=(1, 0)))
     return out, spectra, discarded
+
+
+def apply_round_density_matrix_structured(X, W, chi_max, cutoff=0.0):
+    """Same algorithm as apply_round_density_matrix, with every contraction done through the (X, W) structure so that no
+    product core (D x d x D) is formed -- the exact sequence of contractions the CUDA fast path executes, in numpy/BLAS.
+    Used by bench.py as the like-for-like CPU timing of the algorithm the GPU runs."""
+    n = len(X)
+    E = [None] * (n + 1)
+    E[n] = np.ones((1, 1))
+    for k in range(n - 1, 0, -1):
+        Xk, Wk = X[k], W[k]
+        a, i, b = Xk.shape
+        l, _, o, r = Wk.shape
+        En = E[k + 1].reshape(b, r, b * r)
+        P1 = np.tensordot(Xk, En, axes=(2, 0))                         # (a, i, r, y)
+        P2 = np.tensordot(Wk, P1, axes=([1, 3], [1, 2]))               # (l, o, a, y)
+        P2 = P2.reshape(l, o, a, b, r)
+        Z = np.tensordot(P2, Wk, axes=([1, 4], [2, 3]))                # (l, a, b', l', i')
+        Ek = np.tensordot(Z, Xk, axes=([4, 2], [1, 2]))                # (l, a, l', a')
+        E[k] = Ek.transpose(1, 0, 3, 2).reshape(a * l, a * l)
+    carry = np.ones((1, 1, 1))                                          # (s, a, l)
+    out, spectra, discarded = [], [], []
+    for k in range(n):
+        Xk, Wk = X[k], W[k]
+        a, i, b = Xk.shape
+        l, _, o, r = Wk.shape
+        T1 = np.tensordot(carry, Xk, axes=(1, 0))                      # (s, l, i, b)
+        M = np.tensordot(T1, Wk, axes=([1, 2], [0, 1]))                # (s, b, o, r)
+        M = M.transpose(0, 2, 1, 3)                                    # (s, o, b, r)
+        s = M.shape[0]
+        if k == n - 1:
+            out.append(M.reshape(s, o, b * r))
+            break
+        M2 = M.reshape(s * o, b * r)
+        A = M2 @ E[k + 1] @ M2.T
+        A = 0.5 * (A + A.T)
+        lam, U = np.linalg.eigh(A)
+        lam, U = lam[::-1], U[:, ::-1]
+        S = np.sqrt(np.clip(lam, 0.0, None))
+        keep = keep_count(S, chi_max, cutoff)
+        spectra.append(S.copy())
+        discarded.append(float(np.sum(S[keep:] ** 2)))
+        out.append(U[:, :keep].reshape(s, o, keep))
+        carry = (U[:, :keep].T @ M2).reshape(keep, b, r)
+    return out, spectra, discarded

@@ -143,12 +143,12 @@ class MatrixProductOperator(_MatrixProduct):
         raise NotImplementedError("empty stub in the reference (MPO:653-655)")
 
 
-def _apply_to_state(W, X, min_bond):
+def _apply_to_state(W, X, min_bond, rounding=None, guard=True):
     """MPO x MPS then `>> min_bond` (MPO:181-192).  The guard of `>>` is evaluated on the bonds the product WOULD have
     (from_sites metadata: products of the actual bonds), exactly like the reference's from_sites + compress."""
     prod_bonds = tuple(x.shape[2] * w.shape[3] for x, w in zip(X.sites[:-1], W.sites[:-1]))
-    rounding = MatrixProductState.ROUNDING
-    guard_noop = min_bond >= min(prod_bonds)
+    rounding = rounding or MatrixProductState.ROUNDING
+    guard_noop = guard and min_bond >= min(prod_bonds)      # explicit `bond=` targets (syn.mul extension) skip the guard
     if guard_noop or (MatrixProductOperator.MATMUL_MODE == "standard" and rounding == "qr" and not _FUSE_STANDARD):
         sites = [sw.site_mpo_mps(x, w) for x, w in zip(X.sites, W.sites)]
         return MatrixProductState.from_sites(sites) >> min_bond

@@ -4,20 +4,37 @@ from syngular.tensor.matrix_product_operator import MatrixProductOperator, _appl
 from syngular.tensor.matrix_product_state import MatrixProductState
 
 
-def mul(op1, op2, mode="standard"):
+def mul(op1, op2, mode="standard", bond=None):
+    """mode="standard": the reference's path (contraction + `>> min_bond`, QR truncation unless set_rounding("svd")).
+    mode="optimized": the density-matrix algorithm the reference sketched but never finished (MPO:193-260, utils.py:84-91):
+    MPO x MPS with optimal (SVD) truncation, product cores never formed.
+    `bond` (extension): target bond dimension; defaults to the reference's min_bond rule."""
     n, m = op1.sites_number, op2.sites_number
     min_bond = min(min(op1.bond_shape), min(op2.bond_shape))                 # utils.py:12
+    guard = bond is None
+    if bond is not None:
+        if not isinstance(bond, int):
+            raise Exception("dimension should be an integer")
+        min_bond = bond
     if n != m:
         raise Exception("both operator do not have the same number of sites")
+    if mode == "optimized":
+        if isinstance(op1, MatrixProductState) and isinstance(op2, MatrixProductOperator):
+            op1, op2 = op2, op1
+        if not (isinstance(op1, MatrixProductOperator) and isinstance(op2, MatrixProductState)):
+            raise Exception("`syn.mul` mode 'optimized' needs one MatrixProductOperator and one MatrixProductState")
+        if not op1.decomposed or not op2.decomposed:
+            raise Exception("Operators and States must be decomposed")
+        return _apply_to_state(op1, op2, min_bond, rounding="svd", guard=guard)
     if mode == "standard":
         if isinstance(op1, MatrixProductState) and isinstance(op2, MatrixProductOperator):
             if not op1.decomposed or not op2.decomposed:
                 raise Exception("Operators and States must be decomposed")
-            return _apply_to_state(op2, op1, min_bond)                       # utils.py:30-43
+            return _apply_to_state(op2, op1, min_bond, guard=guard)          # utils.py:30-43
         if isinstance(op1, MatrixProductOperator) and isinstance(op2, MatrixProductState):
             if not op1.decomposed or not op2.decomposed:
                 raise Exception("Operators and States must be decomposed")
-            return _apply_to_state(op1, op2, min_bond)                       # utils.py:44-57
+            return _apply_to_state(op1, op2, min_bond, guard=guard)          # utils.py:44-57
         if isinstance(op1, MatrixProductState) and isinstance(op2, MatrixProductState):
             return op1 | op2                                                 # utils.py:58-59
         if isinstance(op1, MatrixProductOperator) and isinstance(op2, MatrixProductOperator):
@@ -25,6 +42,6 @@ def mul(op1, op2, mode="standard"):
             sites = [sw.site_mpo_mpo(b, a) for a, b in zip(op1.sites, op2.sites)]
             return MatrixProductOperator.from_sites(sites) >> min_bond
         raise Exception("`syn.mul` should be provided MatrixProductState or MatrixProductOperator objects only")
-    if mode in ("variational", "optimized", "fitup"):
+    if mode in ("variational", "fitup"):
         return None                                                          # empty stubs in the reference (utils.py:76-99)
     return None

@@ -51,6 +51,7 @@ def _load():
             "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     lib.syn_last_error.restype = ctypes.c_char_p
+    lib.syn_launch_count.restype = ctypes.c_longlong
     return lib
 
 

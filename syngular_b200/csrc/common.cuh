@@ -27,7 +27,10 @@ int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         }                                         \
     } while (0)
 
+void note_launch();   // counts kernel launches made by this library (bench.py's gpu_launches)
+
 inline int launch_status(const char* what) {
+    note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, what, __FILE__, __LINE__);
     return 0;

@@ -2,11 +2,14 @@
 #include "common.cuh"
 
 #include <cstring>
-#include <mutex>
+#include <atomic>
 
 namespace syn {
 
 static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -35,3 +38,4 @@ int sm_count() {
 extern "C" int syn_version(void) { return 100; }
 extern "C" const char* syn_last_error(void) { return syn::g_error; }
 extern "C" int syn_device_sm_count(void) { return syn::sm_count(); }
+extern "C" long long syn_launch_count(void) { return syn::g_launches.load(); }

@@ -306,6 +306,7 @@ static int launch_jacobi(double* G, int64_t ld, int64_t bs, int n, int batch, co
         dim3 grid(pl.P, nb), block(JAC_THREADS);
         if (pl.P > 1) {
             SYN_CUDA(cudaLaunchCooperativeKernel((void*)kern, grid, block, args, pl.smem, st));
+            note_launch();
         } else {
             kern<<<grid, block, pl.smem, st>>>(Gb, ld, bs, n, w, P, cb, ctrl_stride, max_sweeps, tol);
             if (int rc = launch_status("jacobi_rows_kernel")) return rc;

@@ -7,13 +7,27 @@ from . import _lib
 from ._lib import GemmDesc, check, ix, lib, ptr, require_cuda_f64, stream_ptr
 
 
+# When set to a list, every Python-level gemm() call is bracketed by CUDA events on the launching stream and
+# (start, end, flops, bytes, (M, N, K, batch)) is appended: bench.py uses it to time the dominant kernel inside a real sweep.
+GEMM_PROFILE = None
+
+
 def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, c_b=0, alpha=1.0, beta=0.0):
     """C[m,n] = alpha * sum_k A[m,k] B[k,n] + beta * C[m,n] with two-level strided indices (see syngular_b200.h).
     A, B, C are CUDA float64 tensors used as base pointers (their own strides are ignored)."""
     require_cuda_f64(A, B, C)
     d = GemmDesc(int(M), int(N), int(K), int(batch), ix(a_m), ix(a_k), ix(a_b), ix(b_k), ix(b_n), ix(b_b),
                  ix(c_m), ix(c_n), ix(c_b), float(alpha), float(beta))
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.syn_gemm_f64(ctypes.byref(d), ptr(A), ptr(B), ptr(C), stream_ptr()), "syn_gemm_f64")
+    if prof is not None:
+        e1.record()
+        M_, N_, K_, b_ = int(M), int(N), int(K), int(batch)
+        prof.append((e0, e1, 2.0 * M_ * N_ * K_ * b_, 8.0 * b_ * (M_ * K_ + K_ * N_ + M_ * N_), (M_, N_, K_, b_)))
     return C
 
 
