@@ -18,12 +18,12 @@
 // (2P-1 rounds per sweep).  Convergence (no rotation above tol in a whole sweep) is detected on the device.
 // The finalize kernel sorts sigma descending, normalises the rows, applies chi_max / cutoff and reports the kept rank and
 // the discarded weight -- the singular-value cutoff is fused here, not done on the host.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace syn {
 
-constexpr int JAC_THREADS = 512;
-constexpr int JAC_WARPS = JAC_THREADS / 32;
 constexpr size_t JAC_SMEM_CAP = 160 * 1024;
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -44,9 +44,49 @@ __device__ __forceinline__ void problem_barrier(unsigned* ctr, unsigned target) 
     __syncthreads();
 }
 
-// rotate rows a and b (in shared memory, length n) so that they become orthogonal; returns true if a rotation was applied
+// ---- fast scalar math for the rotation ----------------------------------------------------------------------------
+// FP64 division and sqrt are long dependent software sequences; the rotation sits on the critical path of every Jacobi
+// round, so it is built from the MUFU seeds (rcp / rsqrt.approx.f64, 2^-22) plus Newton steps.  Only c needs full
+// precision (s = c*t makes c^2 + s^2 = 1 to rounding whatever t is); a t accurate to ~1e-13 only perturbs the
+// convergence rate, never the orthogonality of the accumulated transform.
+__device__ __forceinline__ double rcp_newton1(double x) {      // ~2^-44
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double rsqrt_newton1(double x) {    // ~2^-43
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return fma(y, fma(-0.5 * x * y, y, 0.5), y);
+}
+__device__ __forceinline__ double rsqrt_newton2(double x) {    // full double precision
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+}
+
+// Jacobi rotation (Hestenes / Rutishauser) from aa = a.a, bb = b.b, ab = a.b: a' = c a - s b, b' = s a + c b are orthogonal.
+// Returns false when the pair is already orthogonal to tolerance (ab^2 <= tol^2 aa bb) or numerically null.
+__device__ __forceinline__ bool rotation(double aa, double bb, double ab, double tol2, double& c, double& s, double& t_out) {
+    const double prod = aa * bb;
+    if (!(ab * ab > tol2 * prod) || !(prod > 1e-280)) return false;
+    const double d = bb - aa, g = 2.0 * ab;
+    const double h2 = fma(d, d, g * g);
+    const double h = h2 * rsqrt_newton1(h2);
+    double t = fabs(g) * rcp_newton1(fabs(d) + h);         // |t| = |g| / (|d| + sqrt(d^2 + g^2)) <= 1
+    if ((d < 0.0) != (g < 0.0)) t = -t;                   // sign(zeta), zeta = d / g
+    c = rsqrt_newton2(fma(t, t, 1.0));
+    s = c * t;
+    t_out = t;
+    return true;
+}
+
+// rotate rows a and b (both in shared memory, length n): used by the all-pairs round (t == 0) and by single-CTA problems
 template <int NREG>
-__device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __restrict__ b, int n, int lane, double tol) {
+__device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __restrict__ b, int n, int lane, double tol2) {
     double ra[NREG], rb[NREG];
     double aa = 0.0, bb = 0.0, ab = 0.0;
 #pragma unroll
@@ -64,29 +104,77 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __re
         bb += __shfl_xor_sync(0xffffffffu, bb, o);
         ab += __shfl_xor_sync(0xffffffffu, ab, o);
     }
-    if (!(fabs(ab) > tol * sqrt(aa * bb))) return false;   // also false for NaN / zero rows
-    const double zeta = (bb - aa) / (2.0 * ab);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-    const double c = 1.0 / sqrt(fma(t, t, 1.0));
-    const double s = c * t;
+    double c, s, t;
+    if (!rotation(aa, bb, ab, tol2, c, s, t)) return false;
 #pragma unroll
     for (int k = 0; k < NREG; k++) {
         int col = lane + 32 * k;
         if (col < n) {
-            a[col] = c * ra[k] - s * rb[k];
-            b[col] = s * ra[k] + c * rb[k];
+            a[col] = fma(c, ra[k], -s * rb[k]);
+            b[col] = fma(s, ra[k], c * rb[k]);
         }
     }
     return true;
 }
 
-// grid = (P, problems in this launch).  ctrl layout per problem: [0] barrier counter, [1 + sweep] rotation flags, [.. ] sweeps used
-template <int NREG>
-__global__ void __launch_bounds__(JAC_THREADS, 1)
+// Cross-round workhorse: row a lives in the registers of its warp for the whole outer round, the squared norms of both rows
+// are cached (na in a register, *nb in shared memory) and updated analytically (|a'|^2 = aa - t ab, |b'|^2 = bb + t ab), so a
+// round costs ONE dot product, one warp reduction, and one trip of the partner row through shared memory.
+// FULL: n == 32 * NREG, no bounds checks.
+template <int NREG, bool FULL>
+__device__ __forceinline__ bool rotate_cached(double (&ra)[NREG], double& na, double* __restrict__ b, double* __restrict__ nb, int n, int lane,
+                                              double tol2) {
+    double rb[NREG];
+#pragma unroll
+    for (int k = 0; k < NREG; k++) {
+        int c = lane + 32 * k;
+        rb[k] = (FULL || c < n) ? b[c] : 0.0;
+    }
+    double ab0 = 0.0, ab1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NREG; k += 2) {
+        ab0 = fma(ra[k], rb[k], ab0);
+        ab1 = fma(ra[k + 1], rb[k + 1], ab1);
+    }
+    const double ab = warp_sum(ab0 + ab1);
+    const double bb = *nb;
+    double c, s, t;
+    if (!rotation(na, bb, ab, tol2, c, s, t)) return false;
+#pragma unroll
+    for (int k = 0; k < NREG; k++) {
+        int col = lane + 32 * k;
+        const double x = ra[k], y = rb[k];
+        ra[k] = fma(c, x, -s * y);
+        if (FULL || col < n) b[col] = fma(s, x, c * y);
+    }
+    na = fma(-t, ab, na);
+    if (lane == 0) *nb = fma(t, ab, bb);
+    return true;
+}
+
+template <int NREG, bool FULL>
+__device__ __forceinline__ double row_sumsq(const double* __restrict__ a, int n, int lane) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NREG; k += 2) {
+        int c0 = lane + 32 * k, c1 = c0 + 32;
+        double x = (FULL || c0 < n) ? a[c0] : 0.0, y = (FULL || c1 < n) ? a[c1] : 0.0;
+        s0 = fma(x, x, s0);
+        s1 = fma(y, y, s1);
+    }
+    return warp_sum(s0 + s1);
+}
+
+// grid = (P, problems in this launch).  ctrl layout per problem: [0] barrier counter, [1 + sweep] rotation flags,
+// [1 + max_sweeps] sweeps used.
+template <int NREG, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int P, unsigned* __restrict__ ctrl, int ctrl_stride,
-                   int max_sweeps, double tol) {
+                   int max_sweeps, double tol2) {
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) double rows[];   // [2w][LDS]
     __shared__ int s_rot;
+    __shared__ double s_nrm[32];
     const int LDS = (n + 1) & ~1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = blockIdx.x;
@@ -96,19 +184,47 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     unsigned bar_target = 0;
     const int NB = 2 * P;          // number of row blocks
     const int Mr = NB - 1;         // outer rounds per sweep
+    const bool vec2 = ((n & 1) == 0) && ((ld & 1) == 0) && ((((uintptr_t)G) & 15) == 0);
+    const bool full = (n == 32 * NREG);
 
+    // blocks travel through L2 (ld.cg / st.cg: L1 is not coherent across the CTAs of a problem), 16 bytes per thread
     auto load_block = [&](int blk, int half) {
-        for (int idx = tid; idx < w * LDS; idx += JAC_THREADS) {
-            int r = idx / LDS, c = idx - r * LDS;
-            int gr = blk * w + r;
-            rows[(half * w + r) * LDS + c] = (gr < n && c < n) ? __ldcg(G + (int64_t)gr * ld + c) : 0.0;
+        double* dst = rows + half * w * LDS;
+        if (vec2) {
+            const int n2 = n >> 1, L2 = LDS >> 1;
+#pragma unroll 4
+            for (int idx = tid; idx < w * L2; idx += THREADS) {
+                int r = idx / L2, c2 = idx - r * L2;
+                int gr = blk * w + r;
+                double2 v = make_double2(0.0, 0.0);
+                if (gr < n && c2 < n2) v = __ldcg(reinterpret_cast<const double2*>(G + (int64_t)gr * ld) + c2);
+                reinterpret_cast<double2*>(dst + r * LDS)[c2] = v;
+            }
+        } else {
+            for (int idx = tid; idx < w * LDS; idx += THREADS) {
+                int r = idx / LDS, c = idx - r * LDS;
+                int gr = blk * w + r;
+                dst[r * LDS + c] = (gr < n && c < n) ? __ldcg(G + (int64_t)gr * ld + c) : 0.0;
+            }
         }
     };
     auto store_block = [&](int blk, int half) {
-        for (int idx = tid; idx < w * LDS; idx += JAC_THREADS) {
-            int r = idx / LDS, c = idx - r * LDS;
-            int gr = blk * w + r;
-            if (gr < n && c < n) __stcg(G + (int64_t)gr * ld + c, rows[(half * w + r) * LDS + c]);
+        const double* src = rows + half * w * LDS;
+        if (vec2) {
+            const int n2 = n >> 1, L2 = LDS >> 1;
+#pragma unroll 4
+            for (int idx = tid; idx < w * L2; idx += THREADS) {
+                int r = idx / L2, c2 = idx - r * L2;
+                int gr = blk * w + r;
+                if (gr < n && c2 < n2)
+                    __stcg(reinterpret_cast<double2*>(G + (int64_t)gr * ld) + c2, reinterpret_cast<const double2*>(src + r * LDS)[c2]);
+            }
+        } else {
+            for (int idx = tid; idx < w * LDS; idx += THREADS) {
+                int r = idx / LDS, c = idx - r * LDS;
+                int gr = blk * w + r;
+                if (gr < n && c < n) __stcg(G + (int64_t)gr * ld + c, src[r * LDS + c]);
+            }
         }
     };
 
@@ -130,20 +246,47 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                 // all pairs among the 2w local rows (within-block pairs are visited once per sweep, here)
                 const int items = 2 * w, rounds = items - 1;
                 for (int s = 0; s < rounds; ++s) {
-                    for (int k = warp; k < w; k += JAC_WARPS) {
+                    for (int k = warp; k < w; k += WARPS) {
                         int i, j;
                         if (k == 0) { i = items - 1; j = s; }
                         else { i = (s + k) % rounds; j = (s - k + rounds) % rounds; }
-                        rotated |= rotate_pair<NREG>(rows + i * LDS, rows + j * LDS, n, lane, tol);
+                        rotated |= rotate_pair<NREG>(rows + i * LDS, rows + j * LDS, n, lane, tol2);
                     }
                     __syncthreads();
                 }
-            } else {
-                // cross pairs only: row k of block b0 with row (k+s) mod w of block b1
+            } else if (w <= WARPS) {
+                // cross pairs only: row k of block b0 (held in registers by warp k) with row (k+s) mod w of block b1
+                double ra[NREG];
+                double na = 0.0;
+                if (warp < w) {
+#pragma unroll
+                    for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; ra[k] = c < n ? rows[warp * LDS + c] : 0.0; }
+#pragma unroll
+                    for (int k = 0; k < NREG; k++) na = fma(ra[k], ra[k], na);
+                    na = warp_sum(na);
+                    const double nbv = full ? row_sumsq<NREG, true>(rows + (w + warp) * LDS, n, lane)
+                                            : row_sumsq<NREG, false>(rows + (w + warp) * LDS, n, lane);
+                    if (lane == 0) s_nrm[warp] = nbv;
+                }
+                __syncthreads();
                 for (int s = 0; s < w; ++s) {
-                    for (int k = warp; k < w; k += JAC_WARPS) {
+                    if (warp < w) {
+                        const int j = (warp + s) & (w - 1);           // w is a power of two
+                        rotated |= full ? rotate_cached<NREG, true>(ra, na, rows + (w + j) * LDS, s_nrm + j, n, lane, tol2)
+                                        : rotate_cached<NREG, false>(ra, na, rows + (w + j) * LDS, s_nrm + j, n, lane, tol2);
+                    }
+                    __syncthreads();
+                }
+                if (warp < w) {
+#pragma unroll
+                    for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; if (c < n) rows[warp * LDS + c] = ra[k]; }
+                }
+                __syncthreads();
+            } else {
+                for (int s = 0; s < w; ++s) {
+                    for (int k = warp; k < w; k += WARPS) {
                         int j = w + ((k + s) % w);
-                        rotated |= rotate_pair<NREG>(rows + k * LDS, rows + j * LDS, n, lane, tol);
+                        rotated |= rotate_pair<NREG>(rows + k * LDS, rows + j * LDS, n, lane, tol2);
                     }
                     __syncthreads();
                 }
@@ -266,49 +409,59 @@ jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int
 // ---- host drivers --------------------------------------------------------------------------------------------------------
 struct JacPlan { int w, P, nreg; size_t smem; };
 
+static int jac_env_w() {   // experiment knob: SYN_JACOBI_W=8 forces the block height of multi-CTA problems
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SYN_JACOBI_W"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 static int jac_plan(int n, JacPlan& pl) {
     SYN_REQUIRE(n >= 1 && n <= 1024, "syn_jacobi_rows_f64: n=%d out of range (1..1024)", n);
-    int LDS = (n + 1) & ~1;
+    const int LDS = (n + 1) & ~1;
     pl.nreg = n <= 128 ? 4 : (n <= 256 ? 8 : (n <= 512 ? 16 : 32));
-    int w = 1;
-    while (w < 512) w <<= 1;
-    // largest power-of-two w with 2*w rows in JAC_SMEM_CAP, but no more rows than needed (2w >= n is enough)
-    while (w > 1 && ((size_t)2 * w * LDS * sizeof(double) > JAC_SMEM_CAP || w >= n)) w >>= 1;
-    if (n <= 2) w = 1;
+    int w;
+    if (n <= 128) {                 // whole problem in one CTA (P = 1): no grid barriers, good for large batches
+        w = 1;
+        while (2 * w < n) w <<= 1;
+    } else {                        // w rows per block, one warp per stationary row in the cross rounds
+        w = jac_env_w() > 0 ? jac_env_w() : 16;
+        while (w > 1 && (size_t)2 * w * LDS * sizeof(double) > JAC_SMEM_CAP) w >>= 1;
+    }
     pl.w = w;
     pl.P = (n + 2 * w - 1) / (2 * w);
     pl.smem = (size_t)2 * w * LDS * sizeof(double);
     return 0;
 }
 
-template <int NREG>
+template <int NREG, int THREADS>
 static int launch_jacobi(double* G, int64_t ld, int64_t bs, int n, int batch, const JacPlan& pl, unsigned* ctrl, int ctrl_stride,
                          int max_sweeps, double tol, cudaStream_t st) {
-    auto kern = jacobi_rows_kernel<NREG>;
+    auto kern = jacobi_rows_kernel<NREG, THREADS>;
     static bool configured = false;
     static int max_ctas = 0;
     if (!configured) {
         SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_CAP));
         int per_sm = 0;
-        SYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JAC_THREADS, JAC_SMEM_CAP));
+        SYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, JAC_SMEM_CAP));
         max_ctas = per_sm * sm_count();
         configured = true;
     }
     SYN_REQUIRE(pl.P <= max_ctas, "syn_jacobi_rows_f64: problem needs %d co-resident CTAs, device fits %d", pl.P, max_ctas);
     int chunk = max_ctas / pl.P;
     if (chunk > 65535) chunk = 65535;
+    double tol2 = tol * tol;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         int nb = (batch - b0) < chunk ? (batch - b0) : chunk;
         double* Gb = G + (int64_t)b0 * bs;
         unsigned* cb = ctrl + (int64_t)b0 * ctrl_stride;
         int w = pl.w, P = pl.P;
-        void* args[] = {&Gb, &ld, &bs, &n, &w, &P, &cb, &ctrl_stride, &max_sweeps, &tol};
-        dim3 grid(pl.P, nb), block(JAC_THREADS);
+        void* args[] = {&Gb, &ld, &bs, &n, &w, &P, &cb, &ctrl_stride, &max_sweeps, &tol2};
+        dim3 grid(pl.P, nb), block(THREADS);
         if (pl.P > 1) {
             SYN_CUDA(cudaLaunchCooperativeKernel((void*)kern, grid, block, args, pl.smem, st));
             note_launch();
         } else {
-            kern<<<grid, block, pl.smem, st>>>(Gb, ld, bs, n, w, P, cb, ctrl_stride, max_sweeps, tol);
+            kern<<<grid, block, pl.smem, st>>>(Gb, ld, bs, n, w, P, cb, ctrl_stride, max_sweeps, tol2);
             if (int rc = launch_status("jacobi_rows_kernel")) return rc;
         }
     }
@@ -326,10 +479,10 @@ int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* c
     SYN_CUDA(cudaMemsetAsync(ctrl, 0, jacobi_ctrl_bytes(batch, max_sweeps), st));
     const int stride = max_sweeps + 2;
     switch (pl.nreg) {
-        case 4: return launch_jacobi<4>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
-        case 8: return launch_jacobi<8>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
-        case 16: return launch_jacobi<16>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
-        default: return launch_jacobi<32>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
+        case 4: return launch_jacobi<4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
+        case 8: return launch_jacobi<8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
+        case 16: return launch_jacobi<16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
+        default: return launch_jacobi<32, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, st);
     }
 }
 

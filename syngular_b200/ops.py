@@ -147,7 +147,19 @@ def jacobi_rows(G, max_sweeps=40, tol=None):
     rc = lib.syn_jacobi_rows_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(ctrl), _sz(ctrl.numel() * 8),
                                  _i32(max_sweeps), _dbl(tol if tol is not None else jacobi_tol(n)), stream_ptr())
     check(rc, "syn_jacobi_rows_f64")
+    global _last_jacobi
+    _last_jacobi = (ctrl, max_sweeps, nb)
     return G
+
+
+_last_jacobi = None
+
+
+def jacobi_sweeps_used():
+    """Sweeps the last jacobi_rows call needed, per batch member (diagnostic; synchronises)."""
+    ctrl, max_sweeps, nb = _last_jacobi
+    words = ctrl.view(torch.int32)[: nb * (max_sweeps + 2)].reshape(nb, max_sweeps + 2)
+    return words[:, max_sweeps + 1].tolist()
 
 
 def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False):
