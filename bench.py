@@ -279,6 +279,28 @@ def run_ours(args):
     ms_qr = timed(step_qr, max(2, min(args.steps, 5)))
     qr_value = world * max(2, min(args.steps, 5)) / (ms_qr * 1e-3)
 
+    # BASELINE configs[3]: 8192 independent random MPS (N=32, d=2, chi=64), overlaps of state b of set A with state b of set B,
+    # batch-sharded in contiguous blocks, ONE all-gather of the B scalars; reported as states/s
+    from syngular_b200 import parallel
+    from syngular_b200.batched import BatchedMatrixProductState as BMPS
+    B_total, n4 = 8192, 32
+    lo, hi = parallel.shard_bounds(B_total, rank, world)
+    bonds4 = capped_bonds(n4, 2, 64)[1:-1]
+    A4 = BMPS.random(hi - lo, (2,) * n4, bonds4, seed=1000 + rank, device=dev)
+    B4 = BMPS.random(hi - lo, (2,) * n4, bonds4, seed=2000 + rank, device=dev)
+
+    def step_c4():
+        return parallel.gather_scalars(A4.overlap(B4), B_total)
+    for _ in range(2):
+        ov = step_c4()
+    c4_reps = 3
+    ms_c4 = timed(step_c4, c4_reps)
+    c4_value = B_total * c4_reps / (ms_c4 * 1e-3)
+    c4_flops = sum(4.0 * 2 * a * b * max(a, b) for a, b in zip([1] + list(bonds4), list(bonds4) + [1])) * B_total
+    c4_bytes = 2 * 8.0 * sum(a * 2 * b for a, b in zip([1] + list(bonds4), list(bonds4) + [1])) * B_total
+    ov_ok = bool(torch.isfinite(ov).all().item()) and ov.numel() == B_total
+    del A4, B4
+
     line = None
     if rank == 0:
         # roofline of the dominant kernel: profile one sweep with per-launch CUDA events on the launching stream
@@ -328,7 +350,12 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "extra": {"qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),
+            "extra": {"c4_batched_overlaps_states_per_s": c4_value, "c4_ms_per_batch": ms_c4 / c4_reps,
+                      "c4_note": "BASELINE configs[3]: 8192 x (N=32, d=2, chi=64) overlaps, batch-sharded over %d GPU(s), one all-gather of 8192 "
+                                 "float64; %.2f TFLOP/s FP64, %.0f GB/s of core traffic; gathered %s" % (
+                                     world, c4_flops / (ms_c4 / c4_reps * 1e-3) / 1e12, c4_bytes / (ms_c4 / c4_reps * 1e-3) / 1e9,
+                                     "ok" if ov_ok else "BAD"),
+                      "qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),
                       "qr_round_note": "reference-semantic `>>` (QR truncation, fused apply+round) on the same chain"},
         }
     if world > 1:
