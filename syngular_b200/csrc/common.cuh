@@ -41,6 +41,7 @@ int sm_count();
 // ---- device helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t idx2(const syn_index_t& ix, int x) {
     // two-level index: (x / div) * outer + (x % div) * inner ; div >= extent collapses to x * inner
+    if ((unsigned)x < (unsigned)ix.div) return (int64_t)x * ix.inner;      // single level: no integer division on the hot path
     unsigned q = (unsigned)x / (unsigned)ix.div;
     unsigned r = (unsigned)x - q * (unsigned)ix.div;
     return (int64_t)q * ix.outer + (int64_t)r * ix.inner;

@@ -13,6 +13,8 @@
 // comfortably from shared memory: operands are staged by a 4-stage cp.async (LDGSTS) ring, 16-byte chunks along
 // whichever logical dimension is contiguous in HBM; tiles are stored in shared memory in the orientation they
 // arrive in, padded so that the 64-bit fragment loads of a half-warp hit 16 distinct 8-byte bank pairs.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace syn {
@@ -159,23 +161,30 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
         }
         const double* a_s = sA + (kt % C::STAGES) * LA::TILE_ELEMS;
         const double* b_s = sB + (kt % C::STAGES) * LB::TILE_ELEMS;
-#pragma unroll
-        for (int kk = 0; kk < C::BK; kk += 4) {
-            double af[C::MT], bf[C::NT];
+        // fragments are double-buffered in registers: the loads of k-step kk+4 are issued before the DMMAs of step kk, into
+        // registers the in-flight DMMAs do not read (no WAR/RAW serialisation between the LDS and the tensor pipe)
+        double af[2][C::MT], bf[2][C::NT];
+        auto load_frags = [&](int buf, int kk) {
 #pragma unroll
             for (int i = 0; i < C::MT; i++) {
                 int r = wm0 + i * 8 + g;
-                af[i] = A_ALONG_M ? a_s[(kk + t) * LA::STRIDE + r] : a_s[r * LA::STRIDE + kk + t];
+                af[buf][i] = A_ALONG_M ? a_s[(kk + t) * LA::STRIDE + r] : a_s[r * LA::STRIDE + kk + t];
             }
 #pragma unroll
             for (int j = 0; j < C::NT; j++) {
                 int c = wn0 + j * 8 + g;
-                bf[j] = B_ALONG_N ? b_s[(kk + t) * LB::STRIDE + c] : b_s[c * LB::STRIDE + kk + t];
+                bf[buf][j] = B_ALONG_N ? b_s[(kk + t) * LB::STRIDE + c] : b_s[c * LB::STRIDE + kk + t];
             }
+        };
+        load_frags(0, 0);
+#pragma unroll
+        for (int kk = 0; kk < C::BK; kk += 4) {
+            const int cur = (kk >> 2) & 1;
+            if (kk + 4 < C::BK) load_frags(cur ^ 1, kk + 4);
 #pragma unroll
             for (int i = 0; i < C::MT; i++)
 #pragma unroll
-                for (int j = 0; j < C::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < C::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
     }
     cp_async_wait<0>();
@@ -215,8 +224,21 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
 }
 
 // ---------------------------------------------------------------------------------------------------------
-using CfgL = GemmCfg<128, 128, 16, 64, 32, 4>;   // 256 threads, 1 CTA/SM, 160 KB smem
-using CfgS = GemmCfg<64, 64, 16, 32, 32, 4>;     // 128 threads, 80 KB smem, up to 2 CTAs/SM
+using CfgL = GemmCfg<128, 128, 32, 64, 32, 3>;   // 256 threads, 1 CTA/SM, 212 KB smem
+using CfgS = GemmCfg<64, 64, 32, 32, 32, 3>;     // 128 threads, 107 KB smem, 2 CTAs/SM
+using CfgW = GemmCfg<128, 128, 32, 32, 32, 3>;   // 512 threads (4 warps per SM sub-partition), 32x32 warp tiles
+
+using CfgN = GemmCfg<128, 32, 32, 32, 32, 2>;    // skinny outputs (N <= 32): 128 threads, 92 KB smem
+using CfgM = GemmCfg<32, 128, 32, 32, 32, 2>;    // flat outputs (M <= 32)
+
+static int gemm_env_cfg() {   // experiment knob: SYN_GEMM_CFG=L|W|S forces a tile configuration
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SYN_GEMM_CFG");
+        v = !e ? 0 : (e[0] == 'L' ? 1 : (e[0] == 'W' ? 2 : (e[0] == 'S' ? 3 : 0)));
+    }
+    return v;
+}
 
 template <class C, bool AM, bool BN, int VEC>
 static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, int c_vec, cudaStream_t st) {
@@ -294,7 +316,13 @@ int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double*
     // tile choice: the large tile when it still fills the machine, else the small one
     long long big_tiles = (long long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch;
     bool use_large = (d.M > 64 && d.N > 64) && big_tiles >= (long long)sm_count();
-    if (use_large) return dispatch_layout<CfgL>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    const int forced = gemm_env_cfg();
+    if (forced == 1) return dispatch_layout<CfgL>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (forced == 2) return dispatch_layout<CfgW>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (forced == 3) return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (d.N <= 32 && d.M >= 128) return dispatch_layout<CfgN>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (d.M <= 32 && d.N >= 128) return dispatch_layout<CfgM>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (use_large) return dispatch_layout<CfgW>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
 }
 
