@@ -204,6 +204,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: ONE JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import syngular as syn
     from syngular.tensor import MatrixProductOperator as MPO, MatrixProductState as MPS, _sweeps as sw
