@@ -102,7 +102,7 @@ struct OperandLoader {
 template <class C, bool A_ALONG_M, bool B_ALONG_N, int VEC>
 __global__ void __launch_bounds__(C::THREADS)
 gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const double* __restrict__ B,
-                double* __restrict__ Cmat, int tiles_n, int c_vec) {
+                double* __restrict__ Cmat, int tiles_m, int tiles_n, int c_vec) {
     using LA = OperandLoader<C, C::BM, A_ALONG_M, VEC>;
     using LB = OperandLoader<C, C::BN, B_ALONG_N, VEC>;
     extern __shared__ __align__(16) double smem[];
@@ -115,9 +115,14 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
     const int wm0 = (warp / C::WARPS_N) * C::WM;
     const int wn0 = (warp % C::WARPS_N) * C::WN;
 
+    // tile order: the dimension with FEWER tiles varies fastest, so the CTAs that share a tile of the long operand are
+    // co-scheduled and it is fetched from HBM once (ncu: DRAM traffic == algorithmic bytes)
     const int tile = blockIdx.x;
-    const int m0 = (tile / tiles_n) * C::BM;
-    const int n0 = (tile % tiles_n) * C::BN;
+    int tm, tn;
+    if (tiles_m <= tiles_n) { tm = tile % tiles_m; tn = tile / tiles_m; }
+    else { tn = tile % tiles_n; tm = tile / tiles_n; }
+    const int m0 = tm * C::BM;
+    const int n0 = tn * C::BN;
     const int batch = blockIdx.y + gridDim.y * blockIdx.z;
     if (batch >= d.batch) return;
 
@@ -257,7 +262,7 @@ static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* 
     int by = d.batch < 65535 ? d.batch : 65535;
     int bz = (d.batch + by - 1) / by;
     dim3 grid((unsigned)tiles, by, bz);
-    kern<<<grid, C::THREADS, smem, st>>>(d, A, B, Cm, tiles_n, c_vec);
+    kern<<<grid, C::THREADS, smem, st>>>(d, A, B, Cm, tiles_m, tiles_n, c_vec);
     return launch_status("gemm_f64_kernel");
 }
 
