@@ -69,10 +69,14 @@ __device__ __forceinline__ double rsqrt_newton2(double x) {    // full double pr
 }
 
 // Jacobi rotation (Hestenes / Rutishauser) from aa = a.a, bb = b.b, ab = a.b: a' = c a - s b, b' = s a + c b are orthogonal.
-// Returns false when the pair is already orthogonal to tolerance (ab^2 <= tol^2 aa bb) or numerically null.
-__device__ __forceinline__ bool rotation(double aa, double bb, double ab, double tol2, double& c, double& s, double& t_out) {
+// Returns 0 when the pair is already orthogonal to tolerance (ab^2 <= tol^2 aa bb) or numerically null, 1 for a "small"
+// rotation (|cos| <= 1e-9: by quadratic convergence the sweep after a sweep of only small rotations cannot rotate above
+// tol any more, so no verification sweep is needed), 3 for a big one.
+__device__ __forceinline__ int rotation(double aa, double bb, double ab, double tol2, double& c, double& s, double& t_out) {
     const double prod = aa * bb;
-    if (!(ab * ab > tol2 * prod) || !(prod > 1e-280)) return false;
+    const double ab2 = ab * ab;
+    if (!(ab2 > tol2 * prod) || !(prod > 1e-280)) return 0;
+    const int kind = (ab2 > 1e-18 * prod) ? 3 : 1;
     const double d = bb - aa, g = 2.0 * ab;
     const double h2 = fma(d, d, g * g);
     const double h = h2 * rsqrt_newton1(h2);
@@ -81,12 +85,12 @@ __device__ __forceinline__ bool rotation(double aa, double bb, double ab, double
     c = rsqrt_newton2(fma(t, t, 1.0));
     s = c * t;
     t_out = t;
-    return true;
+    return kind;
 }
 
 // rotate rows a and b (both in shared memory, length n): used by the all-pairs round (t == 0) and by single-CTA problems
 template <int NREG>
-__device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __restrict__ b, int n, int lane, double tol2) {
+__device__ __forceinline__ int rotate_pair(double* __restrict__ a, double* __restrict__ b, int n, int lane, double tol2) {
     double ra[NREG], rb[NREG];
     double aa = 0.0, bb = 0.0, ab = 0.0;
 #pragma unroll
@@ -105,7 +109,8 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __re
         ab += __shfl_xor_sync(0xffffffffu, ab, o);
     }
     double c, s, t;
-    if (!rotation(aa, bb, ab, tol2, c, s, t)) return false;
+    const int kind = rotation(aa, bb, ab, tol2, c, s, t);
+    if (!kind) return 0;
 #pragma unroll
     for (int k = 0; k < NREG; k++) {
         int col = lane + 32 * k;
@@ -114,7 +119,7 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __re
             b[col] = fma(s, ra[k], c * rb[k]);
         }
     }
-    return true;
+    return kind;
 }
 
 // Cross-round workhorse: row a lives in the registers of its warp for the whole outer round, the squared norms of both rows
@@ -122,7 +127,7 @@ __device__ __forceinline__ bool rotate_pair(double* __restrict__ a, double* __re
 // round costs ONE dot product, one warp reduction, and one trip of the partner row through shared memory.
 // FULL: n == 32 * NREG, no bounds checks.
 template <int NREG, bool FULL>
-__device__ __forceinline__ bool rotate_cached(double (&ra)[NREG], double& na, double* __restrict__ b, double* __restrict__ nb, int n, int lane,
+__device__ __forceinline__ int rotate_cached(double (&ra)[NREG], double& na, double* __restrict__ b, double* __restrict__ nb, int n, int lane,
                                               double tol2) {
     double rb[NREG];
 #pragma unroll
@@ -139,7 +144,8 @@ __device__ __forceinline__ bool rotate_cached(double (&ra)[NREG], double& na, do
     const double ab = warp_sum(ab0 + ab1);
     const double bb = *nb;
     double c, s, t;
-    if (!rotation(na, bb, ab, tol2, c, s, t)) return false;
+    const int kind = rotation(na, bb, ab, tol2, c, s, t);
+    if (!kind) return 0;
 #pragma unroll
     for (int k = 0; k < NREG; k++) {
         int col = lane + 32 * k;
@@ -149,7 +155,7 @@ __device__ __forceinline__ bool rotate_cached(double (&ra)[NREG], double& na, do
     }
     na = fma(-t, ab, na);
     if (lane == 0) *nb = fma(t, ab, bb);
-    return true;
+    return kind;
 }
 
 template <int NREG, bool FULL>
@@ -192,8 +198,8 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
         double* dst = rows + half * w * LDS;
         if (vec2) {
             const int n2 = n >> 1, L2 = LDS >> 1;
-#pragma unroll 4
-            for (int idx = tid; idx < w * L2; idx += THREADS) {
+#pragma unroll 8
+            for (int idx = tid; idx < w * L2; idx += THREADS) {      // all loads of a block in flight at once
                 int r = idx / L2, c2 = idx - r * L2;
                 int gr = blk * w + r;
                 double2 v = make_double2(0.0, 0.0);
@@ -230,7 +236,7 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
 
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
-        bool rotated = false;
+        int rotated = 0;
         for (int t = 0; t < (P == 1 ? 1 : Mr); ++t) {
             // round-robin tournament over the NB blocks (circle method): CTA p plays (b0, b1) in round t
             int b0, b1;
@@ -301,16 +307,16 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
         // sweep-level convergence vote
         if (tid == 0) s_rot = 0;
         __syncthreads();
-        if (rotated && lane == 0) atomicOr(&s_rot, 1);
+        if (rotated && lane == 0) atomicOr(&s_rot, rotated);
         __syncthreads();
         if (P > 1) {
-            if (tid == 0 && s_rot) atomicOr(flags + sweep, 1u);
+            if (tid == 0 && s_rot) atomicOr(flags + sweep, (unsigned)s_rot);
             bar_target += P;
             problem_barrier(bar, bar_target);
             unsigned f = ld_acquire_u32(flags + sweep);
-            if (f == 0u) { ++sweep; break; }
+            if ((f & 2u) == 0u) { ++sweep; break; }      // no rotation, or only small ones: converged
         } else {
-            if (s_rot == 0) { ++sweep; break; }
+            if ((s_rot & 2) == 0) { ++sweep; break; }
             __syncthreads();
         }
     }
