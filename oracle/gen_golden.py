@@ -266,7 +266,47 @@ def main():
     rd["diag_left0"] = np.diag(Z.left_orthogonality(0))
     rd["diag_left1"] = np.diag(Z.left_orthogonality(1))
     np.savez_compressed(os.path.join(OUT, "readme_chain.npz"), **rd)
+    qd, _ = quantum_goldens(MPS, quiet)
+    np.savez_compressed(os.path.join(OUT, "quantum.npz"), **qd)
+    print("quantum:", len(qd), "arrays; bell =", qd["circuit/bell"], " toffoli|110> =", qd["circuit/toffoli_110"])
     print("readme_chain:", len(rd), "arrays; X|U =", repr(float(rd["X_U"])), " Z|X =", repr(float(rd["Z_X"])))
+
+
+def quantum_goldens(MPS, quiet):
+    """MatrixProductState.apply and Qbit circuits with REAL gates (the CUDA library is FP64-real), run by the reference."""
+    from syngular.quantum import Qbit, gate
+    q = {}
+    rng = np.random.default_rng(99)
+    b = [1, 2, 4, 4, 2, 1]
+    cores = [rng.normal(size=(b[k], 2, b[k + 1])) for k in range(5)]
+    Xr = MPS.from_sites(cores)
+    for k, c in enumerate(cores):
+        q["apply/X/site%d" % k] = c
+    q["apply/X/n"] = np.array(5)
+    for name, g, i in (("cx0", gate.CX, 0), ("swap2", gate.SWAP, 2), ("h4", gate.H, 4), ("tof1", gate.TOFFOLI, 1), ("x0", gate.X, 0),
+                       ("cx3", gate.CX, 3), ("tof2", gate.TOFFOLI, 2), ("z2", gate.Z, 2)):
+        Y = Xr.apply(g, i)
+        q["apply/%s_dense" % name] = Y.to_tensor().real
+        q["apply/%s_bonds" % name] = np.array([s.shape[2] for s in Y.sites[:-1]])
+    circuits = {
+        "bell": (2, [("H", 0), ("CX", 0, 1)]),
+        "ghz4": (4, [("H", 0), ("CX", 0, 1), ("CX", 1, 2), ("CX", 2, 3)]),
+        "x_chain": (5, [("X", 0), ("X", 3), ("CX", 3, 4), ("SWAP", 1)]),
+        "cx_far_02": (3, [("X", 0), ("CX", 0, 2)]),
+        "cx_far_20": (3, [("X", 2), ("CX", 2, 0)]),
+        "cx_far_03": (4, [("X", 0), ("CX", 0, 3)]),
+        "h_layer": (4, [("H", 0), ("H", 1), ("H", 2), ("H", 3), ("Z", 1), ("CX", 1, 2)]),
+        "toffoli_110": (3, [("X", 0), ("X", 1), ("TOFFOLI", 0)]),
+        "toffoli_100": (3, [("X", 0), ("TOFFOLI", 0)]),
+    }
+    for name, (size, ops) in circuits.items():
+        qb = Qbit(size)
+        for op in ops:
+            g = getattr(gate, op[0])
+            qb = quiet(qb.__matmul__, (g,) + tuple(op[1:]))
+        q["circuit/%s" % name] = np.asarray(qb.to_tensor()).real
+    q["circuit/binary_101"] = np.asarray(Qbit.from_binary("101").to_tensor()).real
+    return q, circuits
 
 
 def to_dense_mpo(sites):

@@ -168,6 +168,31 @@ def retrieve(cores, idx_in, idx_out=None):
     return M
 
 
+def mps_apply(cores, gate, index):
+    """`MatrixProductState.apply(gate, index)` (matrix_product_state.py:487-534): contract a dense m-site gate
+    (legs out_0..out_{m-1}, in_0..in_{m-1}; column-vector convention) into cores index..index+m-1, then re-split with the
+    qrt step keeping the EXISTING bonds (the bond never grows; entanglement beyond it is projected away)."""
+    cores = [np.array(c, copy=True) for c in cores]
+    gate = np.asarray(gate)
+    m = gate.ndim // 2
+    T = cores[index]
+    for k in range(index + 1, index + m):
+        T = np.tensordot(T, cores[k], axes=(T.ndim - 1, 0))            # (l, in_0..in_j, r)
+    l, r = T.shape[0], T.shape[-1]
+    din = int(np.prod(T.shape[1:-1]))
+    G = gate.reshape(int(np.prod(gate.shape[:m])), din)
+    T = np.einsum("oi,lir->lor", G, T.reshape(l, din, r)).reshape((l,) + tuple(gate.shape[:m]) + (r,))
+    for k in range(index, index + m - 1):
+        lr, d = T.shape[0], T.shape[1]
+        L = T.reshape(lr * d, -1)
+        Q, R = qrt(L, cores[k].shape[2])
+        kept = Q.shape[1]
+        cores[k] = Q.reshape(lr, d, kept)
+        T = R.reshape(kept, -1, cores[k + 1].shape[2]) if k + 1 == index + m - 1 else R.reshape((kept,) + T.shape[2:])
+    cores[index + m - 1] = T.reshape(T.shape[0], -1, T.shape[-1])
+    return cores
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step, left to right (matrix_product_state.py:298-319,
     matrix_product_operator.py:430-450).  `T` is the (interleaved, for an MPO) dense tensor and `shapes` the
@@ -446,3 +471,58 @@ def mul(op1, op2, mode="standard"):
     if isinstance(op1, MPO) and isinstance(op2, MPO):
         return MPO.from_sites([site_mpo_mpo(b, a) for a, b in zip(op1.sites, op2.sites)]) >> m
     raise Exception("`syn.mul` should be provided MatrixProductState or MatrixProductOperator objects only")
+
+
+# --------------------------------------------------------------------------------------
+# quantum/ (caller of the path for BASELINE configs[2]) -- real gates only
+# --------------------------------------------------------------------------------------
+class Gates:
+    """quantum/gate.py:4-61 (legs of multi-qubit gates: out..., in...)."""
+    I = np.eye(2)
+    X = np.array([[0., 1.], [1., 0.]])
+    Z = np.array([[1., 0.], [0., -1.]])
+    H = np.array([[1., 1.], [1., -1.]]) / np.sqrt(2)
+    CX = np.array([[1., 0, 0, 0], [0, 1., 0, 0], [0, 0, 0, 1.], [0, 0, 1., 0]]).reshape(2, 2, 2, 2)
+    SWAP = np.array([[1., 0, 0, 0], [0, 0, 1., 0], [0, 1., 0, 0], [0, 0, 0, 1.]]).reshape(2, 2, 2, 2)
+    TOFFOLI = np.eye(8)[[0, 1, 2, 3, 4, 5, 7, 6]].reshape((2,) * 6)
+
+
+class Qbit:
+    """quantum/qbit.py:11-150: |0..0> register with every bond fixed at 2; gates through mps_apply."""
+
+    def __init__(self, size, cores=None):
+        self.size = size
+        if cores is None:
+            b = [1] + [2] * (size - 1) + [1]
+            cores = []
+            for k in range(size):
+                c = np.zeros((b[k], 2, b[k + 1]))
+                if k < size - 1:
+                    c[0] = np.eye(2)[:, : b[k + 1]]
+                else:
+                    c[0, 0, 0] = 1.0
+                cores.append(c)
+        self.cores = cores
+
+    def _apply(self, g, i):
+        return Qbit(self.size, mps_apply(self.cores, g, i))
+
+    def __matmul__(self, op):
+        if len(op) == 2:
+            return self._apply(*op)
+        g, a, b = op
+        lo, hi = min(a, b), max(a, b)
+        q = self
+        if hi - lo != 1:                                   # qbit.py:42-50
+            for i in range(lo, hi - 1):
+                q = q._apply(Gates.SWAP, i)
+            if lo != a:
+                q = q._apply(Gates.SWAP, hi - 1)
+        q = q._apply(g, hi - 1)
+        if hi - lo != 1:                                   # qbit.py:57-58, swap_out :91-106
+            for i in range(hi - 1, lo - 1, -1):
+                q = q._apply(Gates.SWAP, i)
+        return q
+
+    def to_tensor(self):
+        return to_dense(self.cores).reshape(-1)

@@ -151,6 +151,42 @@ def retrieve(sites, idx_in, idx_out=None):
     return v
 
 
+def apply_gate(sites, gate, index, mode="compress", chi_max=None, cutoff=0.0):
+    """`MatrixProductState.apply` (MPS:487-534): contract a dense m-site gate (legs out..., in...; column-vector convention)
+    into cores index..index+m-1, then re-split.
+      mode="compress" (reference): qrt split keeping the EXISTING bonds -- the bond never grows;
+      mode="svd" (extension): local SVD split, bonds grow up to chi_max (relative cutoff `cutoff`)."""
+    out = list(sites)
+    m = gate.dim() // 2
+    T = out[index]
+    for k in range(index + 1, index + m):                               # merge the m cores: (l, in_0..in_j, r)
+        c = out[k]
+        T = ops.matmul(T.reshape(-1, T.shape[-1]), c.reshape(c.shape[0], -1)).reshape(tuple(T.shape[:-1]) + tuple(c.shape[1:]))
+    l, r = T.shape[0], T.shape[-1]
+    dims_out = tuple(gate.shape[:m])
+    dout, din = int(np.prod(dims_out)), int(np.prod(gate.shape[m:]))
+    G = gate.reshape(dout, din)
+    T3 = T.reshape(l, din, r)
+    Tn = empty(l, dout, r)
+    # Tn[l] (dout x r) = G (dout x din) @ T3[l] (din x r), batched over l with the gate shared
+    ops.gemm(G, T3, Tn, M=dout, N=r, K=din, a_m=din, a_k=1, b_k=r, b_n=1, c_m=r, c_n=1, batch=l, a_b=0, b_b=din * r, c_b=dout * r)
+    T = Tn.reshape((l,) + dims_out + (r,))
+    trunc = Truncation()
+    for k in range(index, index + m - 1):
+        lr, d = T.shape[0], T.shape[1]
+        L = T.reshape(lr * d, -1)
+        if mode == "svd":
+            core2d, kept = _svd_basis(L, chi_max if chi_max is not None else min(L.shape), cutoff, trunc)
+            S = ops.matmul(core2d.t(), L)
+        else:
+            core2d, S = ops.qrt(L, int(sites[k].shape[2]))
+            kept = core2d.shape[1]
+        out[k] = core2d.reshape(lr, d, kept)
+        T = S.reshape((kept,) + tuple(T.shape[2:]))
+    out[index + m - 1] = T.reshape(T.shape[0], -1, T.shape[-1])
+    return out
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step (MPS:298-319, MPO:430-450)."""
     cores, l, n = [], 1, len(shapes)

@@ -112,5 +112,15 @@ class MatrixProductState(_MatrixProduct):
             self.decomposed = True
         return self
 
-    def apply(self, operator, index, strict=True, mode="compress"):
-        raise NotImplementedError("MatrixProductState.apply (gate application, MPS:487-534) is a 'next' row of the scope table")
+    def apply(self, operator, index, strict=True, mode="compress", chi_max=None, cutoff=0.0):
+        """Apply a dense m-site gate (ndarray with legs out_0..out_{m-1}, in_0..in_{m-1}) at sites index..index+m-1 (MPS:487-534).
+        mode="compress": the reference's behaviour -- QR re-split keeping the existing bonds (never grows).
+        mode="svd"     : extension -- local SVD split, bonds grow up to chi_max (relative singular-value cutoff)."""
+        gate = sw.as_core(operator)
+        m = gate.dim() // 2
+        if gate.dim() != 2 * m or index < 0 or index + m > self.sites_number:
+            raise Exception("gate does not fit the chain at this index")
+        that = self.copy() if strict else self
+        that.sites = sw.apply_gate(that.sites, gate, index, mode=mode, chi_max=chi_max, cutoff=cutoff)
+        that._refresh_from_cores(bonds=(mode == "svd"))
+        return that

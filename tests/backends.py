@@ -27,6 +27,16 @@ class OracleBackend:
     def mul(self, a, b):
         return self.R.mul(a, b)
 
+    def apply_gate(self, cores, gname, index):
+        out = self.R.mps_apply([np.array(c) for c in cores], getattr(self.R.Gates, gname), index)
+        return np.real(self.R.to_dense(out)), [c.shape[2] for c in out[:-1]]
+
+    def run_circuit(self, size, ops):
+        q = self.R.Qbit(size)
+        for op in ops:
+            q = q @ ((getattr(self.R.Gates, op[0]),) + tuple(op[1:]))
+        return np.real(q.to_tensor())
+
     def sites(self, obj):
         return [np.asarray(s) for s in obj.sites]
 
@@ -71,6 +81,18 @@ class ProductBackend:
 
     def mul(self, a, b):
         return self.syn.mul(a, b)
+
+    def apply_gate(self, cores, gname, index):
+        from syngular.quantum import gate
+        Y = self.MPS.from_sites([np.array(c) for c in cores]).apply(getattr(gate, gname), index)
+        return np.real(self.arr(Y.to_tensor())), [s.shape[2] for s in Y.sites[:-1]]
+
+    def run_circuit(self, size, ops):
+        from syngular.quantum import Qbit, gate
+        q = Qbit(size)
+        for op in ops:
+            q @= (getattr(gate, op[0]),) + tuple(op[1:])
+        return np.real(q.to_tensor())
 
     def sites(self, obj):
         return [s.detach().cpu().numpy() for s in obj.sites]

@@ -273,6 +273,40 @@ def case_readme_chain(be, from_dense=False):
     close(be.scalar(Z | X), g["Z16_X"], rtol=1e-9, what="(Z>>16 canonical)|X")
 
 
+QUANTUM_CIRCUITS = {
+    "bell": (2, [("H", 0), ("CX", 0, 1)]),
+    "ghz4": (4, [("H", 0), ("CX", 0, 1), ("CX", 1, 2), ("CX", 2, 3)]),
+    "x_chain": (5, [("X", 0), ("X", 3), ("CX", 3, 4), ("SWAP", 1)]),
+    "cx_far_02": (3, [("X", 0), ("CX", 0, 2)]),
+    "cx_far_20": (3, [("X", 2), ("CX", 2, 0)]),
+    "cx_far_03": (4, [("X", 0), ("CX", 0, 3)]),
+    "h_layer": (4, [("H", 0), ("H", 1), ("H", 2), ("H", 3), ("Z", 1), ("CX", 1, 2)]),
+    "toffoli_110": (3, [("X", 0), ("X", 1), ("TOFFOLI", 0)]),
+    "toffoli_100": (3, [("X", 0), ("TOFFOLI", 0)]),
+}
+
+
+def case_mps_apply_gates(be):
+    """MatrixProductState.apply (MPS:487-534): the bond is frozen at its existing value; goldens from the reference."""
+    g = load("quantum")
+    cores = chain(g, "apply/X")
+    for name, gname, i in (("cx0", "CX", 0), ("swap2", "SWAP", 2), ("h4", "H", 4), ("tof1", "TOFFOLI", 1), ("x0", "X", 0),
+                           ("cx3", "CX", 3), ("tof2", "TOFFOLI", 2), ("z2", "Z", 2)):
+        dense, bonds = be.apply_gate(cores, gname, i)
+        close(dense, g["apply/%s_dense" % name], what="apply " + name)
+        assert list(bonds) == [int(b) for b in g["apply/%s_bonds" % name]]
+
+
+def case_quantum_circuits(be):
+    """Qbit registers (quantum/qbit.py) on real gates: Bell (test_quantum.py:155-163), GHZ-4, non-adjacent CX through the
+    reference's swap_in / swap_out logic, Toffoli truth table rows (readme.md:97-117)."""
+    g = load("quantum")
+    for name, (size, ops) in QUANTUM_CIRCUITS.items():
+        close(be.run_circuit(size, ops), g["circuit/%s" % name], rtol=1e-12, what="circuit " + name)
+    close(be.run_circuit(2, QUANTUM_CIRCUITS["bell"][1]), np.array([1, 0, 0, 1]) / np.sqrt(2), rtol=1e-12, what="Bell state")
+    close(be.run_circuit(3, QUANTUM_CIRCUITS["toffoli_110"][1]), np.eye(8)[7], rtol=1e-12, what="Toffoli |110> -> |111>")
+
+
 ALL_CASES = [
     case_matmul_known_answers,
     case_mps_dot_compress_normalize,
@@ -284,4 +318,6 @@ ALL_CASES = [
     case_random_chain_r1,
     case_random_chain_r2,
     case_readme_chain,
+    case_mps_apply_gates,
+    case_quantum_circuits,
 ]
