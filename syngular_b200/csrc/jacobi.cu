@@ -44,6 +44,40 @@ __device__ __forceinline__ void problem_barrier(unsigned* ctr, unsigned target) 
     __syncthreads();
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) for the block exchange ---------------------------------------------------
+// A block (w rows of n doubles) is contiguous in global memory when ld == n, so one bulk copy per block moves it between L2
+// and shared memory with no register staging and no per-thread address math; completion is tracked by an mbarrier (loads)
+// and by the bulk async-group (stores).  Bulk copies bypass L1, which is what the cross-CTA exchange needs.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (unsigned spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();           // a lost transaction would otherwise hang the GPU
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---- fast scalar math for the rotation ----------------------------------------------------------------------------
 // FP64 division and sqrt are long dependent software sequences; the rotation sits on the critical path of every Jacobi
 // round, so it is built from the MUFU seeds (rcp / rsqrt.approx.f64, 2^-22) plus Newton steps.  Only c needs full
@@ -181,6 +215,7 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     extern __shared__ __align__(16) double rows[];   // [2w][LDS]
     __shared__ int s_rot;
     __shared__ double s_nrm[32];
+    __shared__ __align__(8) uint64_t s_mbar;
     const int LDS = (n + 1) & ~1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = blockIdx.x;
@@ -192,6 +227,13 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     const int Mr = NB - 1;         // outer rounds per sweep
     const bool vec2 = ((n & 1) == 0) && ((ld & 1) == 0) && ((((uintptr_t)G) & 15) == 0);
     const bool full = (n == 32 * NREG);
+    // TMA path: multi-CTA problem, every block full, rows 16-byte aligned and dense in shared memory
+    const bool tma = (P > 1) && vec2 && (n == 2 * P * w) && (LDS == n);
+    uint32_t mbar_phase = 0;
+    if (tma) {
+        if (tid == 0) mbar_init(&s_mbar, 1);
+        __syncthreads();
+    }
 
     // blocks travel through L2 (ld.cg / st.cg: L1 is not coherent across the CTAs of a problem), 16 bytes per thread
     auto load_block = [&](int blk, int half) {
@@ -243,7 +285,22 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
             if (P == 1) { b0 = 0; b1 = 1; }
             else if (p == 0) { b0 = NB - 1; b1 = t % Mr; }
             else { b0 = (t + p) % Mr; b1 = (t - p + Mr) % Mr; }
-            if (P > 1 || sweep == 0) {
+            if (tma) {
+                if (tid == 0) {
+                    const uint32_t row_bytes = (uint32_t)n * 8u, blk_bytes = (uint32_t)w * row_bytes;
+                    fence_proxy_async();
+                    mbar_expect_tx(&s_mbar, 2u * blk_bytes);
+                    const int blks[2] = {b0, b1};
+                    for (int h = 0; h < 2; ++h) {
+                        const double* src = G + (int64_t)blks[h] * w * ld;
+                        double* dst = rows + h * w * LDS;
+                        if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
+                        else for (int r = 0; r < w; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
+                    }
+                }
+                mbar_wait(&s_mbar, mbar_phase);
+                mbar_phase ^= 1u;
+            } else if (P > 1 || sweep == 0) {
                 load_block(b0, 0);
                 load_block(b1, 1);
                 __syncthreads();
@@ -297,7 +354,24 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                     __syncthreads();
                 }
             }
-            if (P > 1) {
+            if (tma) {
+                fence_proxy_async();               // every thread: its st.shared results become visible to the async proxy
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t row_bytes = (uint32_t)n * 8u, blk_bytes = (uint32_t)w * row_bytes;
+                    const int blks[2] = {b0, b1};
+                    for (int h = 0; h < 2; ++h) {
+                        double* dst = G + (int64_t)blks[h] * w * ld;
+                        const double* src = rows + h * w * LDS;
+                        if (ld == n) bulk_s2g(dst, src, blk_bytes);
+                        else for (int r = 0; r < w; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
+                    }
+                    bulk_commit_wait_all();        // writes complete (and shared memory free) before the barrier
+                    fence_proxy_async();
+                }
+                bar_target += P;
+                problem_barrier(bar, bar_target);
+            } else if (P > 1) {
                 store_block(b0, 0);
                 store_block(b1, 1);
                 bar_target += P;
