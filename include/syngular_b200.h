@@ -76,8 +76,11 @@ int syn_copy_strided_f64(const double* src, int64_t s_rs, int64_t s_cs, int64_t 
  *      its only SVD/eigh are dead code -- trash/mpo.py:59-190, experimental/layers.py:241-325, MPO:228) ------------- */
 /* In place: rows of G (n x n, row-major ld, n <= 1024) are rotated until mutually orthogonal: row_i -> sigma_i u_i^T. */
 size_t syn_jacobi_ctrl_bytes(int batch, int max_sweeps);
+int    syn_jacobi_ctrl_stride(int max_sweeps);   /* 32-bit words per problem in ctrl; word [max_sweeps + 1] = sweeps used */
+/* null_rel: pairs of rows whose norms are both below null_rel * (largest row norm) are left alone (they fall under the rank
+ * threshold of the finalize step); 0 disables the test. */
 int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes,
-                        int max_sweeps, double tol, void* stream);
+                        int max_sweeps, double tol, double null_rel, void* stream);
 /* Sort sigma descending, normalise rows into Ut, apply chi_max / relative cutoff on the device.
  * info[2*b] = kept rank, winfo[2*b] = discarded weight sum_{k>=kept} sigma_k^2, winfo[2*b+1] = sigma_0.
  * sqrt_mode = 1 when G was a Gram matrix M E M^T (rows are lambda_i u_i^T, sigma_i = sqrt(lambda_i)). */

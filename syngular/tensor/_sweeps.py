@@ -358,7 +358,7 @@ def right_environments(X, W):
     return E
 
 
-def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=1e-7):
+def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
     """`W @ X` + optimal (SVD) rounding by the density-matrix algorithm: right environments, then a left-to-right sweep that
     diagonalises M E M^T (one-sided Jacobi) -- mathematically the truncation of round_svd(site_mpo_mps(...)) but every matrix
     stays <= (chi d) x D.  Eigenvalues are squared singular values, so values below ~1e-8 sigma_0 are noise: rank_tol."""
@@ -377,7 +377,7 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=1e-7):
         nA = s * o
         if nA > 1024:
             raise NotImplementedError("density-matrix rounding needs chi*d <= 1024 (got %d)" % nA)
-        ops.jacobi_rows(A)
+        ops.jacobi_rows(A, null_rel=rank_tol * rank_tol)        # eigenvalue floor = (singular-value floor)^2
         Ut, sigma, info, winfo = ops.jacobi_finalize(A, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True)
         keep = int(info[0].item())
         trunc.sigma.append(sigma); trunc.keep.append(keep); trunc.discarded.append(winfo[0].item())

@@ -135,7 +135,7 @@ def jacobi_tol(n):
     return 4.0 * (float(n) ** 0.5) * 1.1102230246251565e-16
 
 
-def jacobi_rows(G, max_sweeps=40, tol=None):
+def jacobi_rows(G, max_sweeps=40, tol=None, null_rel=1e-14):
     """In place: G (n x n contiguous, or batched) <- J G with mutually orthogonal rows (one-sided Jacobi)."""
     require_cuda_f64(G)
     batched = G.dim() == 3
@@ -145,7 +145,7 @@ def jacobi_rows(G, max_sweeps=40, tol=None):
     cb = lib.syn_jacobi_ctrl_bytes(nb, max_sweeps)
     ctrl = workspace(cb, G.device, tag="jacobi_ctrl")
     rc = lib.syn_jacobi_rows_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(ctrl), _sz(ctrl.numel() * 8),
-                                 _i32(max_sweeps), _dbl(tol if tol is not None else jacobi_tol(n)), stream_ptr())
+                                 _i32(max_sweeps), _dbl(tol if tol is not None else jacobi_tol(n)), _dbl(null_rel), stream_ptr())
     check(rc, "syn_jacobi_rows_f64")
     global _last_jacobi
     _last_jacobi = (ctrl, max_sweeps, nb)
@@ -158,7 +158,8 @@ _last_jacobi = None
 def jacobi_sweeps_used():
     """Sweeps the last jacobi_rows call needed, per batch member (diagnostic; synchronises)."""
     ctrl, max_sweeps, nb = _last_jacobi
-    words = ctrl.view(torch.int32)[: nb * (max_sweeps + 2)].reshape(nb, max_sweeps + 2)
+    stride = lib.syn_jacobi_ctrl_stride(int(max_sweeps))
+    words = ctrl.view(torch.int32)[: nb * stride].reshape(nb, stride)
     return words[:, max_sweeps + 1].tolist()
 
 
