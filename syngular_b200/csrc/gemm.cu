@@ -99,7 +99,21 @@ struct OperandLoader {
     }
 };
 
-template <class C, bool A_ALONG_M, bool B_ALONG_N, int VEC>
+// TMA staging: one cp.async.bulk (UBLKCP) per contiguous tile line, completion on the stage's mbarrier.  Eligible when the
+// tile is interior (M, N, K multiples of the tile) and every line is one contiguous, 16-byte aligned run in HBM.
+template <class C, int ROWS, bool ALONG_ROWS>
+struct BulkLoader {
+    static constexpr int STRIDE = ALONG_ROWS ? (ROWS + C::PAD) : (C::BK + C::PAD);
+    static constexpr int LINES = ALONG_ROWS ? C::BK : ROWS;
+    static constexpr uint32_t LINE_BYTES = (uint32_t)((ALONG_ROWS ? ROWS : C::BK) * sizeof(double));
+    // source of line `l` of the tile whose first row is row0 and first k is k0
+    __device__ __forceinline__ static const double* src(const double* base, const syn_index_t& rows_ix, const syn_index_t& k_ix, int row0,
+                                                        int k0, int l) {
+        return ALONG_ROWS ? base + idx2(rows_ix, row0) + idx2(k_ix, k0 + l) : base + idx2(rows_ix, row0 + l) + idx2(k_ix, k0);
+    }
+};
+
+template <class C, bool A_ALONG_M, bool B_ALONG_N, int VEC, bool TMA>
 __global__ void __launch_bounds__(C::THREADS)
 gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const double* __restrict__ B,
                 double* __restrict__ Cmat, int tiles_m, int tiles_n, int c_vec) {
@@ -130,10 +144,34 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
     B += idx2(d.b_b, batch);
     Cmat += idx2(d.c_b, batch);
 
+    using TA = BulkLoader<C, C::BM, A_ALONG_M>;
+    using TB = BulkLoader<C, C::BN, B_ALONG_N>;
+    __shared__ __align__(8) uint64_t full_bar[C::STAGES];
     LA la;
     LB lb;
-    la.init(d.a_m, m0, d.M, tid);
-    lb.init(d.b_n, n0, d.N, tid);
+    if constexpr (!TMA) {
+        la.init(d.a_m, m0, d.M, tid);
+        lb.init(d.b_n, n0, d.N, tid);
+    } else {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < C::STAGES; s++) mbar_init(&full_bar[s], TA::LINES + TB::LINES);
+        }
+        __syncthreads();
+    }
+    // TMA producer side: every tile line is owned by one thread, which arms the stage barrier with its bytes and issues the copy
+    auto tma_fill = [&](int stage, int k0) {
+        for (int line = tid; line < TA::LINES + TB::LINES; line += C::THREADS) {
+            if (line < TA::LINES) {
+                mbar_expect_tx(&full_bar[stage], TA::LINE_BYTES);
+                bulk_g2s(sA + stage * LA::TILE_ELEMS + line * TA::STRIDE, TA::src(A, d.a_m, d.a_k, m0, k0, line), TA::LINE_BYTES, &full_bar[stage]);
+            } else {
+                const int l = line - TA::LINES;
+                mbar_expect_tx(&full_bar[stage], TB::LINE_BYTES);
+                bulk_g2s(sB + stage * LB::TILE_ELEMS + l * TB::STRIDE, TB::src(B, d.b_n, d.b_k, n0, k0, l), TB::LINE_BYTES, &full_bar[stage]);
+            }
+        }
+    };
 
     const int KT = (d.K + C::BK - 1) / C::BK;
 
@@ -146,23 +184,35 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
 #pragma unroll
     for (int s = 0; s < C::STAGES - 1; s++) {
         if (s < KT) {
-            la.load(sA + s * LA::TILE_ELEMS, A, d.a_k, s * C::BK, d.K);
-            lb.load(sB + s * LB::TILE_ELEMS, B, d.b_k, s * C::BK, d.K);
+            if constexpr (TMA) {
+                tma_fill(s, s * C::BK);
+            } else {
+                la.load(sA + s * LA::TILE_ELEMS, A, d.a_k, s * C::BK, d.K);
+                lb.load(sB + s * LB::TILE_ELEMS, B, d.b_k, s * C::BK, d.K);
+            }
         }
-        cp_async_commit();
+        if constexpr (!TMA) cp_async_commit();
     }
 
     for (int kt = 0; kt < KT; kt++) {
-        cp_async_wait<C::STAGES - 2>();
+        if constexpr (TMA) {
+            mbar_wait(&full_bar[kt % C::STAGES], (uint32_t)((kt / C::STAGES) & 1));
+        } else {
+            cp_async_wait<C::STAGES - 2>();
+        }
         __syncthreads();
         {
             int nk = kt + C::STAGES - 1;
             if (nk < KT) {
                 int s = nk % C::STAGES;
-                la.load(sA + s * LA::TILE_ELEMS, A, d.a_k, nk * C::BK, d.K);
-                lb.load(sB + s * LB::TILE_ELEMS, B, d.b_k, nk * C::BK, d.K);
+                if constexpr (TMA) {
+                    tma_fill(s, nk * C::BK);
+                } else {
+                    la.load(sA + s * LA::TILE_ELEMS, A, d.a_k, nk * C::BK, d.K);
+                    lb.load(sB + s * LB::TILE_ELEMS, B, d.b_k, nk * C::BK, d.K);
+                }
             }
-            cp_async_commit();
+            if constexpr (!TMA) cp_async_commit();
         }
         const double* a_s = sA + (kt % C::STAGES) * LA::TILE_ELEMS;
         const double* b_s = sB + (kt % C::STAGES) * LB::TILE_ELEMS;
@@ -192,7 +242,7 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
                 for (int j = 0; j < C::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
         }
     }
-    cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
 
     // epilogue: thread owns C[row = g][col = 2t, 2t+1] of every 8x8 tile
     const double alpha = d.alpha, beta = d.beta;
@@ -245,12 +295,12 @@ static int gemm_env_cfg() {   // experiment knob: SYN_GEMM_CFG=L|W|S forces a ti
     return v;
 }
 
-template <class C, bool AM, bool BN, int VEC>
+template <class C, bool AM, bool BN, int VEC, bool TMA = false>
 static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, int c_vec, cudaStream_t st) {
     using LA = OperandLoader<C, C::BM, AM, VEC>;
     using LB = OperandLoader<C, C::BN, BN, VEC>;
     constexpr size_t smem = (size_t)C::STAGES * (LA::TILE_ELEMS + LB::TILE_ELEMS) * sizeof(double);
-    auto kern = gemm_f64_kernel<C, AM, BN, VEC>;
+    auto kern = gemm_f64_kernel<C, AM, BN, VEC, TMA>;
     static bool configured = false;
     if (!configured) {
         SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -266,11 +316,34 @@ static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* 
     return launch_status("gemm_f64_kernel");
 }
 
+static bool gemm_env_tma() {   // SYN_GEMM_TMA=0 disables the TMA-staged variant (A/B comparisons)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SYN_GEMM_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+// can every line of a (rows x BK) tile be fetched by one bulk copy?  (`along`: is the line along this index?)
+static bool tma_line_ok(const syn_index_t& along, int ext, int tile) {
+    return along.inner == 1 && ext % tile == 0 && (along.div >= ext || along.div % tile == 0);
+}
+
+template <class C>
+static bool tma_eligible(const syn_gemm_desc_t& d, bool am, bool bn, int vec) {
+    if (!gemm_env_tma() || vec != 2) return false;                       // vec == 2 already implies 16-byte aligned, even offsets
+    if (C::BM * C::BN < 128 * 128) return false;                         // measured: small tiles (256-512 B lines) are faster with LDGSTS
+    if (d.M % C::BM || d.N % C::BN || d.K % C::BK) return false;
+    const bool a_ok = am ? tma_line_ok(d.a_m, d.M, C::BM) : tma_line_ok(d.a_k, d.K, C::BK);
+    const bool b_ok = bn ? tma_line_ok(d.b_n, d.N, C::BN) : tma_line_ok(d.b_k, d.K, C::BK);
+    return a_ok && b_ok;
+}
+
 template <class C>
 static int dispatch_layout(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, bool am, bool bn, int vec,
                            int c_vec, cudaStream_t st) {
+    const bool tma = tma_eligible<C>(d, am, bn, vec);
 #define SYN_GEMM_CASE(AM, BN)                                                                  \
     if (am == AM && bn == BN) {                                                                \
+        if (tma) return launch_gemm<C, AM, BN, 2, true>(d, A, B, Cm, c_vec, st);               \
         return vec == 2 ? launch_gemm<C, AM, BN, 2>(d, A, B, Cm, c_vec, st)                    \
                         : launch_gemm<C, AM, BN, 1>(d, A, B, Cm, c_vec, st);                   \
     }
@@ -320,7 +393,7 @@ int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double*
 
     // tile choice: the large tile when it still fills the machine, else the small one
     long long big_tiles = (long long)((d.M + 127) / 128) * ((d.N + 127) / 128) * d.batch;
-    bool use_large = (d.M > 64 && d.N > 64) && big_tiles >= (long long)sm_count();
+    bool use_large = (d.M > 64 && d.N > 64) && big_tiles * 5 >= (long long)sm_count() * 4;   // >= 80% of the SMs get a 128x128 tile
     const int forced = gemm_env_cfg();
     if (forced == 1) return dispatch_layout<CfgL>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     if (forced == 2) return dispatch_layout<CfgW>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);

@@ -44,40 +44,6 @@ __device__ __forceinline__ void problem_barrier(unsigned* ctr, unsigned target) 
     __syncthreads();
 }
 
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) for the block exchange ---------------------------------------------------
-// A block (w rows of n doubles) is contiguous in global memory when ld == n, so one bulk copy per block moves it between L2
-// and shared memory with no register staging and no per-thread address math; completion is tracked by an mbarrier (loads)
-// and by the bulk async-group (stores).  Bulk copies bypass L1, which is what the cross-CTA exchange needs.
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (unsigned spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1u << 26)) __trap();           // a lost transaction would otherwise hang the GPU
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_all() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
 // ---- fast scalar math for the rotation ----------------------------------------------------------------------------
 // FP64 division and sqrt are long dependent software sequences; the rotation sits on the critical path of every Jacobi
 // round, so it is built from the MUFU seeds (rcp / rsqrt.approx.f64, 2^-22) plus Newton steps.  Only c needs full
