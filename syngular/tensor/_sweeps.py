@@ -329,8 +329,10 @@ def round_svd(sites, chi_max, cutoff=0.0, canonicalize=True):
 
 
 def right_environments(X, W):
-    """E[k] = Gram matrix of the product chain to the right of bond k (D_k x D_k, index (b,r) b-major), k = 1..n-1,
-    without forming product cores: four strided GEMMs per site (finished form of MPO:193-260)."""
+    """E[k] = Gram matrix of the product chain to the right of bond k (D_k x D_k), k = 1..n-1, without forming product cores:
+    four strided GEMMs per site (finished form of MPO:193-260).
+    Storage: rows indexed (b, r) MPS-bond major, COLUMNS indexed (r', b') MPO-bond major -- so that the last GEMM of every
+    site writes unit-stride rows (its batch index l' becomes the outer column index) and every consumer reads unit strides."""
     n = len(X)
     E = [None] * (n + 1)
     E[n] = torch.ones((1, 1), dtype=F64, device=X[0].device)
@@ -339,23 +341,49 @@ def right_environments(X, W):
         a, i, b = Xk.shape
         l, _, o, r = Wk.shape
         D = b * r
-        # P1[(a,i),(r,y)] = sum_b X[(a,i),b] E[b,(r,y)]
+        # P1[(a,i),(r,y)] = sum_b X[(a,i),b] E[b,(r,y)]                       y = (r', b')
         P1 = empty(a, i, r, D)
         ops.gemm(Xk, En, P1, M=a * i, N=r * D, K=b, a_m=b, a_k=1, b_k=r * D, b_n=1, c_m=r * D, c_n=1)
-        # P2[a,(l,o),y] = sum_{(i,r)} W[l,i,o,r] P1[a,(i,r),y]       batch over a
+        # P2[a,(l,o),y] = sum_{(i,r)} W[l,i,o,r] P1[a,(i,r),y]                batch over a
         P2 = empty(a, l, o, D)
         ops.gemm(Wk, P1, P2, M=l * o, N=D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=1, c_m=D, c_n=1,
                  batch=a, a_b=0, b_b=i * r * D, c_b=l * o * D)
-        # Z[(a,l), l', i', b'] = sum_{(o,r')} P2[(a,l), o, b', r'] W[l', i', o, r']      batch over (a,l)
+        # Z[(a,l), l', i', b'] = sum_{(o,r')} P2[(a,l), o, (r',b')] W[l', i', o, r']  batch over (a,l)
         Z = empty(a * l, l, i, b)
-        ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=r, a_k=(b * r, 1, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
+        ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=1, a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
                  batch=a * l, a_b=o * D, b_b=0, c_b=l * i * b)
-        # E[(a,l),(a',l')] = sum_{(i',b')} Z[(a,l), l', (i',b')] X[a',(i',b')]           batch over l'
-        Ek = empty(a * l, a * l)
-        ops.gemm(Z, Xk, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=l,
-                 batch=l, a_b=i * b, b_b=0, c_b=1)
+        # E[(a,l),(l',a')] = sum_{(i',b')} Z[(a,l), l', (i',b')] X[a',(i',b')]        batch over l'
+        Ek = empty(a * l, l * a)
+        ops.gemm(Z, Xk, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
+                 batch=l, a_b=i * b, b_b=0, c_b=a)
         E[k] = Ek
     return E
+
+
+_ONES = {}
+
+
+def gram_with_environment(M2, E, b, r):
+    """A = M2 E M2^T for an unfolding M2 (rows x (b,r), MPS-bond major) and an environment stored as in right_environments
+    (rows (b,r), columns (r',b')).  M2 E is written with its columns permuted back to (b',r') on the fly (two-level C index),
+    and the final rows x rows product, whose K = D is long and whose output is small, is split 8 ways along K so that it
+    fills the machine; the partial sums are added by one more (tiny) GEMM."""
+    rows, D = M2.shape
+    ME = empty(rows, D)
+    ops.gemm(M2, E, ME, M=rows, N=D, K=D, a_m=M2.stride(0), a_k=1, b_k=E.stride(0), b_n=1, c_m=D, c_n=(1, r, b))
+    split = 8 if (D % (8 * 32) == 0 and D >= 2048) else 1
+    if split == 1:
+        return ops.matmul(ME, M2.t())
+    kc = D // split
+    part = empty(split, rows, rows)
+    ops.gemm(ME, M2, part, M=rows, N=rows, K=kc, a_m=D, a_k=1, b_k=1, b_n=M2.stride(0), c_m=rows, c_n=1,
+             batch=split, a_b=kc, b_b=kc, c_b=rows * rows)
+    ones = _ONES.get((split, M2.device))
+    if ones is None:
+        ones = _ONES[(split, M2.device)] = torch.ones((1, split), dtype=F64, device=M2.device)
+    A = empty(rows, rows)
+    ops.gemm(ones, part, A, M=1, N=rows * rows, K=split, a_m=split, a_k=1, b_k=rows * rows, b_n=1, c_m=rows * rows, c_n=1)
+    return A
 
 
 def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
@@ -372,8 +400,7 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
         s, o, D = M.shape
         b, r = X[k].shape[2], W[k].shape[3]
         M2 = M.reshape(s * o, D)
-        ME = ops.matmul(M2, E[k + 1])
-        A = ops.matmul(ME, M2.t())
+        A = gram_with_environment(M2, E[k + 1], b, r)
         nA = s * o
         if nA > 1024:
             raise NotImplementedError("density-matrix rounding needs chi*d <= 1024 (got %d)" % nA)

@@ -28,7 +28,7 @@ def _norm2_of_product(X, W):
     T = torch.ones((1, 1, 1), dtype=torch.float64, device=X[0].device)
     M0 = sw.contract_carry(T, X[0], W[0])                      # (1, o, D1)
     M2 = M0.reshape(M0.shape[1], M0.shape[2])
-    return float(ops.matmul(ops.matmul(M2, E[1]), M2.t()).diagonal().sum().item())
+    return float(sw.gram_with_environment(M2, E[1], X[0].shape[2], W[0].shape[3]).diagonal().sum().item())
 
 
 def _gram_err(core):
