@@ -327,7 +327,9 @@ def run_ours(args):
         peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
         achieved = g_fl / (g_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": 356.5e6,
+                    "traffic_note": "dram__bytes_read+write of ONE launch of the largest GEMM of the sweep (512 x 65536 x 256: 402.7 MB algorithmic), "
+                                    "ncu --set full capture profiles/r01_gemm_p1_ncu_summary.txt; `achieved` aggregates all GEMM launches of a sweep",
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this process (MEASURED_PEAKS.json has no FP64 entry); DMMA pipe microbench: 37.1",
                     "launches_per_sweep": len(prof), "flops_per_sweep": g_fl, "algorithmic_bytes_per_sweep": g_by,
                     "kernel_ms_per_sweep": g_ms, "share_of_step": g_ms / sweep_ms}
