@@ -32,6 +32,10 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // barrier among the P CTAs of one problem (all co-resident: cooperative launch)
 __device__ __forceinline__ void problem_barrier(unsigned* ctr, unsigned target) {
     __syncthreads();
@@ -189,6 +193,8 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     G += (int64_t)blockIdx.y * bs;
     unsigned* bar = ctrl + (int64_t)blockIdx.y * ctrl_stride;
     unsigned* flags = bar + 1;
+    const int ctrl_base = (max_sweeps + 7) & ~1;      // words before the per-block version counters
+    unsigned* ver = bar + ctrl_base;                  // ver[blk] = number of outer rounds block blk has been through
     unsigned bar_target = 0;
     const int NB = 2 * P;          // number of row blocks
     const int Mr = NB - 1;         // outer rounds per sweep
@@ -248,7 +254,7 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     // among themselves for ever: their mutual cosines are O(1) noise)
     double null2 = 0.0;
     if (null_rel2 > 0.0) {
-        unsigned long long* gmax = reinterpret_cast<unsigned long long*>(bar + ctrl_stride - 2);
+        unsigned long long* gmax = reinterpret_cast<unsigned long long*>(bar + ctrl_base - 2);
         double local = 0.0;
         for (int r = p * 2 * w + warp; r < n && r < (p + 1) * 2 * w; r += WARPS) {
             double sacc = 0.0;
@@ -279,6 +285,13 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
             if (tma) {
                 if (tid == 0) {
                     const uint32_t row_bytes = (uint32_t)n * 8u, blk_bytes = (uint32_t)w * row_bytes;
+                    // point-to-point hand-over instead of a grid barrier: a block is ready when the CTA that held it in the
+                    // previous round has published its version (every block takes part in every round)
+                    const unsigned need = (unsigned)(sweep * Mr + t);
+                    for (unsigned spin = 0; ld_acquire_u32(ver + b0) < need || ld_acquire_u32(ver + b1) < need; ++spin) {
+                        if (spin > (1u << 26)) __trap();
+                        __nanosleep(20);
+                    }
                     fence_proxy_async();
                     mbar_expect_tx(&s_mbar, 2u * blk_bytes);
                     const int blks[2] = {b0, b1};
@@ -357,11 +370,13 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                         if (ld == n) bulk_s2g(dst, src, blk_bytes);
                         else for (int r = 0; r < w; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
                     }
-                    bulk_commit_wait_all();        // writes complete (and shared memory free) before the barrier
+                    bulk_commit_wait_all();        // writes complete (and shared memory free) before they are published
                     fence_proxy_async();
+                    __threadfence();
+                    const unsigned done = (unsigned)(sweep * Mr + t) + 1u;
+                    st_release_u32(ver + b0, done);
+                    st_release_u32(ver + b1, done);
                 }
-                bar_target += P;
-                problem_barrier(bar, bar_target);
             } else if (P > 1) {
                 store_block(b0, 0);
                 store_block(b1, 1);
@@ -539,7 +554,7 @@ static int launch_jacobi(double* G, int64_t ld, int64_t bs, int n, int batch, co
     return 0;
 }
 
-int jacobi_ctrl_stride(int max_sweeps) { return (max_sweeps + 7) & ~1; }   // words: barrier, flags[max_sweeps], sweeps used, pad, 64-bit max norm
+int jacobi_ctrl_stride(int max_sweeps) { return ((max_sweeps + 7) & ~1) + 128; }   // words: barrier, flags[max_sweeps], sweeps used, pad, 64-bit max norm, 128 block versions
 size_t jacobi_ctrl_bytes(int batch, int max_sweeps) { return (size_t)batch * jacobi_ctrl_stride(max_sweeps) * sizeof(unsigned); }
 
 int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes, int max_sweeps, double tol,
