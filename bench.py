@@ -300,7 +300,17 @@ def run_ours(args):
     c4_flops = sum(4.0 * 2 * a * b * max(a, b) for a, b in zip([1] + list(bonds4), list(bonds4) + [1])) * B_total
     c4_bytes = 2 * 8.0 * sum(a * 2 * b for a, b in zip([1] + list(bonds4), list(bonds4) + [1])) * B_total
     ov_ok = bool(torch.isfinite(ov).all().item()) and ov.numel() == B_total
-    del A4, B4
+    # configs[3] (ii): one shared MPO (chi_W = 4) applied to the states and rounded back to chi = 64, both roundings, on the
+    # first 256 states of this rank's shard (the rate is per state; the full shard just repeats it)
+    from syngular.tensor import MatrixProductOperator as MPO4
+    W4 = MPO4.random_cores((2,) * n4, (2,) * n4, capped_bonds(n4, 4, 4)[1:-1], seed=7).sites
+    sub = BMPS([c[:256] for c in A4.sites])
+    sub.apply_round(W4, 64); sub.apply_round_svd(W4, 64, chunk=256)
+    ms_c4q = timed(lambda: sub.apply_round(W4, 64), 2)
+    ms_c4s = timed(lambda: sub.apply_round_svd(W4, 64, chunk=256), 2)
+    c4_apply_qr = world * 256 * 2 / (ms_c4q * 1e-3)
+    c4_apply_svd = world * 256 * 2 / (ms_c4s * 1e-3)
+    del A4, B4, sub
 
     line = None
     if rank == 0:
@@ -358,6 +368,8 @@ def run_ours(args):
                                  "float64; %.2f TFLOP/s FP64, %.0f GB/s of core traffic; gathered %s" % (
                                      world, c4_flops / (ms_c4 / c4_reps * 1e-3) / 1e12, c4_bytes / (ms_c4 / c4_reps * 1e-3) / 1e9,
                                      "ok" if ov_ok else "BAD"),
+                      "c4_apply_qr_round_states_per_s": c4_apply_qr, "c4_apply_svd_round_states_per_s": c4_apply_svd,
+                      "c4_apply_note": "configs[3](ii): shared MPO chi_W=4 applied + rounded to chi=64, batched over 256 states per rank",
                       "qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),
                       "qr_round_note": "reference-semantic `>>` (QR truncation, fused apply+round) on the same chain"},
         }

@@ -96,3 +96,79 @@ class BatchedMatrixProductState:
                      batch=B, a_b=s * o * kept, b_b=s * o * b * r, c_b=kept * r * b)
             T = Tn
         return BatchedMatrixProductState(out)
+
+    # ---- MPO application + optimal (SVD) rounding for the whole batch -------------------------------------------------
+    def apply_round_svd(self, mpo, chi, chunk=512):
+        """`W @ X_b` + SVD rounding to bond `chi` for every state with ONE shared MPO: the density-matrix algorithm of the
+        single-chain path (syngular.tensor._sweeps.apply_round_dm), every GEMM / Jacobi launch batched over the states.
+        Fixed-rank variant: every member keeps exactly min(chi, rows, D, right space) vectors per bond (no per-member cutoff), so the
+        results stack.  Environments cost B * D^2 doubles per site, hence the chunking over the batch."""
+        W = mpo.sites if hasattr(mpo, "sites") else mpo
+        outs = None
+        for lo in range(0, self.batch, chunk):
+            part = BatchedMatrixProductState([c[lo:lo + chunk] for c in self.sites])._apply_round_svd_chunk(W, chi)
+            outs = [[c] for c in part] if outs is None else [o + [c] for o, c in zip(outs, part)]
+        return BatchedMatrixProductState([torch.cat(o, dim=0) if len(o) > 1 else o[0] for o in outs])
+
+    def _apply_round_svd_chunk(self, W, chi):
+        B, n = self.batch, self.sites_number
+        dev = self.sites[0].device
+
+        def empty(*shape):
+            return torch.empty(shape, dtype=F64, device=dev)
+
+        # right environments, rows (b,r), columns (r',b')   (see _sweeps.right_environments)
+        E = [None] * (n + 1)
+        E[n] = torch.ones((B, 1, 1), dtype=F64, device=dev)
+        for k in range(n - 1, 0, -1):
+            X, Wk, En = self.sites[k], W[k], E[k + 1]
+            _, a, i, b = X.shape
+            l, _, o, r = Wk.shape
+            D = b * r
+            P1 = empty(B, a, i, r, D)
+            ops.gemm(X, En, P1, M=a * i, N=r * D, K=b, a_m=b, a_k=1, b_k=r * D, b_n=1, c_m=r * D, c_n=1,
+                     batch=B, a_b=a * i * b, b_b=D * D, c_b=a * i * r * D)
+            P2 = empty(B, a, l, o, D)
+            ops.gemm(Wk, P1, P2, M=l * o, N=D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=1, c_m=D, c_n=1,
+                     batch=B * a, a_b=0, b_b=i * r * D, c_b=l * o * D)
+            Z = empty(B, a * l, l, i, b)
+            ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=1, a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
+                     batch=B * a * l, a_b=o * D, b_b=0, c_b=l * i * b)
+            Ek = empty(B, a * l, l * a)
+            ops.gemm(Z, X, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
+                     batch=B * l, a_b=(a * l * l * i * b, i * b, l), b_b=(a * i * b, 0, l), c_b=(a * l * a * l, a, l))
+            E[k] = Ek
+        T = torch.ones((B, 1, 1, 1), dtype=F64, device=dev)            # carry (B, s, l, a)
+        out = []
+        for k in range(n):
+            X, Wk = self.sites[k], W[k]
+            _, a, i, b = X.shape
+            l, _, o, r = Wk.shape
+            s, D = T.shape[1], b * r
+            T1 = empty(B, s, l, i, b)
+            ops.gemm(T, X, T1, M=s, N=i * b, K=a, a_m=l * a, a_k=1, b_k=i * b, b_n=1, c_m=l * i * b, c_n=1,
+                     batch=B * l, a_b=(s * l * a, a, l), b_b=(a * i * b, 0, l), c_b=(s * l * i * b, i * b, l))
+            M = empty(B, s * o, D)
+            ops.gemm(T1, Wk, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
+                     c_m=(o * b * r, r, b), c_n=(b * r, 1, r), batch=B, a_b=s * l * i * b, b_b=0, c_b=s * o * D)
+            if k == n - 1:
+                out.append(M.reshape(B, s, o, D))
+                break
+            rows = s * o
+            ME = empty(B, rows, D)                                     # columns permuted back to (b', r') on the fly
+            ops.gemm(M, E[k + 1], ME, M=rows, N=D, K=D, a_m=D, a_k=1, b_k=D, b_n=1, c_m=D, c_n=(1, r, b),
+                     batch=B, a_b=rows * D, b_b=D * D, c_b=rows * D)
+            A = ops.matmul(ME, M.transpose(1, 2))
+            ops.jacobi_rows(A, null_rel=1e-13)
+            Ut, sigma, info, winfo = ops.jacobi_finalize(A, chi, rank_tol=0.0, sqrt_mode=True)
+            right_dim = 1                                               # dimension of the space to the right of this bond
+            for wj in W[k + 1:]:
+                right_dim = min(right_dim * int(wj.shape[2]), 1 << 30)
+            keep = min(int(chi), rows, D, right_dim)
+            core = ops.copy_strided(Ut[:, :keep, :].transpose(1, 2))   # (B, rows, keep)
+            out.append(core.reshape(B, s, o, keep))
+            Tn = empty(B, keep, r, b)
+            ops.gemm(Ut, M, Tn, M=keep, N=D, K=rows, a_m=rows, a_k=1, b_k=D, b_n=1, c_m=r * b, c_n=(1, b, r),
+                     batch=B, a_b=rows * rows, b_b=rows * D, c_b=keep * r * b)
+            T = Tn
+        return out

@@ -38,3 +38,20 @@ def test_batched_apply_round_matches_oracle():
         assert [c.shape for c in got] == [c.shape for c in ref]
         dr, dg = R.to_dense(ref), R.to_dense(got)
         assert np.max(np.abs(dr - dg)) < 1e-10 * np.max(np.abs(dr))
+
+
+def test_batched_apply_round_svd_matches_oracle():
+    from syngular_b200.batched import BatchedMatrixProductState as BMPS
+    from syngular.tensor import _sweeps as sw
+    from oracle import ref_numpy as R, svd_numpy as S
+    rng = np.random.default_rng(8)
+    B, n, d, chi, chiw, target = 5, 8, 2, 8, 4, 6
+    Xs = [rand_chain(rng, n, d, chi) for _ in range(B)]
+    W = rand_chain(rng, n, d, chiw, phys=2)
+    out = BMPS.from_states(Xs).apply_round_svd([sw.as_core(w) for w in W], target, chunk=2)     # chunk < B: exercises the stitching
+    for b in range(B):
+        ref, _, _ = S.apply_round_svd(Xs[b], W, target)
+        got = [c[b].cpu().numpy() for c in out.sites]
+        assert [c.shape for c in got] == [c.shape for c in ref]
+        dr, dg = R.to_dense(ref), R.to_dense(got)
+        assert np.max(np.abs(dr - dg)) < 1e-10 * np.max(np.abs(dr))
