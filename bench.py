@@ -311,6 +311,16 @@ def run_ours(args):
     c4_apply_qr = world * 256 * 2 / (ms_c4q * 1e-3)
     c4_apply_svd = world * 256 * 2 / (ms_c4s * 1e-3)
     del A4, B4, sub
+    # BASELINE configs[4]: TensorDense forward, MPO (16,16,16)x(16,16,16) bond 16, batch 65536 x 4096, batch-sharded
+    from syngular.layers import TensorDense
+    layer5 = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), seed=5).build()
+    lo5, hi5 = parallel.shard_bounds(65536, rank, world)
+    g5 = torch.Generator(device=dev).manual_seed(500 + rank)
+    x5 = torch.randn((hi5 - lo5, 4096), dtype=torch.float64, device=dev, generator=g5)
+    layer5(x5[:4096])
+    ms_c5 = timed(lambda: layer5(x5), 1)
+    c5_value = 65536 / (ms_c5 * 1e-3)
+    del x5
 
     line = None
     if rank == 0:
@@ -368,6 +378,9 @@ def run_ours(args):
                                  "float64; %.2f TFLOP/s FP64, %.0f GB/s of core traffic; gathered %s" % (
                                      world, c4_flops / (ms_c4 / c4_reps * 1e-3) / 1e12, c4_bytes / (ms_c4 / c4_reps * 1e-3) / 1e9,
                                      "ok" if ov_ok else "BAD"),
+                      "c5_tensordense_samples_per_s": c5_value,
+                      "c5_note": "configs[4] forward in FP64 on the DMMA GEMM (%.1f TFLOP/s); the reference computes in float32 -- a TF32 "
+                                 "tcgen05 kernel is the planned fast path" % (3.78e7 * 65536 / (ms_c5 * 1e-3) / 1e12),
                       "c4_apply_qr_round_states_per_s": c4_apply_qr, "c4_apply_svd_round_states_per_s": c4_apply_svd,
                       "c4_apply_note": "configs[3](ii): shared MPO chi_W=4 applied + rounded to chi=64, batched over 256 states per rank",
                       "qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),

@@ -98,6 +98,9 @@ int syn_kron_site_f64(const double* A, const double* B, double* out, int la, int
 /* out[0] = sum x_i^2 ; x *= 1/sqrt(sumsq[0])   (normalize: np.linalg.norm + in-place divide, MPS:252-256) */
 int syn_sumsq_f64(const double* x, int64_t n, double* out, void* stream);
 int syn_scale_rsqrt_f64(double* x, int64_t n, const double* sumsq, void* stream);
+/* y[r,c] = act(y[r,c] + bias[c]), act 0 = identity, 1 = relu: the `+ bias` / activation epilogue of the TT layer
+ * (layers/TensorDense.py:139-142).  The TT contraction itself is a chain of syn_gemm_f64 calls. */
+int syn_bias_act_f64(double* y, const double* bias, int64_t rows, int cols, int act, void* stream);
 
 #ifdef __cplusplus
 }

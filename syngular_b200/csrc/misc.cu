@@ -105,3 +105,21 @@ extern "C" int syn_scale_rsqrt_f64(double* x, int64_t n, const double* sumsq, vo
     scale_rsqrt_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, sumsq);
     return launch_status("scale_rsqrt_kernel");
 }
+
+// y[r, c] = act(y[r, c] + bias[c])   act: 0 = identity, 1 = relu.  TensorDense epilogue (layers/TensorDense.py:139-142).
+__global__ void bias_act_kernel(double* __restrict__ y, const double* __restrict__ bias, int64_t rows, int cols, int act) {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        double v = y[idx] + (bias ? bias[idx % cols] : 0.0);
+        if (act == 1) v = v > 0.0 ? v : 0.0;
+        y[idx] = v;
+    }
+}
+
+extern "C" int syn_bias_act_f64(double* y, const double* bias, int64_t rows, int cols, int act, void* stream) {
+    using namespace syn;
+    SYN_REQUIRE(rows >= 0 && cols >= 1 && (act == 0 || act == 1), "syn_bias_act_f64: bad arguments");
+    if (rows == 0) return 0;
+    bias_act_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(y, bias, rows, cols, act);
+    return launch_status("bias_act_kernel");
+}

@@ -223,3 +223,13 @@ def scale_rsqrt_(x, ss):
     assert x.is_contiguous()
     check(lib.syn_scale_rsqrt_f64(ptr(x), _i64(x.numel()), ptr(ss), stream_ptr()), "syn_scale_rsqrt_f64")
     return x
+
+
+def bias_act_(y, bias, act="relu"):
+    """In place: y[r, c] = act(y[r, c] + bias[c]) (TensorDense epilogue)."""
+    require_cuda_f64(y)
+    assert y.is_contiguous() and y.dim() == 2
+    code = {"relu": 1, None: 0, "linear": 0, "identity": 0}[act]
+    b = ptr(bias) if bias is not None else None
+    check(lib.syn_bias_act_f64(ptr(y), b, _i64(y.shape[0]), _i32(y.shape[1]), _i32(code), stream_ptr()), "syn_bias_act_f64")
+    return y
