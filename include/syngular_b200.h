@@ -81,6 +81,14 @@ int    syn_jacobi_ctrl_stride(int max_sweeps);   /* 32-bit words per problem in 
  * threshold of the finalize step); 0 disables the test. */
 int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes,
                         int max_sweeps, double tol, double null_rel, void* stream);
+/* FP32 variant of the same kernel and the helpers of the FP32-preconditioned symmetric eigen-solver
+ * (syngular/tensor/_sweeps.py: eigh_gram): FP32 Jacobi gives an approximate eigenbasis, it is re-orthonormalised in FP64
+ * (Newton-Schulz, GEMMs), the matrix is transformed with it, and the FP64 Jacobi finishes in ~3 sweeps instead of ~13. */
+int syn_jacobi_rows_f32(float* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes,
+                        int max_sweeps, double tol, double null_rel, void* stream);
+int syn_cast_f64_f32(const double* src, float* dst, int64_t n, void* stream);
+int syn_rows_to_basis_f32_f64(const float* G, double* U, int n, void* stream);      /* U[i] = G[i] / |G[i]| in FP64 */
+int syn_identity_deviation_f64(const double* X, int n, double* out, void* stream);  /* out[0] = max |X - I| */
 /* Sort sigma descending, normalise rows into Ut, apply chi_max / relative cutoff on the device.
  * info[2*b] = kept rank, winfo[2*b] = discarded weight sum_{k>=kept} sigma_k^2, winfo[2*b+1] = sigma_0.
  * sqrt_mode = 1 when G was a Gram matrix M E M^T (rows are lambda_i u_i^T, sigma_i = sqrt(lambda_i)). */

@@ -72,6 +72,33 @@ __device__ __forceinline__ double rsqrt_newton2(double x) {    // full double pr
     return y;
 }
 
+template <typename R> struct Vec16;
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; __device__ static double2 zero() { return make_double2(0.0, 0.0); } };
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; __device__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); } };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// FP32 rotation for the preconditioning sweeps: hardware rsqrt / reciprocal are accurate enough (the FP64 sweeps that follow
+// restore full accuracy), and an order of magnitude shorter on the critical path.
+__device__ __forceinline__ int rotation(float aa, float bb, float ab, float tol2, float null2, float& c, float& s, float& t_out) {
+    const float prod = aa * bb;
+    const float ab2 = ab * ab;
+    if (!(ab2 > tol2 * prod) || !(prod > 1e-35f)) return 0;
+    if (aa < null2 && bb < null2) return 0;
+    const float d = bb - aa, g = 2.0f * ab;
+    const float h = sqrtf(fmaf(d, d, g * g));
+    float t = __fdividef(fabsf(g), fabsf(d) + h);
+    if ((d < 0.0f) != (g < 0.0f)) t = -t;
+    c = rsqrtf(fmaf(t, t, 1.0f));
+    s = c * t;
+    t_out = t;
+    return 3;
+}
+
 // Jacobi rotation (Hestenes / Rutishauser) from aa = a.a, bb = b.b, ab = a.b: a' = c a - s b, b' = s a + c b are orthogonal.
 // Returns 0 when the pair is already orthogonal to tolerance (ab^2 <= tol^2 aa bb) or numerically null, 1 for a "small"
 // rotation (|cos| <= 1e-9: by quadratic convergence the sweep after a sweep of only small rotations cannot rotate above
@@ -94,15 +121,15 @@ __device__ __forceinline__ int rotation(double aa, double bb, double ab, double 
 }
 
 // rotate rows a and b (both in shared memory, length n): used by the all-pairs round (t == 0) and by single-CTA problems
-template <int NREG>
-__device__ __forceinline__ int rotate_pair(double* __restrict__ a, double* __restrict__ b, int n, int lane, double tol2, double null2) {
-    double ra[NREG], rb[NREG];
-    double aa = 0.0, bb = 0.0, ab = 0.0;
+template <typename R, int NREG>
+__device__ __forceinline__ int rotate_pair(R* __restrict__ a, R* __restrict__ b, int n, int lane, R tol2, R null2) {
+    R ra[NREG], rb[NREG];
+    R aa = R(0), bb = R(0), ab = R(0);
 #pragma unroll
     for (int k = 0; k < NREG; k++) {
         int c = lane + 32 * k;
-        ra[k] = c < n ? a[c] : 0.0;
-        rb[k] = c < n ? b[c] : 0.0;
+        ra[k] = c < n ? a[c] : R(0);
+        rb[k] = c < n ? b[c] : R(0);
         aa = fma(ra[k], ra[k], aa);
         bb = fma(rb[k], rb[k], bb);
         ab = fma(ra[k], rb[k], ab);
@@ -113,7 +140,7 @@ __device__ __forceinline__ int rotate_pair(double* __restrict__ a, double* __res
         bb += __shfl_xor_sync(0xffffffffu, bb, o);
         ab += __shfl_xor_sync(0xffffffffu, ab, o);
     }
-    double c, s, t;
+    R c, s, t;
     const int kind = rotation(aa, bb, ab, tol2, null2, c, s, t);
     if (!kind) return 0;
 #pragma unroll
@@ -131,30 +158,30 @@ __device__ __forceinline__ int rotate_pair(double* __restrict__ a, double* __res
 // are cached (na in a register, *nb in shared memory) and updated analytically (|a'|^2 = aa - t ab, |b'|^2 = bb + t ab), so a
 // round costs ONE dot product, one warp reduction, and one trip of the partner row through shared memory.
 // FULL: n == 32 * NREG, no bounds checks.
-template <int NREG, bool FULL>
-__device__ __forceinline__ int rotate_cached(double (&ra)[NREG], double& na, double* __restrict__ b, double* __restrict__ nb, int n, int lane,
-                                              double tol2, double null2) {
-    double rb[NREG];
+template <typename R, int NREG, bool FULL>
+__device__ __forceinline__ int rotate_cached(R (&ra)[NREG], R& na, R* __restrict__ b, R* __restrict__ nb, int n, int lane,
+                                              R tol2, R null2) {
+    R rb[NREG];
 #pragma unroll
     for (int k = 0; k < NREG; k++) {
         int c = lane + 32 * k;
-        rb[k] = (FULL || c < n) ? b[c] : 0.0;
+        rb[k] = (FULL || c < n) ? b[c] : R(0);
     }
-    double ab0 = 0.0, ab1 = 0.0;
+    R ab0 = R(0), ab1 = R(0);
 #pragma unroll
     for (int k = 0; k < NREG; k += 2) {
         ab0 = fma(ra[k], rb[k], ab0);
         ab1 = fma(ra[k + 1], rb[k + 1], ab1);
     }
-    const double ab = warp_sum(ab0 + ab1);
-    const double bb = *nb;
-    double c, s, t;
+    const R ab = warp_sum(ab0 + ab1);
+    const R bb = *nb;
+    R c, s, t;
     const int kind = rotation(na, bb, ab, tol2, null2, c, s, t);
     if (!kind) return 0;
 #pragma unroll
     for (int k = 0; k < NREG; k++) {
         int col = lane + 32 * k;
-        const double x = ra[k], y = rb[k];
+        const R x = ra[k], y = rb[k];
         ra[k] = fma(c, x, -s * y);
         if (FULL || col < n) b[col] = fma(s, x, c * y);
     }
@@ -163,13 +190,13 @@ __device__ __forceinline__ int rotate_cached(double (&ra)[NREG], double& na, dou
     return kind;
 }
 
-template <int NREG, bool FULL>
-__device__ __forceinline__ double row_sumsq(const double* __restrict__ a, int n, int lane) {
-    double s0 = 0.0, s1 = 0.0;
+template <typename R, int NREG, bool FULL>
+__device__ __forceinline__ R row_sumsq(const R* __restrict__ a, int n, int lane) {
+    R s0 = R(0), s1 = R(0);
 #pragma unroll
     for (int k = 0; k < NREG; k += 2) {
         int c0 = lane + 32 * k, c1 = c0 + 32;
-        double x = (FULL || c0 < n) ? a[c0] : 0.0, y = (FULL || c1 < n) ? a[c1] : 0.0;
+        R x = (FULL || c0 < n) ? a[c0] : R(0), y = (FULL || c1 < n) ? a[c1] : R(0);
         s0 = fma(x, x, s0);
         s1 = fma(y, y, s1);
     }
@@ -178,16 +205,20 @@ __device__ __forceinline__ double row_sumsq(const double* __restrict__ a, int n,
 
 // grid = (P, problems in this launch).  ctrl layout per problem: [0] barrier counter, [1 + sweep] rotation flags,
 // [1 + max_sweeps] sweeps used.
-template <int NREG, int THREADS>
+template <typename R, int NREG, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int P, unsigned* __restrict__ ctrl, int ctrl_stride,
-                   int max_sweeps, double tol2, double null_rel2) {
+jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int P, unsigned* __restrict__ ctrl, int ctrl_stride,
+                   int max_sweeps, double tol2_, double null_rel2_) {
+    const R tol2 = (R)tol2_, null_rel2 = (R)null_rel2_;
     constexpr int WARPS = THREADS / 32;
-    extern __shared__ __align__(16) double rows[];   // [2w][LDS]
+    extern __shared__ __align__(16) unsigned char jac_smem_raw[];
+    R* rows = reinterpret_cast<R*>(jac_smem_raw);   // [2w][LDS]
     __shared__ int s_rot;
-    __shared__ double s_nrm[32];
+    __shared__ R s_nrm[32];
     __shared__ __align__(8) uint64_t s_mbar;
-    const int LDS = (n + 1) & ~1;
+    using V = typename Vec16<R>::type;               // 16-byte vector: double2 / float4
+    constexpr int VE = Vec16<R>::N;
+    const int LDS = (n + VE - 1) / VE * VE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = blockIdx.x;
     G += (int64_t)blockIdx.y * bs;
@@ -198,7 +229,7 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     unsigned bar_target = 0;
     const int NB = 2 * P;          // number of row blocks
     const int Mr = NB - 1;         // outer rounds per sweep
-    const bool vec2 = ((n & 1) == 0) && ((ld & 1) == 0) && ((((uintptr_t)G) & 15) == 0);
+    const bool vec2 = (n % VE == 0) && (ld % VE == 0) && ((((uintptr_t)G) & 15) == 0);
     const bool full = (n == 32 * NREG);
     // TMA path: multi-CTA problem, every block full, rows 16-byte aligned and dense in shared memory
     const bool tma = (P > 1) && vec2 && (n == 2 * P * w) && (LDS == n);
@@ -210,35 +241,35 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
 
     // blocks travel through L2 (ld.cg / st.cg: L1 is not coherent across the CTAs of a problem), 16 bytes per thread
     auto load_block = [&](int blk, int half) {
-        double* dst = rows + half * w * LDS;
+        R* dst = rows + half * w * LDS;
         if (vec2) {
-            const int n2 = n >> 1, L2 = LDS >> 1;
+            const int n2 = n / VE, L2 = LDS / VE;
 #pragma unroll 8
             for (int idx = tid; idx < w * L2; idx += THREADS) {      // all loads of a block in flight at once
                 int r = idx / L2, c2 = idx - r * L2;
                 int gr = blk * w + r;
-                double2 v = make_double2(0.0, 0.0);
-                if (gr < n && c2 < n2) v = __ldcg(reinterpret_cast<const double2*>(G + (int64_t)gr * ld) + c2);
-                reinterpret_cast<double2*>(dst + r * LDS)[c2] = v;
+                V v = Vec16<R>::zero();
+                if (gr < n && c2 < n2) v = __ldcg(reinterpret_cast<const V*>(G + (int64_t)gr * ld) + c2);
+                reinterpret_cast<V*>(dst + r * LDS)[c2] = v;
             }
         } else {
             for (int idx = tid; idx < w * LDS; idx += THREADS) {
                 int r = idx / LDS, c = idx - r * LDS;
                 int gr = blk * w + r;
-                dst[r * LDS + c] = (gr < n && c < n) ? __ldcg(G + (int64_t)gr * ld + c) : 0.0;
+                dst[r * LDS + c] = (gr < n && c < n) ? __ldcg(G + (int64_t)gr * ld + c) : R(0);
             }
         }
     };
     auto store_block = [&](int blk, int half) {
-        const double* src = rows + half * w * LDS;
+        const R* src = rows + half * w * LDS;
         if (vec2) {
-            const int n2 = n >> 1, L2 = LDS >> 1;
+            const int n2 = n / VE, L2 = LDS / VE;
 #pragma unroll 4
             for (int idx = tid; idx < w * L2; idx += THREADS) {
                 int r = idx / L2, c2 = idx - r * L2;
                 int gr = blk * w + r;
                 if (gr < n && c2 < n2)
-                    __stcg(reinterpret_cast<double2*>(G + (int64_t)gr * ld) + c2, reinterpret_cast<const double2*>(src + r * LDS)[c2]);
+                    __stcg(reinterpret_cast<V*>(G + (int64_t)gr * ld) + c2, reinterpret_cast<const V*>(src + r * LDS)[c2]);
             }
         } else {
             for (int idx = tid; idx < w * LDS; idx += THREADS) {
@@ -252,24 +283,24 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
     // largest squared row norm of the problem -> absolute floor below which a pair of rows is left alone (both would be
     // discarded by the rank threshold of the finalize kernel; without this, null-space rows of a rank-deficient matrix rotate
     // among themselves for ever: their mutual cosines are O(1) noise)
-    double null2 = 0.0;
-    if (null_rel2 > 0.0) {
+    R null2 = R(0);
+    if (null_rel2 > R(0)) {
         unsigned long long* gmax = reinterpret_cast<unsigned long long*>(bar + ctrl_base - 2);
-        double local = 0.0;
+        R local = R(0);
         for (int r = p * 2 * w + warp; r < n && r < (p + 1) * 2 * w; r += WARPS) {
-            double sacc = 0.0;
-            for (int c = lane; c < n; c += 32) { double x = __ldcg(G + (int64_t)r * ld + c); sacc = fma(x, x, sacc); }
+            R sacc = R(0);
+            for (int c = lane; c < n; c += 32) { R x = __ldcg(G + (int64_t)r * ld + c); sacc = fma(x, x, sacc); }
             sacc = warp_sum(sacc);
-            local = fmax(local, sacc);
+            local = sacc > local ? sacc : local;
         }
-        if (lane == 0 && local > 0.0) atomicMax(gmax, (unsigned long long)__double_as_longlong(local));   // positive doubles order like integers
+        if (lane == 0 && local > R(0)) atomicMax(gmax, (unsigned long long)__double_as_longlong((double)local));   // positive doubles order like integers
         if (P > 1) {
             bar_target += P;
             problem_barrier(bar, bar_target);
         } else {
             __syncthreads();
         }
-        const double mx = __longlong_as_double((long long)__ldcg(gmax));
+        const R mx = (R)__longlong_as_double((long long)__ldcg(gmax));
         null2 = null_rel2 * mx;
     }
 
@@ -284,7 +315,7 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
             else { b0 = (t + p) % Mr; b1 = (t - p + Mr) % Mr; }
             if (tma) {
                 if (tid == 0) {
-                    const uint32_t row_bytes = (uint32_t)n * 8u, blk_bytes = (uint32_t)w * row_bytes;
+                    const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)w * row_bytes;
                     // point-to-point hand-over instead of a grid barrier: a block is ready when the CTA that held it in the
                     // previous round has published its version (every block takes part in every round)
                     const unsigned need = (unsigned)(sweep * Mr + t);
@@ -296,8 +327,8 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                     mbar_expect_tx(&s_mbar, 2u * blk_bytes);
                     const int blks[2] = {b0, b1};
                     for (int h = 0; h < 2; ++h) {
-                        const double* src = G + (int64_t)blks[h] * w * ld;
-                        double* dst = rows + h * w * LDS;
+                        const R* src = G + (int64_t)blks[h] * w * ld;
+                        R* dst = rows + h * w * LDS;
                         if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
                         else for (int r = 0; r < w; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
                     }
@@ -317,30 +348,30 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                         int i, j;
                         if (k == 0) { i = items - 1; j = s; }
                         else { i = (s + k) % rounds; j = (s - k + rounds) % rounds; }
-                        rotated |= rotate_pair<NREG>(rows + i * LDS, rows + j * LDS, n, lane, tol2, null2);
+                        rotated |= rotate_pair<R, NREG>(rows + i * LDS, rows + j * LDS, n, lane, tol2, null2);
                     }
                     __syncthreads();
                 }
             } else if (w <= WARPS) {
                 // cross pairs only: row k of block b0 (held in registers by warp k) with row (k+s) mod w of block b1
-                double ra[NREG];
-                double na = 0.0;
+                R ra[NREG];
+                R na = R(0);
                 if (warp < w) {
 #pragma unroll
-                    for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; ra[k] = c < n ? rows[warp * LDS + c] : 0.0; }
+                    for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; ra[k] = c < n ? rows[warp * LDS + c] : R(0); }
 #pragma unroll
                     for (int k = 0; k < NREG; k++) na = fma(ra[k], ra[k], na);
                     na = warp_sum(na);
-                    const double nbv = full ? row_sumsq<NREG, true>(rows + (w + warp) * LDS, n, lane)
-                                            : row_sumsq<NREG, false>(rows + (w + warp) * LDS, n, lane);
+                    const R nbv = full ? row_sumsq<R, NREG, true>(rows + (w + warp) * LDS, n, lane)
+                                            : row_sumsq<R, NREG, false>(rows + (w + warp) * LDS, n, lane);
                     if (lane == 0) s_nrm[warp] = nbv;
                 }
                 __syncthreads();
                 for (int s = 0; s < w; ++s) {
                     if (warp < w) {
                         const int j = (warp + s) & (w - 1);           // w is a power of two
-                        rotated |= full ? rotate_cached<NREG, true>(ra, na, rows + (w + j) * LDS, s_nrm + j, n, lane, tol2, null2)
-                                        : rotate_cached<NREG, false>(ra, na, rows + (w + j) * LDS, s_nrm + j, n, lane, tol2, null2);
+                        rotated |= full ? rotate_cached<R, NREG, true>(ra, na, rows + (w + j) * LDS, s_nrm + j, n, lane, tol2, null2)
+                                        : rotate_cached<R, NREG, false>(ra, na, rows + (w + j) * LDS, s_nrm + j, n, lane, tol2, null2);
                     }
                     __syncthreads();
                 }
@@ -353,7 +384,7 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                 for (int s = 0; s < w; ++s) {
                     for (int k = warp; k < w; k += WARPS) {
                         int j = w + ((k + s) % w);
-                        rotated |= rotate_pair<NREG>(rows + k * LDS, rows + j * LDS, n, lane, tol2, null2);
+                        rotated |= rotate_pair<R, NREG>(rows + k * LDS, rows + j * LDS, n, lane, tol2, null2);
                     }
                     __syncthreads();
                 }
@@ -362,11 +393,11 @@ jacobi_rows_kernel(double* __restrict__ G, int64_t ld, int64_t bs, int n, int w,
                 fence_proxy_async();               // every thread: its st.shared results become visible to the async proxy
                 __syncthreads();
                 if (tid == 0) {
-                    const uint32_t row_bytes = (uint32_t)n * 8u, blk_bytes = (uint32_t)w * row_bytes;
+                    const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)w * row_bytes;
                     const int blks[2] = {b0, b1};
                     for (int h = 0; h < 2; ++h) {
-                        double* dst = G + (int64_t)blks[h] * w * ld;
-                        const double* src = rows + h * w * LDS;
+                        R* dst = G + (int64_t)blks[h] * w * ld;
+                        const R* src = rows + h * w * LDS;
                         if (ld == n) bulk_s2g(dst, src, blk_bytes);
                         else for (int r = 0; r < w; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
                     }
@@ -501,28 +532,29 @@ static int jac_env_w() {   // experiment knob: SYN_JACOBI_W=8 forces the block h
     return v;
 }
 
-static int jac_plan(int n, JacPlan& pl) {
+static int jac_plan(int n, JacPlan& pl, size_t esize = sizeof(double)) {
     SYN_REQUIRE(n >= 1 && n <= 1024, "syn_jacobi_rows_f64: n=%d out of range (1..1024)", n);
-    const int LDS = (n + 1) & ~1;
+    const int ve = (int)(16 / esize);
+    const int LDS = (n + ve - 1) / ve * ve;
     pl.nreg = n <= 128 ? 4 : (n <= 256 ? 8 : (n <= 512 ? 16 : 32));
     int w;
     if (n <= 128) {                 // whole problem in one CTA (P = 1): no grid barriers, good for large batches
         w = 1;
         while (2 * w < n) w <<= 1;
     } else {                        // w rows per block, one warp per stationary row in the cross rounds
-        w = jac_env_w() > 0 ? jac_env_w() : (n >= 512 ? 8 : 16);   // measured: 8 rows per block is ~5% faster at n = 512
-        while (w > 1 && (size_t)2 * w * LDS * sizeof(double) > JAC_SMEM_CAP) w >>= 1;
+        w = jac_env_w() > 0 ? jac_env_w() : ((n >= 512 && esize == sizeof(double)) ? 8 : 16);   // measured: 8 rows per block is ~5% faster at n = 512 (FP64)
+        while (w > 1 && (size_t)2 * w * LDS * esize > JAC_SMEM_CAP) w >>= 1;
     }
     pl.w = w;
     pl.P = (n + 2 * w - 1) / (2 * w);
-    pl.smem = (size_t)2 * w * LDS * sizeof(double);
+    pl.smem = (size_t)2 * w * LDS * esize;
     return 0;
 }
 
-template <int NREG, int THREADS>
-static int launch_jacobi(double* G, int64_t ld, int64_t bs, int n, int batch, const JacPlan& pl, unsigned* ctrl, int ctrl_stride,
+template <typename R, int NREG, int THREADS>
+static int launch_jacobi(R* G, int64_t ld, int64_t bs, int n, int batch, const JacPlan& pl, unsigned* ctrl, int ctrl_stride,
                          int max_sweeps, double tol, double null_rel, cudaStream_t st) {
-    auto kern = jacobi_rows_kernel<NREG, THREADS>;
+    auto kern = jacobi_rows_kernel<R, NREG, THREADS>;
     static bool configured = false;
     static int max_ctas = 0;
     if (!configured) {
@@ -538,7 +570,7 @@ static int launch_jacobi(double* G, int64_t ld, int64_t bs, int n, int batch, co
     double tol2 = tol * tol, null_rel2 = null_rel * null_rel;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         int nb = (batch - b0) < chunk ? (batch - b0) : chunk;
-        double* Gb = G + (int64_t)b0 * bs;
+        R* Gb = G + (int64_t)b0 * bs;
         unsigned* cb = ctrl + (int64_t)b0 * ctrl_stride;
         int w = pl.w, P = pl.P;
         void* args[] = {&Gb, &ld, &bs, &n, &w, &P, &cb, &ctrl_stride, &max_sweeps, &tol2, &null_rel2};
@@ -566,10 +598,10 @@ int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* c
     SYN_CUDA(cudaMemsetAsync(ctrl, 0, jacobi_ctrl_bytes(batch, max_sweeps), st));
     const int stride = jacobi_ctrl_stride(max_sweeps);
     switch (pl.nreg) {
-        case 4: return launch_jacobi<4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        case 8: return launch_jacobi<8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        case 16: return launch_jacobi<16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        default: return launch_jacobi<32, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        case 4: return launch_jacobi<double, 4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        case 8: return launch_jacobi<double, 8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        case 16: return launch_jacobi<double, 16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        default: return launch_jacobi<double, 32, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
     }
 }
 
@@ -581,6 +613,85 @@ int jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batc
 }
 
 }  // namespace syn
+
+namespace syn {
+int jacobi_rows_f32(float* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes, int max_sweeps, double tol,
+                    double null_rel, cudaStream_t st) {
+    SYN_REQUIRE(batch >= 1 && max_sweeps >= 1, "syn_jacobi_rows_f32: bad batch / max_sweeps");
+    SYN_REQUIRE(ctrl_bytes >= jacobi_ctrl_bytes(batch, max_sweeps), "syn_jacobi_rows_f32: control buffer too small");
+    JacPlan pl;
+    if (int rc = jac_plan(n, pl, sizeof(float))) return rc;
+    SYN_CUDA(cudaMemsetAsync(ctrl, 0, jacobi_ctrl_bytes(batch, max_sweeps), st));
+    const int stride = jacobi_ctrl_stride(max_sweeps);
+    switch (pl.nreg) {
+        case 4: return launch_jacobi<float, 4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        case 8: return launch_jacobi<float, 8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        case 16: return launch_jacobi<float, 16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        default: return launch_jacobi<float, 32, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+    }
+}
+
+// ---- helpers of the FP32-preconditioned eigen-solver -------------------------------------------------------------------
+__global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+// U[i][:] = double(G32[i][:]) / |G32[i][:]|   (rows of the FP32 Jacobi result -> approximate eigenvectors)
+__global__ void rows_to_basis_kernel(const float* __restrict__ G, double* __restrict__ U, int n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (r >= n) return;
+    const float* g = G + (int64_t)r * n;
+    double s = 0.0;
+    for (int c = lane; c < n; c += 32) { double x = (double)g[c]; s = fma(x, x, s); }
+    s = warp_sum(s);
+    const double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+    for (int c = lane; c < n; c += 32) U[(int64_t)r * n + c] = (s > 0.0) ? (double)g[c] * inv : (c == r ? 1.0 : 0.0);
+}
+// out[0] = max_ij |X[i][j] - delta_ij|   (single CTA)
+__global__ void __launch_bounds__(1024, 1) identity_dev_kernel(const double* __restrict__ X, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double m = 0.0;
+    for (int64_t i = threadIdx.x; i < (int64_t)n * n; i += 1024) {
+        int r = (int)(i / n), c = (int)(i - (int64_t)r * n);
+        double v = fabs(X[i] - (r == c ? 1.0 : 0.0));
+        m = v > m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (threadIdx.x == 0) out[0] = v;
+    }
+}
+}  // namespace syn
+
+extern "C" int syn_jacobi_rows_f32(float* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes, int max_sweeps,
+                                   double tol, double null_rel, void* stream) {
+    return syn::jacobi_rows_f32(G, ld, bs, n, batch, ctrl, ctrl_bytes, max_sweeps, tol, null_rel, (cudaStream_t)stream);
+}
+extern "C" int syn_cast_f64_f32(const double* src, float* dst, int64_t n, void* stream) {
+    using namespace syn;
+    if (n <= 0) return 0;
+    int64_t b = (n + 255) / 256;
+    cast_f64_f32_kernel<<<(unsigned)(b > 4096 ? 4096 : b), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    return launch_status("cast_f64_f32_kernel");
+}
+extern "C" int syn_rows_to_basis_f32_f64(const float* G, double* U, int n, void* stream) {
+    using namespace syn;
+    SYN_REQUIRE(n >= 1, "syn_rows_to_basis_f32_f64: bad n");
+    rows_to_basis_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(G, U, n);
+    return launch_status("rows_to_basis_kernel");
+}
+extern "C" int syn_identity_deviation_f64(const double* X, int n, double* out, void* stream) {
+    using namespace syn;
+    SYN_REQUIRE(n >= 1, "syn_identity_deviation_f64: bad n");
+    identity_dev_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(X, n, out);
+    return launch_status("identity_dev_kernel");
+}
 
 extern "C" size_t syn_jacobi_ctrl_bytes(int batch, int max_sweeps) { return syn::jacobi_ctrl_bytes(batch, max_sweeps); }
 extern "C" int syn_jacobi_ctrl_stride(int max_sweeps) { return syn::jacobi_ctrl_stride(max_sweeps); }

@@ -105,3 +105,23 @@ def test_site_contractions_and_overlap_vs_oracle():
     P = rand_chain(rng, 9, 2, 10); Q = rand_chain(rng, 9, 2, 7)
     got = sw.overlap([sw.as_core(c) for c in P], [sw.as_core(c) for c in Q]).item()
     assert abs(got - R.overlap(P, Q)) < 1e-12 * abs(R.overlap(P, Q)) + 1e-300
+
+
+def test_fp32_preconditioned_eigensolver_option():
+    """The optional FP32-preconditioned path of eigh_gram gives the same spectrum / subspace as the plain FP64 sweeps."""
+    from syngular.tensor import _sweeps as sw
+    rng = np.random.default_rng(21)
+    B = rng.normal(size=(256, 1024))
+    A = B @ B.T
+    ref = np.linalg.svd(B, compute_uv=False)
+    old = sw.PRECONDITION_MIN_N
+    try:
+        for flag in (0, 256):
+            sw.PRECONDITION_MIN_N = flag
+            Ut, sigma, info, winfo = sw.eigh_gram(torch.from_numpy(A.copy()).cuda(), 100, 0.0, 3.2e-7)
+            assert np.max(np.abs(sigma.cpu().numpy() - ref)) < 1e-10 * ref[0]
+            U = Ut.cpu().numpy()
+            assert np.max(np.abs(U @ U.T - np.eye(256))) < 1e-11
+            assert np.max(np.abs(U[:100] @ A @ U[:100].T - np.diag(ref[:100] ** 2))) < 1e-9 * ref[0] ** 2
+    finally:
+        sw.PRECONDITION_MIN_N = old
