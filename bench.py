@@ -124,6 +124,15 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it can (BLAS/LAPACK thread pools)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=host_threads())
+    except Exception:
+        pass
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # clocks sampler (B200_PROFILING.md "clocks line")
 # ---------------------------------------------------------------------------------------------------------------------
@@ -167,6 +176,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     X, W = make_chain(2)
     sites = [31]                                         # one plateau site per step (a few seconds of LAPACK)
     for _ in range(args.warmup):
@@ -355,6 +365,7 @@ def run_ours(args):
                     "kernel_ms_per_sweep": g_ms, "share_of_step": g_ms / sweep_ms}
         cpu = None
         if world == 1 and not args.no_cpu:
+            use_all_host_threads()
             v, sec, total, fl = cpu_sweeps_per_s(Xh, Wh, CHI, [31, 32])
             cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port",
                    "sample": "oracle textbook apply + right-QR + left-SVD steps at full size on plateau sites 31-32 (%.1f s), scaled to the "
