@@ -332,6 +332,42 @@ def run_ours(args):
     c5_value = 65536 / (ms_c5 * 1e-3)
     del x5
 
+    # BASELINE configs[0]: the README chain (readme.md:53-73) from the reference's decomposed cores (tests/golden), GPU vs the
+    # numpy oracle on the host; tiny tensors (d = 16, bonds <= 24): launch-latency territory, reported for completeness
+    c1 = None
+    if rank == 0:
+        try:
+            gold = np.load(os.path.join(ROOT, "tests", "golden", "readme_chain.npz"))
+
+            def cores(prefix):
+                return [gold["%s/site%d" % (prefix, k)] for k in range(int(gold[prefix + "/n"]))]
+
+            def readme_chain(MPSc, MPOc):
+                Wc, Xc, Tc = MPOc.from_sites(cores("W0")), MPSc.from_sites(cores("X0")), MPOc.from_sites(cores("T0"))
+                Wc = Wc >> 4
+                Tc = Tc >> 2
+                Z = ((Tc + Wc) @ Tc) @ Xc
+                v = Z | Xc
+                Z = Z >> 16
+                Z.left_orthonormalization()
+                return float(v)
+            v_gpu = readme_chain(MPS, MPO)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                readme_chain(MPS, MPO)
+            torch.cuda.synchronize()
+            gpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+            from oracle import ref_numpy as RN
+            t0 = time.perf_counter()
+            for _ in range(3):
+                v_cpu = readme_chain(RN.MPS, RN.MPO)
+            cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+            c1 = {"gpu_ms": gpu_ms, "cpu_oracle_ms": cpu_ms, "Z_X_gpu": v_gpu, "Z_X_golden": float(gold["Z_X"]),
+                  "rel_err": abs(v_gpu - float(gold["Z_X"])) / abs(float(gold["Z_X"]))}
+        except Exception as exc:                     # never let the side measurement break the headline line
+            c1 = {"error": repr(exc)}
+
     line = None
     if rank == 0:
         # roofline of the dominant kernel: profile one sweep with per-launch CUDA events on the launching stream
@@ -384,7 +420,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "extra": {"c4_batched_overlaps_states_per_s": c4_value, "c4_ms_per_batch": ms_c4 / c4_reps,
+            "extra": {"c1_readme_chain": c1, "c4_batched_overlaps_states_per_s": c4_value, "c4_ms_per_batch": ms_c4 / c4_reps,
                       "c4_note": "BASELINE configs[3]: 8192 x (N=32, d=2, chi=64) overlaps, batch-sharded over %d GPU(s), one all-gather of 8192 "
                                  "float64; %.2f TFLOP/s FP64, %.0f GB/s of core traffic; gathered %s" % (
                                      world, c4_flops / (ms_c4 / c4_reps * 1e-3) / 1e12, c4_bytes / (ms_c4 / c4_reps * 1e-3) / 1e9,
