@@ -201,7 +201,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -437,10 +437,30 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything except the final JSON line goes to stderr: libraries (NCCL's version banner, cuBLAS warnings) write to fd 1."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
         print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
