@@ -19,12 +19,22 @@
 // updates and the formation of Q are two strided DMMA GEMMs per panel (gemm.cu).  Inputs/outputs take arbitrary
 // row/column strides, so transposed unfoldings (R^T) and core layouts are consumed and produced in place.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace syn {
 
 int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double* C, cudaStream_t st);
+bool qr_cluster_fits(int m, int qk);
+int qr_cluster_form_q(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int m, int kf, int qk, int batch, double* Q, int64_t q_rs,
+                      int64_t q_cs, int64_t q_bs, cudaStream_t st);
+
+static bool qr_env_cluster() {   // SYN_QR_CLUSTER=0 forces the blocked multi-launch path (A/B comparisons)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SYN_QR_CLUSTER"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 
 static inline syn_index_t IX(int64_t stride) {
     syn_index_t i;
@@ -287,6 +297,15 @@ int qrt_f64(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int m, in
     if (int rc = qr_plan(p, m, n, q, batch, ws, ws_doubles, "syn_qrt_f64")) return rc;
     if (qk_out) *qk_out = p.qk;
     SYN_REQUIRE(A && Q, "syn_qrt_f64: null operand");
+    if (qr_env_cluster() && qr_cluster_fits(m, p.qk)) {
+        // plateau shapes: factor + form Q in ONE cluster-resident launch (qr_cluster.cu), then S = Q^T A
+        if (int rc = qr_cluster_form_q(A, a_rs, a_cs, a_bs, m, p.kf, p.qk, batch, Q, q_rs, q_cs, q_bs, st)) return rc;
+        if (S) {
+            syn_gemm_desc_t d = mk_desc(p.qk, n, m, batch, q_cs, q_rs, q_bs, a_rs, a_cs, a_bs, s_rs, s_cs, s_bs, 1.0, 0.0);
+            if (int rc = gemm_f64(d, Q, A, S, st)) return rc;
+        }
+        return 0;
+    }
     if (int rc = house_factor(p, A, a_rs, a_cs, a_bs, st)) return rc;
     const int qk = p.qk, kf = p.kf, nb = p.nb;
     {   // 3. Q = first qk columns of the identity
