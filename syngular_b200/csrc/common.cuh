@@ -111,4 +111,31 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- MUFU-seeded FP64 reciprocal / rsqrt (seed 2^-22, each Newton step doubles the bits) -------------------------------
+__device__ __forceinline__ double rcp_newton1(double x) {      // ~2^-44
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double rsqrt_newton1(double x) {    // ~2^-43
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return fma(y, fma(-0.5 * x * y, y, 0.5), y);
+}
+__device__ __forceinline__ double rsqrt_newton2(double x) {    // full double precision
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+}
+
+__device__ __forceinline__ double rcp_newton2(double x) {      // full double precision
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 }  // namespace syn

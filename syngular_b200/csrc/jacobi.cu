@@ -53,25 +53,6 @@ __device__ __forceinline__ void problem_barrier(unsigned* ctr, unsigned target) 
 // round, so it is built from the MUFU seeds (rcp / rsqrt.approx.f64, 2^-22) plus Newton steps.  Only c needs full
 // precision (s = c*t makes c^2 + s^2 = 1 to rounding whatever t is); a t accurate to ~1e-13 only perturbs the
 // convergence rate, never the orthogonality of the accumulated transform.
-__device__ __forceinline__ double rcp_newton1(double x) {      // ~2^-44
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return fma(r, fma(-x, r, 1.0), r);
-}
-__device__ __forceinline__ double rsqrt_newton1(double x) {    // ~2^-43
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    return fma(y, fma(-0.5 * x * y, y, 0.5), y);
-}
-__device__ __forceinline__ double rsqrt_newton2(double x) {    // full double precision
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5 * x;
-    y = fma(y, fma(-h * y, y, 0.5), y);
-    y = fma(y, fma(-h * y, y, 0.5), y);
-    return y;
-}
-
 template <typename R> struct Vec16;
 template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; __device__ static double2 zero() { return make_double2(0.0, 0.0); } };
 template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; __device__ static float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); } };
