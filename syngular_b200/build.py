@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 # --use_fast_math only affects FP32 intrinsics; all arithmetic of this library is FP64.
+NVCC_FLAGS += os.environ.get("SYN_NVCC_EXTRA", "").split()      # e.g. -DSYN_JACOBI_TIMING for the in-kernel phase clocks
 
 
 def _nvcc():

@@ -216,7 +216,7 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
     const bool tma = (P > 1) && vec2 && (n == 2 * P * w) && (LDS == n);
     uint32_t mbar_phase = 0;
     if (tma) {
-        if (tid == 0) mbar_init(&s_mbar, 1);
+        if (tid == 0) mbar_init(&s_mbar, 2);       // two producers: one per block
         __syncthreads();
     }
 
@@ -285,37 +285,45 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
         null2 = null_rel2 * mx;
     }
 
+#ifdef SYN_JACOBI_TIMING
+    long long tk[6] = {0, 0, 0, 0, 0, 0};      // poll, load, prologue, steps, epilogue, store+publish   (thread 0 of CTA 1)
+    long long tmark = clock64();
+#define JTICK(i) do { if (tid == 0) { long long now_ = clock64(); tk[i] += now_ - tmark; tmark = now_; } } while (0)
+#else
+#define JTICK(i) do { } while (0)
+#endif
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
         for (int t = 0; t < (P == 1 ? 1 : Mr); ++t) {
+            JTICK(5);
             // round-robin tournament over the NB blocks (circle method): CTA p plays (b0, b1) in round t
             int b0, b1;
             if (P == 1) { b0 = 0; b1 = 1; }
             else if (p == 0) { b0 = NB - 1; b1 = t % Mr; }
             else { b0 = (t + p) % Mr; b1 = (t - p + Mr) % Mr; }
             if (tma) {
-                if (tid == 0) {
+                if (tid == 0 || tid == 32) {       // one thread (of different warps) per block: the two hand-overs run in parallel
                     const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)w * row_bytes;
+                    const int h = tid >> 5, blk = h ? b1 : b0;
                     // point-to-point hand-over instead of a grid barrier: a block is ready when the CTA that held it in the
                     // previous round has published its version (every block takes part in every round)
                     const unsigned need = (unsigned)(sweep * Mr + t);
-                    for (unsigned spin = 0; ld_acquire_u32(ver + b0) < need || ld_acquire_u32(ver + b1) < need; ++spin) {
+                    for (unsigned spin = 0; ld_acquire_u32(ver + blk) < need; ++spin) {
                         if (spin > (1u << 26)) __trap();
                         __nanosleep(20);
                     }
+                    JTICK(0);
                     fence_proxy_async();
-                    mbar_expect_tx(&s_mbar, 2u * blk_bytes);
-                    const int blks[2] = {b0, b1};
-                    for (int h = 0; h < 2; ++h) {
-                        const R* src = G + (int64_t)blks[h] * w * ld;
-                        R* dst = rows + h * w * LDS;
-                        if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
-                        else for (int r = 0; r < w; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
-                    }
+                    mbar_expect_tx(&s_mbar, blk_bytes);
+                    const R* src = G + (int64_t)blk * w * ld;
+                    R* dst = rows + h * w * LDS;
+                    if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
+                    else for (int r = 0; r < w; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
                 }
                 mbar_wait(&s_mbar, mbar_phase);
                 mbar_phase ^= 1u;
+                JTICK(1);
             } else if (P > 1 || sweep == 0) {
                 load_block(b0, 0);
                 load_block(b1, 1);
@@ -348,6 +356,7 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                     if (lane == 0) s_nrm[warp] = nbv;
                 }
                 __syncthreads();
+                JTICK(2);
                 for (int s = 0; s < w; ++s) {
                     if (warp < w) {
                         const int j = (warp + s) & (w - 1);           // w is a power of two
@@ -360,6 +369,7 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
 #pragma unroll
                     for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; if (c < n) rows[warp * LDS + c] = ra[k]; }
                 }
+                JTICK(3);
                 __syncthreads();
             } else {
                 for (int s = 0; s < w; ++s) {
@@ -373,21 +383,17 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
             if (tma) {
                 fence_proxy_async();               // every thread: its st.shared results become visible to the async proxy
                 __syncthreads();
-                if (tid == 0) {
+                JTICK(4);
+                if (tid == 0 || tid == 32) {
                     const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)w * row_bytes;
-                    const int blks[2] = {b0, b1};
-                    for (int h = 0; h < 2; ++h) {
-                        R* dst = G + (int64_t)blks[h] * w * ld;
-                        const R* src = rows + h * w * LDS;
-                        if (ld == n) bulk_s2g(dst, src, blk_bytes);
-                        else for (int r = 0; r < w; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
-                    }
+                    const int h = tid >> 5, blk = h ? b1 : b0;
+                    R* dst = G + (int64_t)blk * w * ld;
+                    const R* src = rows + h * w * LDS;
+                    if (ld == n) bulk_s2g(dst, src, blk_bytes);
+                    else for (int r = 0; r < w; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
                     bulk_commit_wait_all();        // writes complete (and shared memory free) before they are published
-                    fence_proxy_async();
-                    __threadfence();
-                    const unsigned done = (unsigned)(sweep * Mr + t) + 1u;
-                    st_release_u32(ver + b0, done);
-                    st_release_u32(ver + b1, done);
+                    fence_proxy_async();           // async-proxy writes ordered before the generic-proxy release below
+                    st_release_u32(ver + blk, (unsigned)(sweep * Mr + t) + 1u);
                 }
             } else if (P > 1) {
                 store_block(b0, 0);
@@ -417,6 +423,11 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
         store_block(1, 1);
     }
     if (p == 0 && tid == 0) flags[max_sweeps] = (unsigned)sweep;   // sweeps used (diagnostic)
+#ifdef SYN_JACOBI_TIMING
+    if (p == 1 && tid == 0 && blockIdx.y == 0)
+        printf("jacobi n=%d w=%d P=%d sweeps=%d cycles: poll %lld  load %lld  prologue %lld  steps %lld  epilogue %lld  store+publish %lld\n", n, w, P,
+               sweep, tk[0], tk[1], tk[2], tk[3], tk[4], tk[5]);
+#endif
 }
 
 // ---- finalize: sort, normalise, cut ------------------------------------------------------------------------------------
@@ -523,7 +534,7 @@ static int jac_plan(int n, JacPlan& pl, size_t esize = sizeof(double)) {
         w = 1;
         while (2 * w < n) w <<= 1;
     } else {                        // w rows per block, one warp per stationary row in the cross rounds
-        w = jac_env_w() > 0 ? jac_env_w() : ((n >= 512 && esize == sizeof(double)) ? 8 : 16);   // measured: 8 rows per block is ~5% faster at n = 512 (FP64)
+        w = jac_env_w() > 0 ? jac_env_w() : ((n > 256 && esize == sizeof(double)) ? 8 : 16);   // FP64, n > 256: 8 warps of 255 registers (a row is 16 registers per lane)
         while (w > 1 && (size_t)2 * w * LDS * esize > JAC_SMEM_CAP) w >>= 1;
     }
     pl.w = w;
@@ -581,7 +592,7 @@ int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* c
     switch (pl.nreg) {
         case 4: return launch_jacobi<double, 4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
         case 8: return launch_jacobi<double, 8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        case 16: return launch_jacobi<double, 16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+        case 16: return launch_jacobi<double, 16, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);   // w = 8: one warp per stationary row, 255 registers each
         default: return launch_jacobi<double, 32, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
     }
 }
