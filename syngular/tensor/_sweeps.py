@@ -386,6 +386,7 @@ def gram_with_environment(M2, E, b, r):
     return A
 
 
+CHOLESKY_MIN_N = 129          # multi-CTA Jacobi problems run on the shifted Cholesky factor of the Gram matrix (see eigh_gram); 0 = off
 PRECONDITION_MIN_N = 0        # FP32-preconditioned eigen-solver for Gram matrices at least this large; 0 = off (see eigh_gram)
 
 
@@ -404,6 +405,12 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
     a 6 % gain, not worth the extra moving parts -- OFF by default, kept as an option and as a record of the experiment."""
     n = A.shape[0]
     null_rel = rank_tol * rank_tol
+    if CHOLESKY_MIN_N and n >= CHOLESKY_MIN_N and A.is_contiguous():
+        # Jacobi on the rows of B = L^T, G + delta I = L L^T: works on a matrix similar to G instead of G^2 -- 10 sweeps instead of
+        # 13 on the C2 plateau, 15 instead of 27 on its rank-deficient sites (tools/chol_experiment.py); sigma comes out directly.
+        B, shift = ops.chol_upper(A)
+        ops.jacobi_rows(B, null_rel=0.0)
+        return ops.jacobi_finalize(B, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=2, shift=shift)
     if PRECONDITION_MIN_N and n >= PRECONDITION_MIN_N:
         G32 = ops.cast_f32(A)
         ops.jacobi_rows_f32(G32)

@@ -184,6 +184,8 @@ __device__ __forceinline__ R row_sumsq(const R* __restrict__ a, int n, int lane)
     return warp_sum(s0 + s1);
 }
 
+constexpr int JAC_XFER = 4;        // pieces a round's hand-over is split into (2 blocks x 2 halves), each with its own thread and version word
+
 // grid = (P, problems in this launch).  ctrl layout per problem: [0] barrier counter, [1 + sweep] rotation flags,
 // [1 + max_sweeps] sweeps used.
 template <typename R, int NREG, int THREADS>
@@ -216,7 +218,7 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
     const bool tma = (P > 1) && vec2 && (n == 2 * P * w) && (LDS == n);
     uint32_t mbar_phase = 0;
     if (tma) {
-        if (tid == 0) mbar_init(&s_mbar, 2);       // two producers: one per block
+        if (tid == 0) mbar_init(&s_mbar, JAC_XFER);   // one producer per piece
         __syncthreads();
     }
 
@@ -303,23 +305,24 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
             else if (p == 0) { b0 = NB - 1; b1 = t % Mr; }
             else { b0 = (t + p) % Mr; b1 = (t - p + Mr) % Mr; }
             if (tma) {
-                if (tid == 0 || tid == 32) {       // one thread (of different warps) per block: the two hand-overs run in parallel
-                    const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)w * row_bytes;
-                    const int h = tid >> 5, blk = h ? b1 : b0;
+                if (lane == 0 && warp < JAC_XFER) {   // one thread (of different warps) per piece: the hand-overs run in parallel
+                    const int h = warp / (JAC_XFER / 2), sub = warp % (JAC_XFER / 2), blk = h ? b1 : b0;
+                    const int wr = w / (JAC_XFER / 2);                                  // rows per piece
+                    const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)wr * row_bytes;
                     // point-to-point hand-over instead of a grid barrier: a block is ready when the CTA that held it in the
                     // previous round has published its version (every block takes part in every round)
                     const unsigned need = (unsigned)(sweep * Mr + t);
-                    for (unsigned spin = 0; ld_acquire_u32(ver + blk) < need; ++spin) {
+                    for (unsigned spin = 0; ld_acquire_u32(ver + blk * (JAC_XFER / 2) + sub) < need; ++spin) {
                         if (spin > (1u << 26)) __trap();
                         __nanosleep(20);
                     }
                     JTICK(0);
                     fence_proxy_async();
                     mbar_expect_tx(&s_mbar, blk_bytes);
-                    const R* src = G + (int64_t)blk * w * ld;
-                    R* dst = rows + h * w * LDS;
+                    const R* src = G + (int64_t)(blk * w + sub * wr) * ld;
+                    R* dst = rows + (h * w + sub * wr) * LDS;
                     if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
-                    else for (int r = 0; r < w; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
+                    else for (int r = 0; r < wr; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
                 }
                 mbar_wait(&s_mbar, mbar_phase);
                 mbar_phase ^= 1u;
@@ -384,16 +387,17 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                 fence_proxy_async();               // every thread: its st.shared results become visible to the async proxy
                 __syncthreads();
                 JTICK(4);
-                if (tid == 0 || tid == 32) {
-                    const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)w * row_bytes;
-                    const int h = tid >> 5, blk = h ? b1 : b0;
-                    R* dst = G + (int64_t)blk * w * ld;
-                    const R* src = rows + h * w * LDS;
+                if (lane == 0 && warp < JAC_XFER) {
+                    const int h = warp / (JAC_XFER / 2), sub = warp % (JAC_XFER / 2), blk = h ? b1 : b0;
+                    const int wr = w / (JAC_XFER / 2);
+                    const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)wr * row_bytes;
+                    R* dst = G + (int64_t)(blk * w + sub * wr) * ld;
+                    const R* src = rows + (h * w + sub * wr) * LDS;
                     if (ld == n) bulk_s2g(dst, src, blk_bytes);
-                    else for (int r = 0; r < w; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
+                    else for (int r = 0; r < wr; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
                     bulk_commit_wait_all();        // writes complete (and shared memory free) before they are published
                     fence_proxy_async();           // async-proxy writes ordered before the generic-proxy release below
-                    st_release_u32(ver + blk, (unsigned)(sweep * Mr + t) + 1u);
+                    st_release_u32(ver + blk * (JAC_XFER / 2) + sub, (unsigned)(sweep * Mr + t) + 1u);
                 }
             } else if (P > 1) {
                 store_block(b0, 0);
@@ -433,12 +437,13 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
 // ---- finalize: sort, normalise, cut ------------------------------------------------------------------------------------
 // G rows (after jacobi_rows_kernel) -> Ut[k][:] = row_{perm[k]} / |row_{perm[k]}|, sigma[k] (descending).
 //   sqrt_mode = 1: sigma = sqrt(|row|)  (density-matrix use: rows are lambda_i u_i^T)
+//   sqrt_mode = 2: sigma = sqrt(|row|^2 - shift[0])  (rows of the rotated Cholesky factor of G + shift I: sqrt(lambda_i + shift) q_i^T)
 //   info[0] = kept rank = #{k < chi_max : sigma_k > max(cutoff, rank_tol) * sigma_0}, at least 1
 //   winfo[0] = discarded weight sum_{k >= kept} sigma_k^2 ; winfo[1] = sigma_0
 __global__ void __launch_bounds__(1024, 1)
 jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int n, double* __restrict__ Ut, int64_t ldu, int64_t ubs,
                        double* __restrict__ sigma, int64_t sbs, int* __restrict__ info, double* __restrict__ winfo, int chi_max, double cutoff,
-                       double rank_tol, int sqrt_mode) {
+                       double rank_tol, int sqrt_mode, const double* __restrict__ shift) {
     __shared__ double key[1024];
     __shared__ int perm[1024];
     __shared__ double red[32];
@@ -486,12 +491,14 @@ jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int
         for (int c = lane; c < n; c += 32) u[c] = g[c] * inv;
     }
     // singular values, kept rank, discarded weight
-    const double s0 = sqrt_mode ? sqrt(key[0]) : key[0];
+    const double delta = (sqrt_mode == 2 && shift) ? shift[0] : 0.0;
+    auto sv_of = [&](double k) { return sqrt_mode == 1 ? sqrt(k) : (sqrt_mode == 2 ? sqrt(fmax(fma(k, k, -delta), 0.0)) : k); };
+    const double s0 = sv_of(key[0]);
     const double thr = (cutoff > rank_tol ? cutoff : rank_tol) * s0;
     int cnt = 0;
     double wsum = 0.0;
     for (int k = tid; k < n; k += 1024) {
-        double sv = sqrt_mode ? sqrt(key[k]) : key[k];
+        double sv = sv_of(key[k]);
         sigma[k] = sv;
         if (k < chi_max && sv > thr) cnt++;
     }
@@ -503,7 +510,7 @@ jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int
     int keep = s_cnt < 1 ? 1 : s_cnt;
     // singular values are sorted, so the kept set {k < chi_max, sv > thr} is a prefix of length keep
     for (int k = tid; k < n; k += 1024) {
-        if (k >= keep) { double sv = sqrt_mode ? sqrt(key[k]) : key[k]; wsum = fma(sv, sv, wsum); }
+        if (k >= keep) { double sv = sv_of(key[k]); wsum = fma(sv, sv, wsum); }
     }
     wsum = warp_sum(wsum);
     if (lane == 0) red[warp] = wsum;
@@ -578,7 +585,7 @@ static int launch_jacobi(R* G, int64_t ld, int64_t bs, int n, int batch, const J
     return 0;
 }
 
-int jacobi_ctrl_stride(int max_sweeps) { return ((max_sweeps + 7) & ~1) + 128; }   // words: barrier, flags[max_sweeps], sweeps used, pad, 64-bit max norm, 128 block versions
+int jacobi_ctrl_stride(int max_sweeps) { return ((max_sweeps + 7) & ~1) + 128 * (JAC_XFER / 2); }   // words: barrier, flags[max_sweeps], sweeps used, pad, 64-bit max norm, versions of up to 128 blocks x pieces
 size_t jacobi_ctrl_bytes(int batch, int max_sweeps) { return (size_t)batch * jacobi_ctrl_stride(max_sweeps) * sizeof(unsigned); }
 
 int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes, int max_sweeps, double tol,
@@ -592,15 +599,18 @@ int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* c
     switch (pl.nreg) {
         case 4: return launch_jacobi<double, 4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
         case 8: return launch_jacobi<double, 8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        case 16: return launch_jacobi<double, 16, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);   // w = 8: one warp per stationary row, 255 registers each
+        case 16:
+            if (pl.w > 8) return launch_jacobi<double, 16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
+            return launch_jacobi<double, 16, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);   // w = 8: one warp per stationary row, 255 registers each
         default: return launch_jacobi<double, 32, 256>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
     }
 }
 
 int jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs, double* sigma,
-                        int64_t sbs, int* info, double* winfo, int chi_max, double cutoff, double rank_tol, int sqrt_mode, cudaStream_t st) {
+                        int64_t sbs, int* info, double* winfo, int chi_max, double cutoff, double rank_tol, int sqrt_mode, const double* shift,
+                        cudaStream_t st) {
     SYN_REQUIRE(n >= 1 && n <= 1024 && batch >= 1, "syn_jacobi_finalize_f64: n=%d batch=%d out of range", n, batch);
-    jacobi_finalize_kernel<<<batch, 1024, 0, st>>>(G, ld, bs, n, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode);
+    jacobi_finalize_kernel<<<batch, 1024, 0, st>>>(G, ld, bs, n, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode, shift);
     return launch_status("jacobi_finalize_kernel");
 }
 
@@ -695,7 +705,7 @@ extern "C" int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int
 
 extern "C" int syn_jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs,
                                        double* sigma, int64_t sbs, int* info, double* winfo, int chi_max, double cutoff, double rank_tol,
-                                       int sqrt_mode, void* stream) {
-    return syn::jacobi_finalize_f64(G, ld, bs, n, batch, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode,
+                                       int sqrt_mode, const double* shift, void* stream) {
+    return syn::jacobi_finalize_f64(G, ld, bs, n, batch, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode, shift,
                                     (cudaStream_t)stream);
 }

@@ -163,7 +163,20 @@ def jacobi_sweeps_used():
     return words[:, max_sweeps + 1].tolist()
 
 
-def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False):
+def chol_upper(G):
+    """Shifted Cholesky factor of a symmetric PSD matrix G (n x n contiguous, OVERWRITTEN): returns (B, shift) with B upper triangular,
+    G + shift I = B^T B and shift a device scalar.  jacobi_rows(B) + jacobi_finalize(B, ..., sqrt_mode=2, shift=shift) is then the
+    eigen-decomposition of G in fewer sweeps than jacobi_rows(G) (csrc/chol.cu)."""
+    require_cuda_f64(G)
+    n = G.shape[0]
+    assert G.dim() == 2 and G.shape[1] == n and G.stride(1) == 1
+    B = torch.empty((n, n), dtype=torch.float64, device=G.device)
+    shift = torch.empty((1,), dtype=torch.float64, device=G.device)
+    check(lib.syn_chol_upper_f64(ptr(G), _i64(G.stride(0)), _i32(n), ptr(B), _i64(n), ptr(shift), stream_ptr()), "syn_chol_upper_f64")
+    return B, shift
+
+
+def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shift=None):
     """Sort / normalise / cut the rows produced by jacobi_rows.  Returns (Ut, sigma, info[int32: keep, n], winfo[f64: discarded, s0])
     -- all DEVICE tensors; the caller decides when to synchronise on `info`."""
     require_cuda_f64(G)
@@ -176,7 +189,7 @@ def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False):
     winfo = torch.empty((nb, 2), dtype=torch.float64, device=G.device)
     rc = lib.syn_jacobi_finalize_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(Ut), _i64(n), _i64(n * n),
                                      ptr(sigma), _i64(n), ptr(info), ptr(winfo), _i32(int(chi_max)), _dbl(cutoff), _dbl(rank_tol),
-                                     _i32(1 if sqrt_mode else 0), stream_ptr())
+                                     _i32(int(sqrt_mode)), ptr(shift) if shift is not None else None, stream_ptr())
     check(rc, "syn_jacobi_finalize_f64")
     if not batched:
         return Ut[0], sigma[0], info[0], winfo[0]

@@ -114,7 +114,8 @@ def test_fp32_preconditioned_eigensolver_option():
     B = rng.normal(size=(256, 1024))
     A = B @ B.T
     ref = np.linalg.svd(B, compute_uv=False)
-    old = sw.PRECONDITION_MIN_N
+    old, old_chol = sw.PRECONDITION_MIN_N, sw.CHOLESKY_MIN_N
+    sw.CHOLESKY_MIN_N = 0
     try:
         for flag in (0, 256):
             sw.PRECONDITION_MIN_N = flag
@@ -124,4 +125,49 @@ def test_fp32_preconditioned_eigensolver_option():
             assert np.max(np.abs(U @ U.T - np.eye(256))) < 1e-11
             assert np.max(np.abs(U[:100] @ A @ U[:100].T - np.diag(ref[:100] ** 2))) < 1e-9 * ref[0] ** 2
     finally:
-        sw.PRECONDITION_MIN_N = old
+        sw.PRECONDITION_MIN_N, sw.CHOLESKY_MIN_N = old, old_chol
+
+
+@pytest.mark.parametrize("n,rank", [(200, 200), (512, 512), (320, 100), (130, 1), (1024, 700)])
+def test_shifted_cholesky_factor(n, rank):
+    """syn_chol_upper_f64: G + shift I = B^T B with B upper triangular, also for singular G (bond "inflation", short chains)."""
+    from syngular_b200 import ops
+    rng = np.random.default_rng(n + rank)
+    F = rng.normal(size=(n, rank)) * np.exp(-np.arange(rank) / (rank / 6.0 + 1.0))[None, :]
+    G = F @ F.T
+    B, shift = ops.chol_upper(torch.from_numpy(G.copy()).cuda())
+    B, delta = B.cpu().numpy(), float(shift.item())
+    assert 0.0 < delta <= 4.0 * n * 2.3e-16 * np.max(np.diag(G))
+    assert np.max(np.abs(np.tril(B, -1))) == 0.0
+    assert np.max(np.abs(B.T @ B - G - delta * np.eye(n))) < 2e-13 * np.max(np.diag(G))
+
+
+@pytest.mark.parametrize("n,rank", [(256, 256), (512, 512), (384, 150), (512, 256)])
+def test_eigh_gram_on_cholesky_factor(n, rank):
+    """eigh_gram through the shifted Cholesky factor (n > 128) against numpy and against the direct Jacobi-on-G path:
+    singular values to 1e-10 sigma_0, orthonormal eigenvectors, kept rank = numerical rank for singular Gram matrices."""
+    from syngular.tensor import _sweeps as sw
+    from syngular_b200 import ops
+    rng = np.random.default_rng(7 * n + rank)
+    F = rng.normal(size=(n, rank)) * np.exp(-np.arange(rank) / (rank / 8.0))[None, :]
+    A = F @ F.T
+    ref = np.zeros(n)
+    ref[:rank] = np.linalg.svd(F, compute_uv=False)
+    keep_ref = int(np.sum(ref[:n // 2] > 3.2e-7 * ref[0]))
+    sweeps = {}
+    old = sw.CHOLESKY_MIN_N
+    try:
+        for flag in (129, 0):
+            sw.CHOLESKY_MIN_N = flag
+            Ut, sigma, info, winfo = sw.eigh_gram(torch.from_numpy(A.copy()).cuda(), n // 2, 0.0, 3.2e-7)
+            sweeps[flag] = ops.jacobi_sweeps_used()[0]
+            keep = int(info[0].item())
+            assert keep == keep_ref
+            assert np.max(np.abs(sigma.cpu().numpy()[:keep] - ref[:keep])) < 1e-10 * ref[0]
+            U = Ut.cpu().numpy()[:keep]
+            assert np.max(np.abs(U @ U.T - np.eye(keep))) < 1e-11
+            assert np.max(np.abs(U @ A @ U.T - np.diag(ref[:keep] ** 2))) < 1e-9 * ref[0] ** 2
+            assert abs(winfo[0].item() - np.sum(ref[keep:] ** 2)) < 1e-10 * ref[0] ** 2
+    finally:
+        sw.CHOLESKY_MIN_N = old
+    assert sweeps[129] <= sweeps[0]
