@@ -81,6 +81,12 @@ int    syn_jacobi_ctrl_stride(int max_sweeps);   /* 32-bit words per problem in 
  * threshold of the finalize step); 0 disables the test. */
 int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes,
                         int max_sweeps, double tol, double null_rel, void* stream);
+/* Host only (no GPU needed): the block-level ordering of one sweep that the multi-CTA kernel follows for P CTAs (P = 2..64, a
+ * power of two; 2P row blocks, 2P - 1 rounds).  table[2 * (round * P + cta)] = blockA | blockB << 8 | flags << 16 with flags
+ * 1/2 = load A/B, 4/8 = store A/B, 16 = also rotate the pairs inside both blocks; table[.. + 1] = versionA | versionB << 16 the
+ * blocks must have reached (stores earlier in the sweep); cnt[block] = stores of the block per sweep.  Slot A only changes when
+ * the recursion descends (log2 P times per sweep), so only slot B is handed from CTA to CTA each round. */
+int syn_jacobi_ring_schedule(int P, uint32_t* table, uint32_t* cnt);
 /* FP32 variant of the same kernel and the helpers of the FP32-preconditioned symmetric eigen-solver
  * (syngular/tensor/_sweeps.py: eigh_gram): FP32 Jacobi gives an approximate eigenbasis, it is re-orthonormalised in FP64
  * (Newton-Schulz, GEMMs), the matrix is transformed with it, and the FP64 Jacobi finishes in ~3 sweeps instead of ~13. */

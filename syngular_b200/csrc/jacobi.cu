@@ -20,6 +20,10 @@
 // the discarded weight -- the singular-value cutoff is fused here, not done on the host.
 #include <cstdlib>
 
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace syn {
@@ -184,6 +188,7 @@ __device__ __forceinline__ R row_sumsq(const R* __restrict__ a, int n, int lane)
     return warp_sum(s0 + s1);
 }
 
+constexpr unsigned JF_LOAD_A = 1u, JF_LOAD_B = 2u, JF_STORE_A = 4u, JF_STORE_B = 8u, JF_ALLPAIRS = 16u;   // per-round flags of the hand-over schedule
 constexpr int JAC_XFER = 4;        // pieces a round's hand-over is split into (2 blocks x 2 halves), each with its own thread and version word
 
 // grid = (P, problems in this launch).  ctrl layout per problem: [0] barrier counter, [1 + sweep] rotation flags,
@@ -191,7 +196,7 @@ constexpr int JAC_XFER = 4;        // pieces a round's hand-over is split into (
 template <typename R, int NREG, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int P, unsigned* __restrict__ ctrl, int ctrl_stride,
-                   int max_sweeps, double tol2_, double null_rel2_) {
+                   int max_sweeps, double tol2_, double null_rel2_, const uint2* __restrict__ sched, const unsigned* __restrict__ sched_cnt) {
     const R tol2 = (R)tol2_, null_rel2 = (R)null_rel2_;
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char jac_smem_raw[];
@@ -216,6 +221,10 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
     const bool full = (n == 32 * NREG);
     // TMA path: multi-CTA problem, every block full, rows 16-byte aligned and dense in shared memory
     const bool tma = (P > 1) && vec2 && (n == 2 * P * w) && (LDS == n);
+    // Ring schedule (host-built table, see jac_ring_schedule): slot A (rows [0, w)) keeps its block over many rounds -- it stays in the
+    // registers of the warps and never travels --, only slot B (rows [w, 2w)) is handed over: half the bytes of the circle method,
+    // and the hand-over is bound by the ~46 B/clk one SM can move to and from L2 (tools/microbench/l2_handover.cu).
+    const bool ring = tma && (sched != nullptr) && (w <= WARPS);
     uint32_t mbar_phase = 0;
     if (tma) {
         if (tid == 0) mbar_init(&s_mbar, JAC_XFER);   // one producer per piece
@@ -294,6 +303,11 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
 #else
 #define JTICK(i) do { } while (0)
 #endif
+    R ra[NREG];                    // stationary row of this warp (ring schedule: lives across rounds)
+    R na = R(0);
+    bool a_regs = false;           // slot A currently lives in registers, its shared-memory copy is stale
+#pragma unroll
+    for (int k = 0; k < NREG; k++) ra[k] = R(0);
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
@@ -301,7 +315,16 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
             JTICK(5);
             // round-robin tournament over the NB blocks (circle method): CTA p plays (b0, b1) in round t
             int b0, b1;
+            unsigned fl = JF_LOAD_A | JF_LOAD_B | JF_STORE_A | JF_STORE_B | (t == 0 ? JF_ALLPAIRS : 0u);
+            unsigned need0 = (unsigned)(sweep * Mr + t), need1 = need0, done0 = need0 + 1u, done1 = done0;
             if (P == 1) { b0 = 0; b1 = 1; }
+            else if (ring) {
+                const uint2 e = sched[t * P + p];
+                b0 = (int)(e.x & 0xffu); b1 = (int)((e.x >> 8) & 0xffu); fl = (e.x >> 16) & 0xffu;
+                const unsigned c0 = sched_cnt[b0] * (unsigned)sweep, c1 = sched_cnt[b1] * (unsigned)sweep;
+                need0 = c0 + (e.y & 0xffffu); need1 = c1 + (e.y >> 16);
+                done0 = need0 + 1u; done1 = need1 + 1u;
+            }
             else if (p == 0) { b0 = NB - 1; b1 = t % Mr; }
             else { b0 = (t + p) % Mr; b1 = (t - p + Mr) % Mr; }
             if (tma) {
@@ -311,18 +334,22 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                     const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)wr * row_bytes;
                     // point-to-point hand-over instead of a grid barrier: a block is ready when the CTA that held it in the
                     // previous round has published its version (every block takes part in every round)
-                    const unsigned need = (unsigned)(sweep * Mr + t);
-                    for (unsigned spin = 0; ld_acquire_u32(ver + blk * (JAC_XFER / 2) + sub) < need; ++spin) {
-                        if (spin > (1u << 26)) __trap();
-                        __nanosleep(20);
+                    if (fl & (h ? JF_LOAD_B : JF_LOAD_A)) {
+                        const unsigned need = h ? need1 : need0;
+                        for (unsigned spin = 0; ld_acquire_u32(ver + blk * (JAC_XFER / 2) + sub) < need; ++spin) {
+                            if (spin > (1u << 26)) __trap();
+                            __nanosleep(20);
+                        }
+                        JTICK(0);
+                        fence_proxy_async();
+                        mbar_expect_tx(&s_mbar, blk_bytes);
+                        const R* src = G + (int64_t)(blk * w + sub * wr) * ld;
+                        R* dst = rows + (h * w + sub * wr) * LDS;
+                        if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
+                        else for (int r = 0; r < wr; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
+                    } else {
+                        mbar_arrive(&s_mbar);          // this piece stays where it is
                     }
-                    JTICK(0);
-                    fence_proxy_async();
-                    mbar_expect_tx(&s_mbar, blk_bytes);
-                    const R* src = G + (int64_t)(blk * w + sub * wr) * ld;
-                    R* dst = rows + (h * w + sub * wr) * LDS;
-                    if (ld == n) bulk_g2s(dst, src, blk_bytes, &s_mbar);
-                    else for (int r = 0; r < wr; ++r) bulk_g2s(dst + r * LDS, src + (int64_t)r * ld, row_bytes, &s_mbar);
                 }
                 mbar_wait(&s_mbar, mbar_phase);
                 mbar_phase ^= 1u;
@@ -332,7 +359,15 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                 load_block(b1, 1);
                 __syncthreads();
             }
-            if (t == 0) {
+            if (fl & JF_ALLPAIRS) {
+                if (a_regs) {              // slot A comes back from the registers
+                    if (warp < w) {
+#pragma unroll
+                        for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; if (c < n) rows[warp * LDS + c] = ra[k]; }
+                    }
+                    a_regs = false;
+                    __syncthreads();
+                }
                 // all pairs among the 2w local rows (within-block pairs are visited once per sweep, here)
                 const int items = 2 * w, rounds = items - 1;
                 for (int s = 0; s < rounds; ++s) {
@@ -346,11 +381,12 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                 }
             } else if (w <= WARPS) {
                 // cross pairs only: row k of block b0 (held in registers by warp k) with row (k+s) mod w of block b1
-                R ra[NREG];
-                R na = R(0);
                 if (warp < w) {
+                    if (!a_regs) {
 #pragma unroll
-                    for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; ra[k] = c < n ? rows[warp * LDS + c] : R(0); }
+                        for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; ra[k] = c < n ? rows[warp * LDS + c] : R(0); }
+                    }
+                    na = R(0);             // recomputed every round: the analytic updates of the cached norm do not accumulate
 #pragma unroll
                     for (int k = 0; k < NREG; k++) na = fma(ra[k], ra[k], na);
                     na = warp_sum(na);
@@ -368,9 +404,13 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                     }
                     __syncthreads();
                 }
-                if (warp < w) {
+                a_regs = true;
+                if (!ring || (fl & JF_STORE_A)) {          // slot A leaves (always, under the circle method)
+                    if (warp < w) {
 #pragma unroll
-                    for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; if (c < n) rows[warp * LDS + c] = ra[k]; }
+                        for (int k = 0; k < NREG; k++) { int c = lane + 32 * k; if (c < n) rows[warp * LDS + c] = ra[k]; }
+                    }
+                    a_regs = false;
                 }
                 JTICK(3);
                 __syncthreads();
@@ -391,13 +431,15 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
                     const int h = warp / (JAC_XFER / 2), sub = warp % (JAC_XFER / 2), blk = h ? b1 : b0;
                     const int wr = w / (JAC_XFER / 2);
                     const uint32_t row_bytes = (uint32_t)n * (uint32_t)sizeof(R), blk_bytes = (uint32_t)wr * row_bytes;
-                    R* dst = G + (int64_t)(blk * w + sub * wr) * ld;
-                    const R* src = rows + (h * w + sub * wr) * LDS;
-                    if (ld == n) bulk_s2g(dst, src, blk_bytes);
-                    else for (int r = 0; r < wr; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
-                    bulk_commit_wait_all();        // writes complete (and shared memory free) before they are published
-                    fence_proxy_async();           // async-proxy writes ordered before the generic-proxy release below
-                    st_release_u32(ver + blk * (JAC_XFER / 2) + sub, (unsigned)(sweep * Mr + t) + 1u);
+                    if (fl & (h ? JF_STORE_B : JF_STORE_A)) {
+                        R* dst = G + (int64_t)(blk * w + sub * wr) * ld;
+                        const R* src = rows + (h * w + sub * wr) * LDS;
+                        if (ld == n) bulk_s2g(dst, src, blk_bytes);
+                        else for (int r = 0; r < wr; ++r) bulk_s2g(dst + (int64_t)r * ld, src + r * LDS, row_bytes);
+                        bulk_commit_wait_all();        // writes complete (and shared memory free) before they are published
+                        fence_proxy_async();           // async-proxy writes ordered before the generic-proxy release below
+                        st_release_u32(ver + blk * (JAC_XFER / 2) + sub, h ? done1 : done0);
+                    }
                 }
             } else if (P > 1) {
                 store_block(b0, 0);
@@ -523,6 +565,113 @@ jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int
 }
 
 // ---- host drivers --------------------------------------------------------------------------------------------------------
+// ---- ring schedule ----------------------------------------------------------------------------------------------------------
+// Block-level ordering of one sweep for NB = 2P blocks (P a power of two), as a table [round][CTA] -> (block in slot A, block in
+// slot B, flags, versions to wait for).  Recursive: the first half of the blocks stays put (slot A of P CTAs), the second half
+// rotates past them (slot B) for NB/2 rounds; then both halves are treated the same way on half the CTAs each, down to pairs of
+// blocks, whose round also visits the pairs inside the two blocks.  NB - 1 rounds like the circle method, every pair of rows once,
+// same or fewer sweeps to converge (simulated on Gram matrices of the density-matrix algorithm) -- but slot A only moves when the
+// recursion descends, log2(P) times per sweep instead of every round.
+struct RingRound { std::vector<int> a, b; bool allpairs; };
+
+static void ring_rounds(const std::vector<int>& blocks, const std::vector<int>& ctas, size_t first, std::vector<RingRound>& out, int P) {
+    const size_t m = blocks.size();
+    auto at = [&](size_t r) -> RingRound& {
+        while (out.size() <= r) { RingRound rr; rr.a.assign(P, -1); rr.b.assign(P, -1); rr.allpairs = false; out.push_back(rr); }
+        return out[r];
+    };
+    if (m == 2) {
+        RingRound& rr = at(first);
+        rr.a[ctas[0]] = blocks[0]; rr.b[ctas[0]] = blocks[1]; rr.allpairs = true;
+        return;
+    }
+    const size_t h = m / 2;
+    for (size_t t = 0; t < h; ++t) {
+        RingRound& rr = at(first + t);
+        for (size_t q = 0; q < h; ++q) { rr.a[ctas[q]] = blocks[q]; rr.b[ctas[q]] = blocks[h + (q + t) % h]; }
+    }
+    std::vector<int> s(blocks.begin(), blocks.begin() + h), mv(blocks.begin() + h, blocks.end());
+    std::vector<int> c0(ctas.begin(), ctas.begin() + h / 2), c1(ctas.begin() + h / 2, ctas.end());
+    ring_rounds(s, c0, first + h, out, P);
+    ring_rounds(mv, c1, first + h, out, P);
+}
+
+// entries: x = blkA | blkB << 8 | flags << 16 ; y = needA | needB << 16 (stores of that block earlier in the sweep); cnt[blk] = stores
+// of the block per sweep (the version counters keep counting across sweeps)
+static void jac_ring_schedule(int P, std::vector<uint2>& table, std::vector<unsigned>& cnt) {
+    const int NB = 2 * P;
+    std::vector<int> blocks(NB), ctas(P);
+    for (int i = 0; i < NB; ++i) blocks[i] = i;
+    for (int i = 0; i < P; ++i) ctas[i] = i;
+    std::vector<RingRound> rounds;
+    ring_rounds(blocks, ctas, 0, rounds, P);
+    const int R = (int)rounds.size();           // NB - 1
+    table.assign((size_t)R * P, make_uint2(0u, 0u));
+    cnt.assign(NB, 0u);
+    for (int r = 0; r < R; ++r) {
+        for (int q = 0; q < P; ++q) {
+            const int a = rounds[r].a[q], b = rounds[r].b[q];
+            unsigned fl = rounds[r].allpairs ? JF_ALLPAIRS : 0u;
+            if (r == 0 || rounds[r - 1].a[q] != a) fl |= JF_LOAD_A;
+            if (r == 0 || rounds[r - 1].b[q] != b) fl |= JF_LOAD_B;
+            if (r == R - 1 || rounds[r + 1].a[q] != a) fl |= JF_STORE_A;
+            if (r == R - 1 || rounds[r + 1].b[q] != b) fl |= JF_STORE_B;
+            table[(size_t)r * P + q] = make_uint2((unsigned)a | ((unsigned)b << 8) | (fl << 16), cnt[a] | (cnt[b] << 16));
+        }
+        for (int q = 0; q < P; ++q) {            // versions advance after the round
+            const unsigned fl = (table[(size_t)r * P + q].x >> 16) & 0xffu;
+            if (fl & JF_STORE_A) cnt[rounds[r].a[q]]++;
+            if (fl & JF_STORE_B) cnt[rounds[r].b[q]]++;
+        }
+    }
+}
+
+constexpr int JAC_SCHED_MAX_LOG2P = 6;                     // P <= 64 (n = 1024, w = 8)
+constexpr int JAC_SCHED_ENTRIES = 10800;                   // sum over P = 2 .. 64 of (2P - 1) P  = 10794
+__device__ uint2 g_jac_sched[JAC_SCHED_ENTRIES];
+__device__ unsigned g_jac_sched_cnt[JAC_SCHED_MAX_LOG2P * 128];
+
+static bool jac_env_ring() {   // experiment knob: SYN_JACOBI_RING=0 falls back to the circle method
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SYN_JACOBI_RING"); v = e ? (atoi(e) != 0) : 1; }
+    return v != 0;
+}
+
+// device pointers to the schedule of a P-CTA problem (uploaded once per device), or nulls when P is not a power of two
+static int jac_schedule_ptrs(int P, const uint2** sched, const unsigned** cnt) {
+    *sched = nullptr; *cnt = nullptr;
+    int lg = 0;
+    while ((1 << lg) < P) ++lg;
+    if (P < 2 || (1 << lg) != P || lg > JAC_SCHED_MAX_LOG2P || !jac_env_ring()) return 0;
+    static std::mutex mu;
+    static bool uploaded[64] = {false};
+    int dev = 0;
+    SYN_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && !uploaded[dev]) {
+        std::vector<uint2> all(JAC_SCHED_ENTRIES, make_uint2(0u, 0u));
+        std::vector<unsigned> allc(JAC_SCHED_MAX_LOG2P * 128, 0u);
+        size_t off = 0;
+        for (int k = 1; k <= JAC_SCHED_MAX_LOG2P; ++k) {
+            std::vector<uint2> t; std::vector<unsigned> c;
+            jac_ring_schedule(1 << k, t, c);
+            std::copy(t.begin(), t.end(), all.begin() + off);
+            std::copy(c.begin(), c.end(), allc.begin() + (size_t)(k - 1) * 128);
+            off += t.size();
+        }
+        SYN_CUDA(cudaMemcpyToSymbol(g_jac_sched, all.data(), all.size() * sizeof(uint2)));
+        SYN_CUDA(cudaMemcpyToSymbol(g_jac_sched_cnt, allc.data(), allc.size() * sizeof(unsigned)));
+        uploaded[dev] = true;
+    }
+    size_t off = 0;
+    for (int k = 1; k < lg; ++k) off += (size_t)((2 << k) - 1) * (1 << k);
+    uint2* base = nullptr; unsigned* cbase = nullptr;
+    SYN_CUDA(cudaGetSymbolAddress((void**)&base, g_jac_sched));
+    SYN_CUDA(cudaGetSymbolAddress((void**)&cbase, g_jac_sched_cnt));
+    *sched = base + off;
+    *cnt = cbase + (size_t)(lg - 1) * 128;
+    return 0;
+}
 struct JacPlan { int w, P, nreg; size_t smem; };
 
 static int jac_env_w() {   // experiment knob: SYN_JACOBI_W=8 forces the block height of multi-CTA problems
@@ -566,19 +715,22 @@ static int launch_jacobi(R* G, int64_t ld, int64_t bs, int n, int batch, const J
     SYN_REQUIRE(pl.P <= max_ctas, "syn_jacobi_rows_f64: problem needs %d co-resident CTAs, device fits %d", pl.P, max_ctas);
     int chunk = max_ctas / pl.P;
     if (chunk > 65535) chunk = 65535;
+    const uint2* sched = nullptr;
+    const unsigned* sched_cnt = nullptr;
+    if (pl.P > 1) { if (int rc = jac_schedule_ptrs(pl.P, &sched, &sched_cnt)) return rc; }
     double tol2 = tol * tol, null_rel2 = null_rel * null_rel;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         int nb = (batch - b0) < chunk ? (batch - b0) : chunk;
         R* Gb = G + (int64_t)b0 * bs;
         unsigned* cb = ctrl + (int64_t)b0 * ctrl_stride;
         int w = pl.w, P = pl.P;
-        void* args[] = {&Gb, &ld, &bs, &n, &w, &P, &cb, &ctrl_stride, &max_sweeps, &tol2, &null_rel2};
+        void* args[] = {&Gb, &ld, &bs, &n, &w, &P, &cb, &ctrl_stride, &max_sweeps, &tol2, &null_rel2, &sched, &sched_cnt};
         dim3 grid(pl.P, nb), block(THREADS);
         if (pl.P > 1) {
             SYN_CUDA(cudaLaunchCooperativeKernel((void*)kern, grid, block, args, pl.smem, st));
             note_launch();
         } else {
-            kern<<<grid, block, pl.smem, st>>>(Gb, ld, bs, n, w, P, cb, ctrl_stride, max_sweeps, tol2, null_rel2);
+            kern<<<grid, block, pl.smem, st>>>(Gb, ld, bs, n, w, P, cb, ctrl_stride, max_sweeps, tol2, null_rel2, sched, sched_cnt);
             if (int rc = launch_status("jacobi_rows_kernel")) return rc;
         }
     }
@@ -695,6 +847,17 @@ extern "C" int syn_identity_deviation_f64(const double* X, int n, double* out, v
     return launch_status("identity_dev_kernel");
 }
 
+extern "C" int syn_jacobi_ring_schedule(int P, uint32_t* table, uint32_t* cnt) {
+    int lg = 0;
+    while ((1 << lg) < P) ++lg;
+    SYN_REQUIRE(P >= 2 && P <= 64 && (1 << lg) == P && table && cnt, "syn_jacobi_ring_schedule: P=%d must be a power of two in 2..64", P);
+    std::vector<uint2> t;
+    std::vector<unsigned> c;
+    syn::jac_ring_schedule(P, t, c);
+    for (size_t i = 0; i < t.size(); ++i) { table[2 * i] = t[i].x; table[2 * i + 1] = t[i].y; }
+    for (size_t i = 0; i < c.size(); ++i) cnt[i] = c[i];
+    return 0;
+}
 extern "C" size_t syn_jacobi_ctrl_bytes(int batch, int max_sweeps) { return syn::jacobi_ctrl_bytes(batch, max_sweeps); }
 extern "C" int syn_jacobi_ctrl_stride(int max_sweeps) { return syn::jacobi_ctrl_stride(max_sweeps); }
 

@@ -67,3 +67,53 @@ def test_product_has_no_cpu_fallback():
     for mod in ("syngular", "syngular.tensor", "syngular_b200.ops"):
         src = open(sys.modules[mod].__file__).read()
         assert "oracle" not in src
+
+
+def test_jacobi_ring_schedule_is_a_complete_consistent_ordering():
+    """Host logic of the multi-CTA Jacobi: every pair of row blocks meets exactly once per sweep, no block is in two places in
+    one round, a slot that is not reloaded still holds the block from the previous round, and the version a load waits for is
+    exactly the number of earlier stores of that block."""
+    import ctypes
+    import numpy as np
+    from syngular_b200.build import LIB
+    lib = ctypes.CDLL(LIB)
+    for P in (2, 4, 8, 16, 32, 64):
+        NB, R = 2 * P, 2 * P - 1
+        table = np.zeros((R * P, 2), dtype=np.uint32)
+        cnt = np.zeros(NB, dtype=np.uint32)
+        rc = lib.syn_jacobi_ring_schedule(P, table.ctypes.data_as(ctypes.c_void_p), cnt.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        pairs, ver = set(), [0] * NB
+        hold_a, hold_b = [-1] * P, [-1] * P
+        loads = 0
+        for r in range(R):
+            used = set()
+            for q in range(P):
+                x, y = int(table[r * P + q, 0]), int(table[r * P + q, 1])
+                a, b, fl = x & 0xFF, (x >> 8) & 0xFF, (x >> 16) & 0xFF
+                assert a != b and a < NB and b < NB and a not in used and b not in used
+                used.update((a, b))
+                key = (min(a, b), max(a, b))
+                assert key not in pairs
+                pairs.add(key)
+                if fl & 1:
+                    assert ver[a] == (y & 0xFFFF); loads += 1
+                else:
+                    assert hold_a[q] == a
+                if fl & 2:
+                    assert ver[b] == (y >> 16); loads += 1
+                else:
+                    assert hold_b[q] == b
+                assert bool(fl & 16) == (r == R - 1)
+                hold_a[q], hold_b[q] = a, b
+            assert len(used) == NB
+            for q in range(P):
+                x = int(table[r * P + q, 0]); a, b, fl = x & 0xFF, (x >> 8) & 0xFF, (x >> 16) & 0xFF
+                if fl & 4:
+                    ver[a] += 1; hold_a[q] = -1
+                if fl & 8:
+                    ver[b] += 1; hold_b[q] = -1
+        assert len(pairs) == NB * (NB - 1) // 2
+        assert ver == [int(c) for c in cnt]
+        assert loads < (0.6 if P >= 8 else 0.8) * 2 * P * R        # about half the block traffic of the circle method
+    assert lib.syn_jacobi_ring_schedule(3, table.ctypes.data_as(ctypes.c_void_p), cnt.ctypes.data_as(ctypes.c_void_p)) != 0
