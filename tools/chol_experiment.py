@@ -26,7 +26,9 @@ def spy(G, *a, **k):
 X, W = bench.make_chain(2)
 Xd = [sw.as_core(x) for x in X]; Wd = [sw.as_core(w) for w in W]
 ops.jacobi_rows = spy
+sw.CHOLESKY_MIN_N = 0            # capture the Gram matrices themselves, not their factors
 sw.apply_round_dm(Xd, Wd, 256)
+sw.CHOLESKY_MIN_N = 129
 ops.jacobi_rows = orig
 for idx in (3, 8, 20, 32, 50):
     A = captured[idx]; n = A.shape[-1]
