@@ -99,17 +99,18 @@ int syn_identity_deviation_f64(const double* X, int n, double* out, void* stream
  * info[2*b] = kept rank, winfo[2*b] = discarded weight sum_{k>=kept} sigma_k^2, winfo[2*b+1] = sigma_0.
  * sqrt_mode = 1 when G was a Gram matrix M E M^T (rows are lambda_i u_i^T, sigma_i = sqrt(lambda_i));
  * sqrt_mode = 2 when G was the factor of syn_chol_upper_f64 (rows are sqrt(lambda_i + shift) q_i^T, sigma_i = sqrt(lambda_i));
- * shift: device scalar written by syn_chol_upper_f64 (read only when sqrt_mode = 2; may be NULL otherwise). */
+ * shift: device array (one per problem) written by syn_chol_upper_f64 (read only when sqrt_mode = 2; may be NULL otherwise). */
 int syn_jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs,
                             double* sigma, int64_t sbs, int* info, double* winfo, int chi_max, double cutoff,
                             double rank_tol, int sqrt_mode, const double* shift, void* stream);
 /* Shifted Cholesky factor of a symmetric PSD Gram matrix (the M E M^T of the density-matrix rounding; finished form of the
  * reference's MATMUL_MODE "opti" branch, matrix_product_operator.py:193-260, whose np.linalg.eigh at :228 this pipeline replaces):
- *   G (n x n, row-major ld, overwritten)  ->  B (n x n, row-major ldb) upper triangular with  G + shift[0] I = B^T B,
- *   shift[0] = 2 n eps max_i G_ii (device scalar) keeps the factorisation defined for singular G.
+ *   G (batch x n x n, row-major ld, batch stride bs, overwritten when n > 128)  ->  B (row-major ldb, batch stride bbs) upper
+ *   triangular with  G_b + shift[b] I = B_b^T B_b;  shift[b] = 2 n eps max_i G_ii (device array of `batch` doubles) keeps the
+ *   factorisation defined for singular G.  n <= 128: one CTA per problem, one launch; larger n: 64-column panels.
  * One-sided Jacobi on the rows of B (syn_jacobi_rows_f64) then converges in ~10 sweeps instead of ~13-27 on G itself, and
  * syn_jacobi_finalize_f64(sqrt_mode = 2, shift) returns the eigenvectors of G and sigma_i = sqrt(lambda_i). */
-int syn_chol_upper_f64(double* G, int64_t ld, int n, double* B, int64_t ldb, double* shift, void* stream);
+int syn_chol_upper_f64(double* G, int64_t ld, int64_t bs, int n, int batch, double* B, int64_t ldb, int64_t bbs, double* shift, void* stream);
 
 /* ---- block assembly and elementwise kernels ---------------------------------------------------------------- */
 /* `A + B` site: direct sum of the bond spaces, self's block first; cores as (l, phys, r) with the physical legs flattened

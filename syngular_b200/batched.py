@@ -159,8 +159,10 @@ class BatchedMatrixProductState:
             ops.gemm(M, E[k + 1], ME, M=rows, N=D, K=D, a_m=D, a_k=1, b_k=D, b_n=1, c_m=D, c_n=(1, r, b),
                      batch=B, a_b=rows * D, b_b=D * D, c_b=rows * D)
             A = ops.matmul(ME, M.transpose(1, 2))
-            ops.jacobi_rows(A, null_rel=1e-13)
-            Ut, sigma, info, winfo = ops.jacobi_finalize(A, chi, rank_tol=0.0, sqrt_mode=True)
+            # Jacobi on the rows of the shifted Cholesky factor of A (fewer sweeps than on A itself, see csrc/chol.cu)
+            Bf, shift = ops.chol_upper(A)
+            ops.jacobi_rows(Bf, null_rel=0.0)
+            Ut, sigma, info, winfo = ops.jacobi_finalize(Bf, chi, rank_tol=0.0, sqrt_mode=2, shift=shift)
             right_dim = 1                                               # dimension of the space to the right of this bond
             for wj in W[k + 1:]:
                 right_dim = min(right_dim * int(wj.shape[2]), 1 << 30)

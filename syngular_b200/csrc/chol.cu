@@ -44,6 +44,104 @@ static syn_index_t CIX(int64_t stride) {
     return i;
 }
 
+// Cholesky factor of a (16 BS) x (16 BS) symmetric positive definite block held in REGISTERS: 16 x 16 threads own BS x BS blocks
+// (the lower triangle of blocks works).  Step j: the owners of column j publish it unscaled (its entry j is the pivot) in a
+// double-buffered shared vector -- one barrier per step --, everybody derives 1/pivot itself and applies the rank-1 update to its
+// block.  On return a holds L (garbage above the diagonal of the diagonal blocks), invd[j] = 1 / L_jj.
+template <int BS>
+__device__ __forceinline__ void potrf_regs(double (&a)[BS][BS], double* __restrict__ col /* [2][16 BS] */, double* __restrict__ invd,
+                                           double floor_piv, int ty, int tx, int block_cols) {
+    constexpr int N = 16 * BS;
+    for (int jb = 0; jb < block_cols; ++jb) {
+#pragma unroll
+        for (int jj = 0; jj < BS; ++jj) {
+            const int j = BS * jb + jj;
+            double* cb = col + (j & 1) * N;
+            const bool col_owner = (tx == jb && ty >= jb);
+            if (col_owner) {
+#pragma unroll
+                for (int r = 0; r < BS; ++r) cb[BS * ty + r] = a[r][jj];
+            }
+            __syncthreads();
+            double piv = cb[j];
+            piv = piv > floor_piv ? piv : floor_piv;                    // only reachable through rounding: G + delta I is positive definite
+            if (ty >= tx && tx >= jb) {
+                const double rinv = rcp_newton2(piv);
+                double cr[BS], cc[BS];
+#pragma unroll
+                for (int r = 0; r < BS; ++r) cr[r] = cb[BS * ty + r];
+#pragma unroll
+                for (int c = 0; c < BS; ++c) cc[c] = cb[BS * tx + c] * rinv;
+#pragma unroll
+                for (int r = 0; r < BS; ++r)
+#pragma unroll
+                    for (int c = 0; c < BS; ++c)
+                        if (BS * tx + c > j && BS * ty + r > j) a[r][c] = fma(-cr[r], cc[c], a[r][c]);
+            }
+            if (col_owner) {                                            // column j of L
+                const double rs = rsqrt_newton2(piv);
+                double l = piv * rs;
+                l = fma(fma(-l, l, piv), 0.5 * rs, l);                  // sqrt(piv) to the last bit or two
+#pragma unroll
+                for (int r = 0; r < BS; ++r) {
+                    if (BS * ty + r > j) a[r][jj] *= rs;
+                    else if (BS * ty + r == j) { a[r][jj] = l; invd[j] = rs; }
+                }
+            }
+        }
+    }
+}
+
+// Small problems (n <= 128), one CTA per problem, batched: shift, factor and transposed write in one launch.
+template <int BS>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_small_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int n, double* __restrict__ B, int64_t ldb, int64_t bbs,
+                  double* __restrict__ shift) {
+    constexpr int N = 16 * BS;
+    __shared__ double col[2 * N];
+    __shared__ double invd[N];
+    __shared__ double red[CH_THREADS / 32];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    G += (int64_t)blockIdx.x * bs;
+    B += (int64_t)blockIdx.x * bbs;
+    double a[BS][BS];
+    double mx = 0.0;
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) {
+            const int i = BS * ty + r, j = BS * tx + c;
+            double v = (i == j) ? 1.0 : 0.0;
+            if (i < n && j < n) {
+                v = (j <= i) ? G[(int64_t)i * ld + j] : 0.0;
+                if (i == j) mx = fmax(mx, v);
+            }
+            a[r][c] = v;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int k = 1; k < CH_THREADS / 32; k++) mx = fmax(mx, red[k]);
+    const double delta = 2.0 * (double)n * 2.220446049250313e-16 * mx;
+    if (tid == 0) shift[blockIdx.x] = delta;
+    if (ty == tx) {
+#pragma unroll
+        for (int r = 0; r < BS; ++r)
+            if (BS * ty + r < n) a[r][r] += delta;
+    }
+    potrf_regs<BS>(a, col, invd, 0.25 * delta, ty, tx, (n + BS - 1) / BS);
+#pragma unroll
+    for (int c = 0; c < BS; ++c)
+#pragma unroll
+        for (int r = 0; r < BS; ++r) {
+            const int i = BS * ty + r, j = BS * tx + c;       // L[i][j] -> B[j][i]; zeros below the diagonal of B
+            if (i < n && j < n) B[(int64_t)j * ldb + i] = (j <= i) ? a[r][c] : 0.0;
+        }
+}
+
 // Panel k0: D = G[k0:k0+nb, k0:k0+nb] -> L11 (lower); rows below: L21 = A21 L11^-T.  L is written back into G (lower part, the
 // trailing GEMM reads L21 from there) and, transposed, into B.
 __global__ void __launch_bounds__(CH_THREADS, 1)
@@ -57,7 +155,7 @@ chol_panel_kernel(double* __restrict__ G, int64_t ld, int n, int k0, int nb, dou
     // Diagonal block, padded to 64 x 64 with the identity, factored in REGISTERS: 16 x 16 threads own 4 x 4 blocks (the lower
     // triangle of blocks works).  Step j: the owners of column j publish it unscaled (its entry j is the pivot) in a double-buffered
     // shared vector -- one barrier per step --, everybody derives 1/pivot itself and applies the rank-1 update to its block.
-    __shared__ double col[2][CH_NB];
+    __shared__ double col[2 * CH_NB];
     const int ty = tid >> 4, tx = tid & 15;
     double a[4][4];
 #pragma unroll
@@ -69,43 +167,7 @@ chol_panel_kernel(double* __restrict__ G, int64_t ld, int n, int k0, int nb, dou
             if (i < nb && j < nb) v = (j <= i) ? G[(int64_t)(k0 + i) * ld + k0 + j] : 0.0;
             a[r][c] = v;
         }
-    for (int jb = 0; jb < CH_NB / 4; ++jb) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = 4 * jb + jj, buf = j & 1;
-            const bool col_owner = (tx == jb && ty >= jb);
-            if (col_owner) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) col[buf][4 * ty + r] = a[r][jj];
-            }
-            __syncthreads();
-            double piv = col[buf][j];
-            piv = piv > floor_piv ? piv : floor_piv;                    // only reachable through rounding: G + delta I is positive definite
-            if (ty >= tx && tx >= jb) {
-                const double rinv = rcp_newton2(piv);
-                double cr[4], cc[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) cr[r] = col[buf][4 * ty + r];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) cc[c] = col[buf][4 * tx + c] * rinv;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (4 * tx + c > j && 4 * ty + r > j) a[r][c] = fma(-cr[r], cc[c], a[r][c]);
-            }
-            if (col_owner) {                                            // column j of L
-                const double rs = rsqrt_newton2(piv);
-                double l = piv * rs;
-                l = fma(fma(-l, l, piv), 0.5 * rs, l);                  // sqrt(piv) to the last bit or two
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if (4 * ty + r > j) a[r][jj] *= rs;
-                    else if (4 * ty + r == j) { a[r][jj] = l; invd[j] = rs; }
-                }
-            }
-        }
-    }
+    potrf_regs<4>(a, col, invd, floor_piv, ty, tx, CH_NB / 4);
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -174,9 +236,7 @@ chol_panel_kernel(double* __restrict__ G, int64_t ld, int n, int k0, int nb, dou
     }
 }
 
-int chol_upper_f64(double* G, int64_t ld, int n, double* B, int64_t ldb, double* shift, cudaStream_t st) {
-    SYN_REQUIRE(n >= 1 && n <= 4096 && ld >= n && ldb >= n, "syn_chol_upper_f64: n=%d ld=%lld ldb=%lld out of range", n, (long long)ld, (long long)ldb);
-    SYN_REQUIRE(G && B && shift, "syn_chol_upper_f64: null pointer");
+static int chol_upper_one(double* G, int64_t ld, int n, double* B, int64_t ldb, double* shift, cudaStream_t st) {
     static bool configured = false;
     const size_t smem = (size_t)CH_SLAB * CH_LD * sizeof(double);
     if (!configured) {
@@ -206,8 +266,27 @@ int chol_upper_f64(double* G, int64_t ld, int n, double* B, int64_t ldb, double*
     return 0;
 }
 
+int chol_upper_f64(double* G, int64_t ld, int64_t bs, int n, int batch, double* B, int64_t ldb, int64_t bbs, double* shift, cudaStream_t st) {
+    SYN_REQUIRE(n >= 1 && n <= 4096 && ld >= n && ldb >= n && batch >= 1, "syn_chol_upper_f64: n=%d ld=%lld ldb=%lld batch=%d out of range", n,
+                (long long)ld, (long long)ldb, batch);
+    SYN_REQUIRE(G && B && shift, "syn_chol_upper_f64: null pointer");
+    if (n <= 128) {                      // one CTA per problem, everything in registers
+        for (int b0 = 0; b0 < batch; b0 += 65535) {
+            const int nb = (batch - b0) < 65535 ? (batch - b0) : 65535;
+            if (n <= 64) chol_small_kernel<4><<<nb, CH_THREADS, 0, st>>>(G + (int64_t)b0 * bs, ld, bs, n, B + (int64_t)b0 * bbs, ldb, bbs, shift + b0);
+            else chol_small_kernel<8><<<nb, CH_THREADS, 0, st>>>(G + (int64_t)b0 * bs, ld, bs, n, B + (int64_t)b0 * bbs, ldb, bbs, shift + b0);
+            if (int rc = launch_status("chol_small_kernel")) return rc;
+        }
+        return 0;
+    }
+    for (int b = 0; b < batch; ++b)
+        if (int rc = chol_upper_one(G + (int64_t)b * bs, ld, n, B + (int64_t)b * bbs, ldb, shift + b, st)) return rc;
+    return 0;
+}
+
 }  // namespace syn
 
-extern "C" int syn_chol_upper_f64(double* G, int64_t ld, int n, double* B, int64_t ldb, double* shift, void* stream) {
-    return syn::chol_upper_f64(G, ld, n, B, ldb, shift, (cudaStream_t)stream);
+extern "C" int syn_chol_upper_f64(double* G, int64_t ld, int64_t bs, int n, int batch, double* B, int64_t ldb, int64_t bbs, double* shift,
+                                  void* stream) {
+    return syn::chol_upper_f64(G, ld, bs, n, batch, B, ldb, bbs, shift, (cudaStream_t)stream);
 }

@@ -533,7 +533,7 @@ jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int
         for (int c = lane; c < n; c += 32) u[c] = g[c] * inv;
     }
     // singular values, kept rank, discarded weight
-    const double delta = (sqrt_mode == 2 && shift) ? shift[0] : 0.0;
+    const double delta = (sqrt_mode == 2 && shift) ? shift[blockIdx.x] : 0.0;
     auto sv_of = [&](double k) { return sqrt_mode == 1 ? sqrt(k) : (sqrt_mode == 2 ? sqrt(fmax(fma(k, k, -delta), 0.0)) : k); };
     const double s0 = sv_of(key[0]);
     const double thr = (cutoff > rank_tol ? cutoff : rank_tol) * s0;

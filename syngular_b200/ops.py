@@ -164,16 +164,20 @@ def jacobi_sweeps_used():
 
 
 def chol_upper(G):
-    """Shifted Cholesky factor of a symmetric PSD matrix G (n x n contiguous, OVERWRITTEN): returns (B, shift) with B upper triangular,
-    G + shift I = B^T B and shift a device scalar.  jacobi_rows(B) + jacobi_finalize(B, ..., sqrt_mode=2, shift=shift) is then the
-    eigen-decomposition of G in fewer sweeps than jacobi_rows(G) (csrc/chol.cu)."""
+    """Shifted Cholesky factor of symmetric PSD matrices G (n x n or batch x n x n, contiguous rows; OVERWRITTEN when n > 128): returns
+    (B, shift) with B upper triangular, G + shift I = B^T B and shift a device array (one per problem).  jacobi_rows(B) +
+    jacobi_finalize(B, ..., sqrt_mode=2, shift=shift) is then the eigen-decomposition of G in fewer sweeps than jacobi_rows(G)
+    (csrc/chol.cu)."""
     require_cuda_f64(G)
-    n = G.shape[0]
-    assert G.dim() == 2 and G.shape[1] == n and G.stride(1) == 1
-    B = torch.empty((n, n), dtype=torch.float64, device=G.device)
-    shift = torch.empty((1,), dtype=torch.float64, device=G.device)
-    check(lib.syn_chol_upper_f64(ptr(G), _i64(G.stride(0)), _i32(n), ptr(B), _i64(n), ptr(shift), stream_ptr()), "syn_chol_upper_f64")
-    return B, shift
+    batched = G.dim() == 3
+    G3 = G if batched else G.unsqueeze(0)
+    nb, n, n2 = G3.shape
+    assert n == n2 and G3.stride(2) == 1
+    B = torch.empty((nb, n, n), dtype=torch.float64, device=G.device)
+    shift = torch.empty((nb,), dtype=torch.float64, device=G.device)
+    check(lib.syn_chol_upper_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(B), _i64(n), _i64(n * n), ptr(shift),
+                                 stream_ptr()), "syn_chol_upper_f64")
+    return (B, shift) if batched else (B[0], shift)
 
 
 def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shift=None):

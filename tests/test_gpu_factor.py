@@ -61,7 +61,7 @@ def test_qrt_rank_deficient_and_zero_columns():
     assert np.max(np.abs(Q.cpu().numpy().T @ Q.cpu().numpy() - np.eye(4))) < 1e-14 and S.abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 8, 33, 64, 100, 128, 130, 256, 300, 512, 1024])
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 33, 64, 100, 128, 130, 192, 256, 300, 384, 512, 1024])
 def test_jacobi_rows_singular_values(n):
     from syngular_b200 import ops
     G0 = _rand((n, n), n)

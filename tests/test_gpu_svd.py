@@ -128,7 +128,7 @@ def test_fp32_preconditioned_eigensolver_option():
         sw.PRECONDITION_MIN_N, sw.CHOLESKY_MIN_N = old, old_chol
 
 
-@pytest.mark.parametrize("n,rank", [(200, 200), (512, 512), (320, 100), (130, 1), (1024, 700)])
+@pytest.mark.parametrize("n,rank", [(1, 1), (5, 5), (64, 64), (100, 37), (128, 128), (200, 200), (512, 512), (320, 100), (130, 1), (1024, 700)])
 def test_shifted_cholesky_factor(n, rank):
     """syn_chol_upper_f64: G + shift I = B^T B with B upper triangular, also for singular G (bond "inflation", short chains)."""
     from syngular_b200 import ops
@@ -140,6 +140,22 @@ def test_shifted_cholesky_factor(n, rank):
     assert 0.0 < delta <= 4.0 * n * 2.3e-16 * np.max(np.diag(G))
     assert np.max(np.abs(np.tril(B, -1))) == 0.0
     assert np.max(np.abs(B.T @ B - G - delta * np.eye(n))) < 2e-13 * np.max(np.diag(G))
+
+
+def test_shifted_cholesky_factor_batched():
+    """One launch, one CTA per problem (n <= 128): every member gets its own shift and factor."""
+    from syngular_b200 import ops
+    rng = np.random.default_rng(5)
+    nb, n = 37, 96
+    F = rng.normal(size=(nb, n, 40)) * rng.uniform(0.1, 10.0, size=(nb, 1, 1))
+    G = F @ F.transpose(0, 2, 1)
+    B, shift = ops.chol_upper(torch.from_numpy(G.copy()).cuda())
+    B, shift = B.cpu().numpy(), shift.cpu().numpy()
+    for b in range(nb):
+        dmax = np.max(np.diag(G[b]))
+        assert 0.0 < shift[b] <= 4.0 * n * 2.3e-16 * dmax
+        assert np.max(np.abs(np.tril(B[b], -1))) == 0.0
+        assert np.max(np.abs(B[b].T @ B[b] - G[b] - shift[b] * np.eye(n))) < 2e-13 * dmax
 
 
 @pytest.mark.parametrize("n,rank", [(256, 256), (512, 512), (384, 150), (512, 256)])
