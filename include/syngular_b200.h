@@ -112,6 +112,29 @@ int syn_jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int 
  * syn_jacobi_finalize_f64(sqrt_mode = 2, shift) returns the eigenvectors of G and sigma_i = sqrt(lambda_i). */
 int syn_chol_upper_f64(double* G, int64_t ld, int64_t bs, int n, int batch, double* B, int64_t ldb, int64_t bbs, double* shift, void* stream);
 
+/* ---- fused transfer-matrix inner product (FP64 DMMA, persistent over the batch) ------------------------------------ */
+/* <A_s | B_s> for s = 0..batch-1 (bilinear, no conjugation):  E <- sum_{a,a',i} A_k[a,i,b] E[a,a'] B_k[a',i,b'],  k = 0..n_sites-1.
+ * Replaces the 2N-operand opt_einsum.contract of MatrixProductState.__or__ (MPS:116-129), `dot` (MPS:243) and syn.mul on two
+ * states (tensor/utils.py:22-28) -- in the reference a batch is a Python loop over that call.  One CTA walks one pair of chains;
+ * the transfer matrix stays in shared memory and every core is read from HBM exactly once.
+ *   sites   HOST array; site k: `a` / `b` = core k of state 0 of either chain, C-ordered (la, d, ra) / (lb, d, rb); state s lives
+ *           a_stride / b_stride elements further (0 = one core shared by the whole batch).
+ *   E_in    (batch, la_0, lb_0) or NULL (then la_0 = lb_0 = 1 and E starts as the scalar 1);  E_out (batch, ra_last, rb_last).
+ * Chains longer than SYN_OVERLAP_MAX_SITES are split by the caller (E_out of one call is E_in of the next).
+ * syn_overlap_batched_fits() != 0 when every bond is <= SYN_OVERLAP_MAX_BOND, round8(l) * d and d * r are <= 2 * SYN_OVERLAP_MAX_BOND
+ * and consecutive bonds match; other chains take the GEMM-per-site route (syn_gemm_f64). */
+#define SYN_OVERLAP_MAX_SITES 64
+#define SYN_OVERLAP_MAX_BOND 64
+typedef struct {
+    const double* a;
+    const double* b;
+    int64_t a_stride, b_stride;
+    int32_t la, ra, lb, rb, d;
+    int32_t _pad;
+} syn_overlap_site_t;
+int syn_overlap_batched_fits(const syn_overlap_site_t* sites, int n_sites);
+int syn_overlap_batched_f64(const syn_overlap_site_t* sites, int n_sites, int batch, const double* E_in, double* E_out, void* stream);
+
 /* ---- block assembly and elementwise kernels ---------------------------------------------------------------- */
 /* `A + B` site: direct sum of the bond spaces, self's block first; cores as (l, phys, r) with the physical legs flattened
  * (np.block / scipy.linalg.block_diag loops of MPS:82-96 and MPO:90-106). */

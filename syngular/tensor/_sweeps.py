@@ -118,7 +118,11 @@ def right_orthonormalize(sites):
 
 
 def overlap(A, B):
-    """`A | B` (MPS:116-129): bilinear transfer-matrix contraction, two GEMMs per site.  Returns a (1,1) device tensor."""
+    """`A | B` (MPS:116-129): bilinear transfer-matrix contraction.  Chains with bonds <= 64 run as ONE launch of the fused kernel
+    (csrc/overlap.cu: the transfer matrix never leaves shared memory); larger bonds take two GEMMs per site.  Returns a (1,1)
+    device tensor."""
+    if A[-1].shape[-1] == 1 and B[-1].shape[-1] == 1 and A[0].shape[0] == 1 and B[0].shape[0] == 1 and ops.overlap_fits(A, B, batched=False):
+        return ops.overlap_batched(A, B, batched=False).reshape(1, 1)
     E = torch.ones((1, 1), dtype=F64, device=A[0].device)
     for a, b in zip(A, B):
         la, lb = a.shape[0], b.shape[0]

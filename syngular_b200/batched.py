@@ -51,9 +51,12 @@ class BatchedMatrixProductState:
 
     # ---- `|` for the whole batch ----------------------------------------------------------------------------------
     def overlap(self, other):
-        """(B,) tensor of <self_b | other_b> (bilinear, like MPS:116-129): two batched strided GEMMs per site."""
+        """(B,) tensor of <self_b | other_b> (bilinear, like MPS:116-129): one launch of the fused transfer-matrix kernel
+        (csrc/overlap.cu, one CTA per pair of chains) when every bond is <= 64, else two batched strided GEMMs per site."""
         assert other.batch == self.batch and other.sites_number == self.sites_number
         B = self.batch
+        if self.sites[0].shape[1] == 1 and other.sites[0].shape[1] == 1 and ops.overlap_fits(self.sites, other.sites):
+            return ops.overlap_batched(self.sites, other.sites).reshape(B)
         E = torch.ones((B, 1, 1), dtype=F64, device=self.sites[0].device)
         for a, b in zip(self.sites, other.sites):
             la, ra, lb, rb = a.shape[1], a.shape[-1], b.shape[1], b.shape[-1]

@@ -1,5 +1,6 @@
 """Thin Python wrappers over the C ABI (one function per exported entry point).  No arithmetic happens here."""
 import ctypes
+import os
 
 import torch
 
@@ -283,3 +284,64 @@ def identity_deviation(X):
     out = torch.empty((1,), dtype=torch.float64, device=X.device)
     check(lib.syn_identity_deviation_f64(ptr(X.contiguous()), _i32(X.shape[0]), ptr(out), stream_ptr()), "syn_identity_deviation_f64")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused transfer-matrix inner product (csrc/overlap.cu)
+class OverlapSite(ctypes.Structure):
+    _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("a_stride", _i64), ("b_stride", _i64),
+                ("la", _i32), ("ra", _i32), ("lb", _i32), ("rb", _i32), ("d", _i32), ("_pad", _i32)]
+
+
+OVERLAP_MAX_SITES = 64
+OVERLAP_FUSED = os.environ.get("SYN_OVERLAP_FUSED", "1") != "0"      # experiment knob: 0 = GEMM-per-site route only
+lib.syn_overlap_batched_fits.argtypes = [ctypes.POINTER(OverlapSite), _i32]
+lib.syn_overlap_batched_f64.argtypes = [ctypes.POINTER(OverlapSite), _i32, _i32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+
+
+def _overlap_sites(a_cores, b_cores, batched):
+    """Site table of syn_overlap_batched_f64 for cores (B, l, d, r) (batched; B = 1 on one side means a shared chain) or (l, d, r)."""
+    n = len(a_cores)
+    tab = (OverlapSite * n)()
+    for k, (a, b) in enumerate(zip(a_cores, b_cores)):
+        require_cuda_f64(a, b)
+        if not (a.is_contiguous() and b.is_contiguous()):
+            raise _lib.SynError("overlap: cores must be contiguous")
+        sa, sb = (a.shape[1:], b.shape[1:]) if batched else (a.shape, b.shape)
+        if len(sa) != 3 or len(sb) != 3 or sa[1] != sb[1]:
+            raise _lib.SynError("overlap: cores must be (l, d, r) with equal physical dimensions, got %r and %r" % (tuple(sa), tuple(sb)))
+        ast = sa[0] * sa[1] * sa[2] if (batched and a.shape[0] > 1) else 0
+        bst = sb[0] * sb[1] * sb[2] if (batched and b.shape[0] > 1) else 0
+        tab[k] = OverlapSite(a.data_ptr(), b.data_ptr(), ast, bst, sa[0], sa[2], sb[0], sb[2], sa[1], 0)
+    return tab
+
+
+def overlap_fits(a_cores, b_cores, batched=True):
+    """True when the fused kernel takes these chains (bonds <= 64, round8(l) * d <= 128, d * r <= 128)."""
+    if not OVERLAP_FUSED or len(a_cores) != len(b_cores) or len(a_cores) == 0:
+        return False
+    tab = _overlap_sites(a_cores, b_cores, batched)
+    n = len(a_cores)
+    return all(lib.syn_overlap_batched_fits(ctypes.cast(ctypes.byref(tab, k0 * ctypes.sizeof(OverlapSite)), ctypes.POINTER(OverlapSite)),
+                                            min(OVERLAP_MAX_SITES, n - k0)) != 0 for k0 in range(0, n, OVERLAP_MAX_SITES))
+
+
+def overlap_batched(a_cores, b_cores, batched=True):
+    """E (batch, r_a, r_b) of the transfer-matrix chain  E <- sum A[a,i,b] E[a,a'] B[a',i,b']  over all sites (MPS:116-129) in ONE
+    launch per 64 sites; cores are lists of contiguous (B, l, d, r) tensors (or (l, d, r) with batched=False)."""
+    n = len(a_cores)
+    tab = _overlap_sites(a_cores, b_cores, batched)
+    batch = max(int(a_cores[0].shape[0]), int(b_cores[0].shape[0])) if batched else 1
+    dev = a_cores[0].device
+    if tab[0].la == 1 and tab[0].lb == 1:
+        E = None
+    else:
+        raise _lib.SynError("overlap: the first bonds must be 1")
+    for k0 in range(0, n, OVERLAP_MAX_SITES):
+        m = min(OVERLAP_MAX_SITES, n - k0)
+        out = torch.empty((batch, tab[k0 + m - 1].ra, tab[k0 + m - 1].rb), dtype=torch.float64, device=dev)
+        seg = ctypes.cast(ctypes.byref(tab, k0 * ctypes.sizeof(OverlapSite)), ctypes.POINTER(OverlapSite))
+        check(lib.syn_overlap_batched_f64(seg, m, batch, ptr(E) if E is not None else None, ptr(out), stream_ptr()),
+              "syn_overlap_batched_f64")
+        E = out
+    return E
