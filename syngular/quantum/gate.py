@@ -1,5 +1,6 @@
 """Gate tensors (reference: quantum/gate.py:4-61).  Multi-qubit gates are stored with legs (out..., in...).
-Real gates run on the FP64 kernels; Y, T, S are complex and are rejected by the (real) library when applied."""
+Real gates run on the FP64 kernels directly; Y, T, S (and any complex unitary) make the touched cores complex128 and run
+planar on the same kernels (syngular_b200/cplx.py)."""
 import numpy as np
 
 I = np.array([[1., 0.], [0., 1.]])

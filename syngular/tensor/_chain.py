@@ -88,13 +88,7 @@ class _MatrixProduct:
             if self.orthonormalized != "right":
                 self.right_orthonormalization()
             # mirror image of the left sweep: reverse the chain and swap the bond legs (views), sweep, mirror back
-            mirrored = [s.reshape(s.shape[0], -1, s.shape[-1]).permute(2, 1, 0).contiguous() for s in reversed(self.sites)]
-            swept = sw.round_qr(mirrored, dim)
-            new = []
-            for s, old in zip(reversed(swept), self.sites):
-                t = s.permute(2, 1, 0).contiguous()
-                new.append(t.reshape((t.shape[0],) + tuple(old.shape[1:-1]) + (t.shape[2],)))
-            self.sites = new
+            self.sites = sw.unmirror(sw.round_qr(sw.mirror(self.sites), dim), self.sites)
         self._refresh_from_cores(bonds=False)
         return None
 
@@ -139,11 +133,11 @@ class _MatrixProduct:
 
     def left_orthogonality(self, index):
         L = self.sites[index].reshape(-1, self.sites[index].shape[-1])
-        return sw.ops.matmul(L.t(), L).cpu().numpy()
+        return sw.gram(L, "left").cpu().numpy()
 
     def right_orthogonality(self, index):
         R = self.sites[index].reshape(self.sites[index].shape[0], -1)
-        return sw.ops.matmul(R, R.t()).cpu().numpy()
+        return sw.gram(R, "right").cpu().numpy()
 
     def grad(self, index):
         return self.sites[:index] + self.sites[index + 2:]

@@ -7,9 +7,11 @@ and views.  Citations are to the reference (MPS = tensor/matrix_product_state.py
 import numpy as np
 import torch
 
-from syngular_b200 import ops
+from syngular_b200 import cplx, ops
+from syngular_b200.cplx import Cx
 
 F64 = torch.float64
+C128 = torch.complex128
 
 
 def device():
@@ -25,12 +27,13 @@ def as_core(x):
     else:
         a = np.asarray(x)
         if np.iscomplexobj(a):
-            if np.max(np.abs(a.imag)) > 0:
-                raise NotImplementedError("complex cores are not supported by the FP64 library yet")
+            if a.size and np.max(np.abs(a.imag)) > 0:
+                t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128))
+                return t.to(device()).contiguous()
             a = a.real
         t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
-    if t.dtype != F64:
-        t = t.to(F64)
+    if t.dtype not in (F64, C128):
+        t = t.to(C128 if t.is_complex() else F64)
     if not t.is_cuda:
         t = t.to(device())
     return t.contiguous()
@@ -40,29 +43,107 @@ def empty(*shape):
     return torch.empty(shape, dtype=F64, device=device())
 
 
+# ---- complex128 cores: planar operands on the same kernels, see syngular_b200/cplx.py -------------------------
+def any_complex(*chains):
+    """True when any core / tensor of the given lists (or single tensors) is complex128."""
+    for ch in chains:
+        for t in (ch if isinstance(ch, (list, tuple)) else (ch,)):
+            if t is not None and (isinstance(t, Cx) or t.dtype == C128):
+                return True
+    return False
+
+
+def lift(x):
+    """torch core(s) -> planar complex operand(s)."""
+    if isinstance(x, (list, tuple)):
+        return [lift(t) for t in x]
+    return x if isinstance(x, Cx) else Cx.from_torch(x)
+
+
+def lower(x):
+    """planar complex operand(s) -> torch complex128 core(s)."""
+    if isinstance(x, (list, tuple)):
+        return [lower(t) for t in x]
+    return x.to_torch() if isinstance(x, Cx) else x
+
+
+def _O(x):
+    """Kernel namespace for an operand: the real wrappers, or their 4-launch complex compositions."""
+    return cplx if isinstance(x, Cx) else ops
+
+
+def empty_for(x, *shape):
+    return Cx.empty(shape, x.device) if isinstance(x, Cx) else torch.empty(shape, dtype=F64, device=x.device)
+
+
+def ones_for(x, *shape):
+    return Cx.ones(shape, x.device) if isinstance(x, Cx) else torch.ones(shape, dtype=F64, device=x.device)
+
+
+def mirror(sites):
+    """Reverse the chain and swap the bond legs of every core (physical legs flattened): right sweeps become left sweeps."""
+    return [s.reshape(s.shape[0], -1, s.shape[-1]).permute(2, 1, 0).contiguous() for s in reversed(sites)]
+
+
+def unmirror(swept, like):
+    out = []
+    for s, old in zip(reversed(swept), like):
+        t = s.permute(2, 1, 0).contiguous()
+        out.append(t.reshape((t.shape[0],) + tuple(old.shape[1:-1]) + (t.shape[2],)))
+    return out
+
+
+def _is_operand(a):
+    return isinstance(a, (torch.Tensor, Cx)) or (isinstance(a, (list, tuple)) and len(a) > 0 and isinstance(a[0], (torch.Tensor, Cx)))
+
+
+def _lower_result(r):
+    if isinstance(r, Cx):
+        return r.to_torch()
+    if isinstance(r, list):
+        return [_lower_result(x) for x in r]
+    if isinstance(r, tuple):
+        return tuple(_lower_result(x) for x in r)
+    return r
+
+
+def complex_aware(fn):
+    """Entry points called with torch cores: when any operand is complex128, every tensor operand is converted to planar form
+    (real ones get a zero imaginary part), the generic body runs on the complex compositions, and results come back complex128."""
+    def wrapper(*args, **kw):
+        operands = [a for a in args if _is_operand(a)]
+        if not any_complex(*operands) or any(isinstance(a, Cx) or (isinstance(a, (list, tuple)) and isinstance(a[0], Cx)) for a in operands):
+            return fn(*args, **kw)
+        return _lower_result(fn(*[lift(a) if _is_operand(a) else a for a in args], **kw))
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
 # ---------------------------------------------------------------------------------------------------------
 # site contractions (K1 / K2 of SURVEY section 2.4) as single strided GEMMs
 # ---------------------------------------------------------------------------------------------------------
+@complex_aware
 def site_mpo_mps(X, W):
     """C[(a,l), o, (b,r)] = sum_i X[a,i,b] W[l,i,o,r]   (MPO:184-190; MPS bond major, MPO bond minor)."""
     a, i, b = X.shape
     l, i2, o, r = W.shape
     assert i == i2, (X.shape, W.shape)
-    out = empty(a * l, o, b * r)
-    ops.gemm(X, W, out, M=b, N=o * r, K=i,
+    out = empty_for(X, a * l, o, b * r)
+    _O(X).gemm(X, W, out, M=b, N=o * r, K=i,
              a_m=1, a_k=b, b_k=o * r, b_n=1,
              c_m=r, c_n=(b * r, 1, r),
              batch=a * l, a_b=(i * b, 0, l), b_b=(0, i * o * r, l), c_b=o * b * r)
     return out
 
 
+@complex_aware
 def site_mpo_mpo(A, B):
     """C[(lA,lB), iA, oB, (rA,rB)] = sum_x A[lA,iA,x,rA] B[lB,x,oB,rB]   (MPO:280-287; A acts first)."""
     la, ia, xa, ra = A.shape
     lb, xb, ob, rb = B.shape
     assert xa == xb, (A.shape, B.shape)
-    out = empty(la * lb, ia, ob, ra * rb)
-    ops.gemm(A, B, out, M=ia * ra, N=ob * rb, K=xa,
+    out = empty_for(A, la * lb, ia, ob, ra * rb)
+    _O(A).gemm(A, B, out, M=ia * ra, N=ob * rb, K=xa,
              a_m=(xa * ra, 1, ra), a_k=ra, b_k=ob * rb, b_n=1,
              c_m=(ob * ra * rb, rb, ra), c_n=(ra * rb, 1, rb),
              batch=la * lb, a_b=(ia * xa * ra, 0, lb), b_b=(0, xb * ob * rb, lb), c_b=ia * ob * ra * rb)
@@ -72,6 +153,7 @@ def site_mpo_mpo(A, B):
 # ---------------------------------------------------------------------------------------------------------
 # reference-semantic sweeps
 # ---------------------------------------------------------------------------------------------------------
+@complex_aware
 def round_qr(sites, dim):
     """Strict `>>` sweep (MPS:432-468, MPO:544-580): QR-truncation left to right, no canonicalisation.
     Natural clamp: kept width = min(dim, rows)."""
@@ -79,30 +161,34 @@ def round_qr(sites, dim):
     for k in range(len(out) - 1):
         cur, nxt = out[k], out[k + 1]
         L = cur.reshape(-1, cur.shape[-1])
-        Q, S = ops.qrt(L, dim)
+        Q, S = _O(L).qrt(L, dim)
         kept = Q.shape[1]
-        Wn = ops.matmul(S, nxt.reshape(nxt.shape[0], -1))
+        Wn = _O(S).matmul(S, nxt.reshape(nxt.shape[0], -1))
         out[k] = Q.reshape(tuple(cur.shape[:-1]) + (kept,))
         out[k + 1] = Wn.reshape((kept,) + tuple(nxt.shape[1:]))
     return out
 
 
+@complex_aware
 def left_orthonormalize(sites):
     """MPS:554-566 / MPO:673-694 (reduced QR, left to right)."""
     out = list(sites)
     for k in range(len(out) - 1):
         cur, nxt = out[k], out[k + 1]
         L = cur.reshape(-1, cur.shape[-1])
-        Q, S = ops.qrt(L, min(L.shape))
+        Q, S = _O(L).qrt(L, min(L.shape))
         kept = Q.shape[1]
-        Wn = ops.matmul(S, nxt.reshape(nxt.shape[0], -1))
+        Wn = _O(S).matmul(S, nxt.reshape(nxt.shape[0], -1))
         out[k] = Q.reshape(tuple(cur.shape[:-1]) + (kept,))
         out[k + 1] = Wn.reshape((kept,) + tuple(nxt.shape[1:]))
     return out
 
 
+@complex_aware
 def right_orthonormalize(sites):
     """MPS:568-580 / MPO:696-719: QR of R^T right to left; the transposed factor is written straight into the core."""
+    if any_complex(sites):                                 # planar operands: the mirrored left sweep (same factorisation)
+        return unmirror(left_orthonormalize(mirror(sites)), sites)
     out = list(sites)
     for k in range(len(out) - 1, 0, -1):
         cur, prv = out[k], out[k - 1]
@@ -117,27 +203,32 @@ def right_orthonormalize(sites):
     return out
 
 
+@complex_aware
 def overlap(A, B):
     """`A | B` (MPS:116-129): bilinear transfer-matrix contraction.  Chains with bonds <= 64 run as ONE launch of the fused kernel
     (csrc/overlap.cu: the transfer matrix never leaves shared memory); larger bonds take two GEMMs per site.  Returns a (1,1)
     device tensor."""
-    if A[-1].shape[-1] == 1 and B[-1].shape[-1] == 1 and A[0].shape[0] == 1 and B[0].shape[0] == 1 and ops.overlap_fits(A, B, batched=False):
+    cx = isinstance(A[0], Cx)
+    if (not cx and A[-1].shape[-1] == 1 and B[-1].shape[-1] == 1 and A[0].shape[0] == 1 and B[0].shape[0] == 1
+            and ops.overlap_fits(A, B, batched=False)):
         return ops.overlap_batched(A, B, batched=False).reshape(1, 1)
-    E = torch.ones((1, 1), dtype=F64, device=A[0].device)
+    O = _O(A[0])
+    E = ones_for(A[0], 1, 1)
     for a, b in zip(A, B):
         la, lb = a.shape[0], b.shape[0]
-        T = ops.matmul(E.t(), a.reshape(la, -1))           # (lb, d*ra')
+        T = O.matmul(E.t(), a.reshape(la, -1))             # (lb, d*ra')
         ra, rb = a.shape[-1], b.shape[-1]
-        E = ops.matmul(T.reshape(-1, ra).t(), b.reshape(-1, rb))   # (ra', rb')
+        E = O.matmul(T.reshape(-1, ra).t(), b.reshape(-1, rb))     # (ra', rb')
     return E
 
 
+@complex_aware
 def to_dense(sites):
     """Dense tensor by one left-to-right chain of GEMMs (the reference loops over every index: MPS:265-273, MPO:405-416)."""
     T = sites[0].reshape(-1, sites[0].shape[-1])
     dims = list(sites[0].shape[1:-1])
     for c in sites[1:]:
-        T = ops.matmul(T, c.reshape(c.shape[0], -1)).reshape(-1, c.shape[-1])
+        T = _O(T).matmul(T, c.reshape(c.shape[0], -1)).reshape(-1, c.shape[-1])
         dims += list(c.shape[1:-1])
     T = T.reshape(dims)
     if sites[0].dim() == 4:
@@ -146,51 +237,82 @@ def to_dense(sites):
     return T
 
 
+@complex_aware
 def retrieve(sites, idx_in, idx_out=None):
     """One amplitude = product of the sliced bond matrices (MPS:546-551, MPO:663-670); (1,1) device tensor."""
     v = None
     for k, c in enumerate(sites):
         m = c[:, int(idx_in[k]), :] if idx_out is None else c[:, int(idx_in[k]), int(idx_out[k]), :]
-        v = m if v is None else ops.matmul(v, m)
+        v = m if v is None else _O(v).matmul(v, m)
     return v
+
+
+@complex_aware
+def add_site(A, B, first, last):
+    """Block assembly of `A + B` for one site (MPS:82-96, MPO:90-106)."""
+    return _O(A).add_site(A, B, first, last)
+
+
+@complex_aware
+def gram(M, side):
+    """Gram matrix of an unfolding: side="left" -> M^H M (columns), "right" -> M M^H (rows)  (MPS:624-630, MPO:771-777)."""
+    Mh = M.h() if isinstance(M, Cx) else M.t()
+    return _O(M).matmul(Mh, M) if side == "left" else _O(M).matmul(M, Mh)
+
+
+def normalize_last(core):
+    """New last core divided by its Frobenius norm (MPS:252-256); complex cores through their float64 (..., 2) view."""
+    last = core.clone()
+    flat = torch.view_as_real(last) if last.dtype == C128 else last
+    ops.scale_rsqrt_(flat, ops.sumsq(flat))
+    return last
 
 
 def apply_gate(sites, gate, index, mode="compress", chi_max=None, cutoff=0.0):
     """`MatrixProductState.apply` (MPS:487-534): contract a dense m-site gate (legs out..., in...; column-vector convention)
     into cores index..index+m-1, then re-split.
       mode="compress" (reference): qrt split keeping the EXISTING bonds -- the bond never grows;
-      mode="svd" (extension): local SVD split, bonds grow up to chi_max (relative cutoff `cutoff`)."""
+      mode="svd" (extension): local SVD split, bonds grow up to chi_max (relative cutoff `cutoff`).
+    Complex gates or cores (quantum/gate.py:9-13) run planar on the same kernels (syngular_b200/cplx.py); only the m cores
+    touched are converted, and the result cores are complex128."""
     out = list(sites)
     m = gate.dim() // 2
-    T = out[index]
-    for k in range(index + 1, index + m):                               # merge the m cores: (l, in_0..in_j, r)
-        c = out[k]
-        T = ops.matmul(T.reshape(-1, T.shape[-1]), c.reshape(c.shape[0], -1)).reshape(tuple(T.shape[:-1]) + tuple(c.shape[1:]))
+    touched = out[index:index + m]
+    cx = any_complex(touched, gate)
+    if cx:
+        touched, gate = lift(touched), lift(gate)
+    T = touched[0]
+    O = _O(T)
+    for c in touched[1:]:                                               # merge the m cores: (l, in_0..in_j, r)
+        T = O.matmul(T.reshape(-1, T.shape[-1]), c.reshape(c.shape[0], -1)).reshape(tuple(T.shape[:-1]) + tuple(c.shape[1:]))
     l, r = T.shape[0], T.shape[-1]
     dims_out = tuple(gate.shape[:m])
     dout, din = int(np.prod(dims_out)), int(np.prod(gate.shape[m:]))
     G = gate.reshape(dout, din)
     T3 = T.reshape(l, din, r)
-    Tn = empty(l, dout, r)
+    Tn = empty_for(T3, l, dout, r)
     # Tn[l] (dout x r) = G (dout x din) @ T3[l] (din x r), batched over l with the gate shared
-    ops.gemm(G, T3, Tn, M=dout, N=r, K=din, a_m=din, a_k=1, b_k=r, b_n=1, c_m=r, c_n=1, batch=l, a_b=0, b_b=din * r, c_b=dout * r)
+    O.gemm(G, T3, Tn, M=dout, N=r, K=din, a_m=din, a_k=1, b_k=r, b_n=1, c_m=r, c_n=1, batch=l, a_b=0, b_b=din * r, c_b=dout * r)
     T = Tn.reshape((l,) + dims_out + (r,))
     trunc = Truncation()
+    new = []
     for k in range(index, index + m - 1):
         lr, d = T.shape[0], T.shape[1]
         L = T.reshape(lr * d, -1)
         if mode == "svd":
             core2d, kept = _svd_basis(L, chi_max if chi_max is not None else min(L.shape), cutoff, trunc)
-            S = ops.matmul(core2d.t(), L)
+            S = O.matmul(core2d.h() if cx else core2d.t(), L)
         else:
-            core2d, S = ops.qrt(L, int(sites[k].shape[2]))
+            core2d, S = O.qrt(L, int(sites[k].shape[2]))
             kept = core2d.shape[1]
-        out[k] = core2d.reshape(lr, d, kept)
+        new.append(core2d.reshape(lr, d, kept))
         T = S.reshape((kept,) + tuple(T.shape[2:]))
-    out[index + m - 1] = T.reshape(T.shape[0], -1, T.shape[-1])
+    new.append(T.reshape(T.shape[0], -1, T.shape[-1]))
+    out[index:index + m] = lower(new) if cx else new
     return out
 
 
+@complex_aware
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step (MPS:298-319, MPO:430-450)."""
     cores, l, n = [], 1, len(shapes)
@@ -198,7 +320,7 @@ def decompose_left(T, shapes):
     for k in range(n - 1):
         phys = int(np.prod(shapes[k][1:-1]))
         L = T.reshape(l * phys, -1)
-        Q, S = ops.qrt(L, int(shapes[k][-1]))
+        Q, S = _O(L).qrt(L, int(shapes[k][-1]))
         kept = Q.shape[1]
         cores.append(Q.reshape((l,) + tuple(shapes[k][1:-1]) + (kept,)))
         T, l = S, kept
@@ -296,6 +418,19 @@ class Truncation:
 def _svd_basis(M, chi_max, cutoff, trunc):
     """Left singular basis of the unfolding M (m x c): returns (core2d (m x keep) contiguous, keep)."""
     m, c = M.shape
+    if isinstance(M, Cx):
+        # complex unfolding: eigen-decomposition of the embedded Hermitian Gram matrix (cplx.svd_basis); a tall unfolding is
+        # first reduced to its square triangular factor by the complex qrt
+        if m > c:
+            Q1, R1 = cplx.qrt(M, c)
+            U, keep, sigma, disc = cplx.svd_basis(R1, chi_max, cutoff, eigh_gram)
+            core2d = cplx.matmul(Q1, U)
+        else:
+            core2d, keep, sigma, disc = cplx.svd_basis(M, chi_max, cutoff, eigh_gram)
+        trunc.sigma.append(sigma)
+        trunc.keep.append(keep)
+        trunc.discarded.append(float(disc.item()))
+        return core2d, keep
     if m <= c:
         G = ops.qr_r(M.t())                                 # R factor of M^T (m x m); rows rotate to sigma_i u_i^T
         ops.jacobi_rows(G)
@@ -315,6 +450,7 @@ def _svd_basis(M, chi_max, cutoff, trunc):
     return core2d, keep
 
 
+@complex_aware
 def round_svd(sites, chi_max, cutoff=0.0, canonicalize=True):
     """Textbook rounding: right-to-left QR canonicalisation, then left-to-right truncated SVD with S V^T absorbed into the
     next core (oracle/svd_numpy.round_svd).  The SVD is Householder reduction + one-sided Jacobi on the device; the cutoff and
@@ -325,8 +461,9 @@ def round_svd(sites, chi_max, cutoff=0.0, canonicalize=True):
         cur, nxt = out[k], out[k + 1]
         M = cur.reshape(-1, cur.shape[-1])
         core2d, keep = _svd_basis(M, chi_max, cutoff, trunc)
-        carry = ops.matmul(core2d.t(), M)                   # U^T M = S V^T  (keep x c)
-        Wn = ops.matmul(carry, nxt.reshape(nxt.shape[0], -1))
+        O = _O(M)
+        carry = O.matmul(core2d.h() if isinstance(M, Cx) else core2d.t(), M)       # U^H M = S V^H  (keep x c)
+        Wn = O.matmul(carry, nxt.reshape(nxt.shape[0], -1))
         out[k] = core2d.reshape(tuple(cur.shape[:-1]) + (keep,))
         out[k + 1] = Wn.reshape((keep,) + tuple(nxt.shape[1:]))
     return out, trunc

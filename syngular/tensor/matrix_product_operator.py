@@ -44,7 +44,7 @@ class MatrixProductOperator(_MatrixProduct):
         min_bond = min(min(self.bond_shape), min(mpo.bond_shape))            # MPO:80 (metadata)
         if self.decomposed and mpo.decomposed:
             n = self.sites_number
-            sites = [sw.ops.add_site(self.sites[k], mpo.sites[k], k == 0, k == n - 1) for k in range(n)]
+            sites = [sw.add_site(self.sites[k], mpo.sites[k], k == 0, k == n - 1) for k in range(n)]
             return MatrixProductOperator.from_sites(sites) >> min_bond      # MPO:110
         raise Exception("Both Matrix Product Operator must be in canonical form (use .decompose()")
 
@@ -149,6 +149,14 @@ def _apply_to_state(W, X, min_bond, rounding=None, guard=True):
     prod_bonds = tuple(x.shape[2] * w.shape[3] for x, w in zip(X.sites[:-1], W.sites[:-1]))
     rounding = rounding or MatrixProductState.ROUNDING
     guard_noop = guard and min_bond >= min(prod_bonds)      # explicit `bond=` targets (syn.mul extension) skip the guard
+    if sw.any_complex(W.sites, X.sites) and not guard_noop:
+        # complex128 cores: the literal route on the planar compositions (the fused sweeps are real-only)
+        prod = MatrixProductState.from_sites([sw.site_mpo_mps(x, w) for x, w in zip(X.sites, W.sites)])
+        if rounding == "svd":
+            prod.sites, prod.truncation = sw.round_svd(prod.sites, min_bond, MatrixProductState.SVD_CUTOFF)
+            prod._refresh_from_cores(bonds=False)
+            return prod
+        return prod >> min_bond
     if guard_noop or (MatrixProductOperator.MATMUL_MODE == "standard" and rounding == "qr" and not _FUSE_STANDARD):
         sites = [sw.site_mpo_mps(x, w) for x, w in zip(X.sites, W.sites)]
         return MatrixProductState.from_sites(sites) >> min_bond

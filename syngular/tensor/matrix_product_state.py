@@ -34,13 +34,14 @@ class MatrixProductState(_MatrixProduct):
     def __add__(self, mps):
         if self.decomposed and mps.decomposed:                   # MPS:75-102 (no truncation for states)
             n = self.sites_number
-            sites = [sw.ops.add_site(self.sites[k], mps.sites[k], k == 0, k == n - 1) for k in range(n)]
+            sites = [sw.add_site(self.sites[k], mps.sites[k], k == 0, k == n - 1) for k in range(n)]
             return MatrixProductState.from_sites(sites)
         raise Exception("Both Matrix Product Operator must be in canonical form (use .decompose()")
 
     def __or__(self, mp):
         if isinstance(mp, MatrixProductState):                   # MPS:116-129, bilinear, no conjugation
-            return np.float64(sw.overlap(self.sites, mp.sites).item())
+            v = sw.overlap(self.sites, mp.sites).item()
+            return np.complex128(v) if isinstance(v, complex) else np.float64(v)
         raise Exception("right-hand site must be a MatrixProductState")
 
     def overlap_device(self, mp):
@@ -83,10 +84,12 @@ class MatrixProductState(_MatrixProduct):
         return np.sqrt(self | self)
 
     def normalize(self):
-        last = self.sites[-1].clone()                            # MPS:252-256 divides the last core by its Frobenius norm
-        sw.ops.scale_rsqrt_(last, sw.ops.sumsq(last))
-        self.sites[-1] = last
+        self.sites[-1] = sw.normalize_last(self.sites[-1])       # MPS:252-256 divides the last core by its Frobenius norm
         return self
+
+    def conj(self):
+        """Complex conjugate chain (extension: the reference's `|` is bilinear, so <psi|psi> is `psi.conj() | psi`)."""
+        return MatrixProductState.from_sites([s.conj().resolve_conj() if s.is_complex() else s for s in self.sites])
 
     def to_tensor(self):
         return sw.to_dense(self.sites).cpu().numpy().astype(complex)     # the reference returns a complex array (MPS:266)

@@ -1,0 +1,285 @@
+"""complex128 on the FP64 kernels: planar (split re / im) tensors and the complex versions of the library calls.
+
+The sm_100a library is real FP64 (DMMA GEMM, Householder qrt, one-sided Jacobi).  Gates of the quantum callers
+(reference: quantum/gate.py:9-13 Y, T, S; SURVEY 8f-1, BASELINE configs[2]) make cores complex, so this module maps the
+complex operations onto the same kernels:
+
+  * a complex tensor is held PLANAR -- two contiguous float64 tensors of the logical shape -- so every two-level strided
+    index of the real GEMM descriptor applies unchanged to both parts; a complex GEMM is 4 real GEMM launches
+    (C_re = A_re B_re - A_im B_im, C_im = A_re B_im + A_im B_re; alpha/beta accumulate in the kernel);
+  * the truncation step qrt runs on the real embedding [[a, -b], [b, a]] of every entry (rows AND columns interleaved):
+    Householder QR of that matrix is the embedding of the complex QR, so the even columns of its Q are the complex basis;
+  * the bond SVD diagonalises the embedded Hermitian Gram matrix (2m x 2m real symmetric, every eigenvalue doubled) with the
+    Jacobi kernel; one vector per pair is kept and the result is polished by Newton-Schulz steps (complex GEMMs), which also
+    repairs the pairing when singular values are degenerate (Bell / GHZ states).
+
+No arithmetic happens on the host or in PyTorch: torch is used for allocation, views, concatenation / interleaving copies and
+the host read-back of kept ranks.  Limits: embedded problems must fit the Jacobi kernel (2 * rows <= 1024)."""
+import torch
+
+from . import ops
+from ._lib import SynError
+
+F64 = torch.float64
+C128 = torch.complex128
+JACOBI_MAX_N = 1024
+
+
+class Cx:
+    """Planar complex tensor: `re` and `im` are float64 tensors with identical shape and strides (views allowed)."""
+    __slots__ = ("re", "im")
+
+    def __init__(self, re, im):
+        assert re.shape == im.shape, (re.shape, im.shape)
+        self.re, self.im = re, im
+
+    # ---- construction / conversion ----------------------------------------------------------------------
+    @staticmethod
+    def from_torch(t):
+        """torch tensor (complex128 or float64, already on the device) -> planar."""
+        if t.dtype == C128:
+            v = torch.view_as_real(t)
+            return Cx(v[..., 0].contiguous(), v[..., 1].contiguous())
+        t = t.to(F64).contiguous()
+        return Cx(t, torch.zeros_like(t))
+
+    def to_torch(self):
+        return torch.complex(self.re.contiguous(), self.im.contiguous())
+
+    @staticmethod
+    def empty(shape, device):
+        return Cx(torch.empty(tuple(shape), dtype=F64, device=device), torch.empty(tuple(shape), dtype=F64, device=device))
+
+    @staticmethod
+    def ones(shape, device):
+        return Cx(torch.ones(tuple(shape), dtype=F64, device=device), torch.zeros(tuple(shape), dtype=F64, device=device))
+
+    # ---- tensor-like view interface (what the sweeps use) -------------------------------------------------
+    @property
+    def shape(self):
+        return self.re.shape
+
+    @property
+    def device(self):
+        return self.re.device
+
+    def dim(self):
+        return self.re.dim()
+
+    def stride(self, *a):
+        return self.re.stride(*a)
+
+    def is_contiguous(self):
+        return self.re.is_contiguous() and self.im.is_contiguous()
+
+    def _map(self, f):
+        return Cx(f(self.re), f(self.im))
+
+    def reshape(self, *shape):
+        return self._map(lambda x: x.reshape(*shape))
+
+    def t(self):
+        return self._map(lambda x: x.t())
+
+    def permute(self, *dims):
+        return self._map(lambda x: x.permute(*dims))
+
+    def contiguous(self):
+        return self._map(lambda x: x.contiguous())
+
+    def unsqueeze(self, d):
+        return self._map(lambda x: x.unsqueeze(d))
+
+    def clone(self):
+        return self._map(lambda x: x.clone())
+
+    def __getitem__(self, key):
+        return Cx(self.re[key], self.im[key])
+
+    def conj(self):
+        return Cx(self.re, -self.im)
+
+    def h(self):
+        """Conjugate transpose of a 2-D view (the imaginary part is negated into a new buffer)."""
+        return Cx(self.re.t(), (-self.im).t())
+
+
+def is_cx(x):
+    return isinstance(x, Cx)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# complex library calls on planar operands
+# ---------------------------------------------------------------------------------------------------------
+def empty(shape, device):
+    return Cx.empty(shape, device)
+
+
+def gemm(A, B, C, alpha=1.0, beta=0.0, **kw):
+    """Complex C = alpha A B + beta C (alpha, beta real) with the real kernel's strided descriptor `kw`: 4 launches."""
+    ops.gemm(A.re, B.re, C.re, alpha=alpha, beta=beta, **kw)
+    ops.gemm(A.im, B.im, C.re, alpha=-alpha, beta=1.0, **kw)
+    ops.gemm(A.re, B.im, C.im, alpha=alpha, beta=beta, **kw)
+    ops.gemm(A.im, B.re, C.im, alpha=alpha, beta=1.0, **kw)
+    return C
+
+
+def matmul(a, b, out=None, alpha=1.0, beta=0.0):
+    """Complex out = alpha a @ b + beta out on 2-D strided planar views."""
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2, (a.shape, b.shape)
+    if out is None:
+        out = Cx.empty((M, N), a.device)
+    return gemm(a, b, out, alpha=alpha, beta=beta, M=M, N=N, K=K, a_m=a.stride(0), a_k=a.stride(1), b_k=b.stride(0), b_n=b.stride(1),
+                c_m=out.stride(0), c_n=out.stride(1))
+
+
+def copy_strided(src):
+    return Cx(ops.copy_strided(src.re), ops.copy_strided(src.im))
+
+
+def add_site(A, B, first, last):
+    """Block assembly of `A + B` is linear: one kernel call per part."""
+    return Cx(ops.add_site(A.re, B.re, first, last), ops.add_site(A.im, B.im, first, last))
+
+
+def embed(A):
+    """(m x n) complex -> (2m x 2n) real with every entry a + ib replaced by [[a, -b], [b, a]] (rows and columns interleaved)."""
+    m, n = A.shape
+    E = torch.empty((m, 2, n, 2), dtype=F64, device=A.device)
+    E[:, 0, :, 0] = A.re
+    E[:, 1, :, 1] = A.re
+    E[:, 1, :, 0] = A.im
+    E[:, 0, :, 1] = -A.im
+    return E.reshape(2 * m, 2 * n)
+
+
+def unembed_columns(Qe, m, k):
+    """Even columns of an embedded (2m x 2k) basis -> planar complex (m x k): column j = Qe[0::2, 2j] + i Qe[1::2, 2j]."""
+    V = Qe.reshape(m, 2, k, 2)
+    return Cx(V[:, 0, :, 0].contiguous(), V[:, 1, :, 0].contiguous())
+
+
+def gram_deviation(Q):
+    """max |Q^H Q - I| of a planar (m x k) matrix: device scalar (two Gram GEMM pairs + the identity-deviation kernel)."""
+    k = Q.shape[1]
+    G = matmul(Q.h(), Q)
+    d_re = ops.identity_deviation(G.re)
+    # imaginary part must vanish: measure it as the deviation of (I + G_im) from the identity
+    eye = torch.eye(k, dtype=F64, device=Q.device)
+    d_im = ops.identity_deviation(G.im + eye)
+    return torch.maximum(d_re, d_im)
+
+
+ORTHO_TOL = 1e-13
+
+
+def polish_columns(Q, dev=None, max_steps=60):
+    """Newton-Schulz orthonormalisation of the columns of a planar (m x k) matrix, Q <- Q (1.5 I - 0.5 Q^H Q), until
+    max|Q^H Q - I| < ORTHO_TOL.  Quadratic once the deviation is below ~0.5 (2 steps from 1e-4); preserves the column space."""
+    d = float((gram_deviation(Q) if dev is None else dev).item())
+    steps = 0
+    while d > ORTHO_TOL:
+        if steps >= max_steps:
+            raise SynError("complex basis did not orthonormalise (deviation %.2e after %d Newton-Schulz steps)" % (d, steps))
+        G = matmul(Q.h(), Q)
+        Qn = copy_strided(Q)
+        matmul(Q, G, out=Qn, alpha=-0.5, beta=1.5)
+        Q = Qn
+        d = float(gram_deviation(Q).item())
+        steps += 1
+    return Q
+
+
+DEPENDENT_TOL = 1e-12
+
+
+def _embedded_basis(Aq, qk, want_R):
+    """Real Householder factorisation of the embedding of Aq (m x k): (planar basis (m x qk) from the even columns, |R_jj| of the
+    complex columns as a device vector or None)."""
+    m, k = Aq.shape
+    Qe, Se = ops.qrt(embed(Aq), 2 * qk, want_S=want_R)
+    Q = unembed_columns(Qe, m, qk)
+    if not want_R:
+        return Q, None
+    kk = min(qk, k)
+    return Q, Se[: 2 * kk, : 2 * kk].diagonal()[0::2].abs()
+
+
+def qrt(A, q, want_S=True):
+    """Complex truncation step (reference MPS:443-446 on complex cores): Q (m x qk) = orthonormal basis of span(A[:, :q]),
+    S = Q^H A, qk = min(q, m).  Runs the real Householder kernel on the embedded first q columns: with rows and columns
+    interleaved the real factorisation is the embedding of the complex one, so its even columns are the complex basis.
+    When the leading columns are numerically dependent the reflectors built from rounding noise break that pairing (detected
+    by the orthonormality check): dependent columns are then removed one at a time (the first flagged column is always
+    reliable), the basis is completed with fixed pseudo-random columns and factored again.  The completion directions are as
+    arbitrary as LAPACK's in the reference; span(A[:, :q]) is reproduced exactly."""
+    m, n = A.shape
+    q = int(q)
+    if q > n:
+        raise NotImplementedError("complex qrt cannot inflate a bond (q = %d > %d columns)" % (q, n))
+    qk = min(q, m)
+    Aq = A[:, :q]
+    if not Aq.is_contiguous():
+        Aq = copy_strided(Aq)
+    Q, _ = _embedded_basis(Aq, qk, want_R=False)
+    if float(gram_deviation(Q).item()) > ORTHO_TOL:
+        cols = list(range(q))
+        while cols:
+            sub = Cx(Aq.re[:, cols].contiguous(), Aq.im[:, cols].contiguous())
+            _, diag = _embedded_basis(sub, min(len(cols), m), want_R=True)
+            d = diag.cpu()
+            bad = (d <= DEPENDENT_TOL * float(d.max())).nonzero()
+            if bad.numel() == 0 and len(cols) <= m:
+                break
+            cols.pop(int(bad[0]) if bad.numel() else len(cols) - 1)
+        extra = qk - len(cols)
+        g = torch.Generator(device="cpu").manual_seed(1000 * m + q)
+        fill = torch.randn((2, m, max(extra, 0)), dtype=F64, generator=g).to(A.device)
+        full = Cx(torch.cat([Aq.re[:, cols], fill[0]], dim=1).contiguous(), torch.cat([Aq.im[:, cols], fill[1]], dim=1).contiguous())
+        Q, _ = _embedded_basis(full, qk, want_R=False)
+        Q = polish_columns(Q)
+    S = matmul(Q.h(), A) if want_S else None
+    return Q, S
+
+
+def _hermitian_embedding(H):
+    """(m x m) Hermitian planar -> (2m x 2m) real symmetric [[Hr, -Hi], [Hi, Hr]] (block layout; symmetrised)."""
+    top = torch.cat([H.re, -H.im], dim=1)
+    bot = torch.cat([H.im, H.re], dim=1)
+    S = torch.cat([top, bot], dim=0)
+    return (0.5 * (S + S.t())).contiguous()
+
+
+def svd_basis(M, chi_max, cutoff, eigh, rank_tol=3.2e-7):
+    """Left singular basis of a planar complex unfolding M (m x c), m <= c or reduced by the caller:
+    returns (U (m x keep) planar with orthonormal columns, keep, sigma (device, m values, descending), discarded weight).
+    `eigh(S, chi, cutoff, rank_tol)` is the real symmetric eigen-solver (syngular.tensor._sweeps.eigh_gram)."""
+    m, c = M.shape
+    if 2 * m > JACOBI_MAX_N:
+        raise NotImplementedError("complex bond SVD needs 2 * rows <= %d (got rows = %d)" % (JACOBI_MAX_N, m))
+    H = matmul(M, M.h())                                         # Hermitian Gram matrix (squared singular values)
+    S = _hermitian_embedding(H)
+    Ut, sigma2, info, winfo = eigh(S, 2 * int(chi_max), cutoff, rank_tol)
+    keep = max(1, int(info[0].item()) // 2)
+    sigma = sigma2[0::2]
+    discarded = 0.5 * winfo[0]
+    # rows of Ut are the embedded eigenvectors [x ; y], pairs (v, Jv) adjacent when the spectrum is simple: keep one per pair
+    V = Ut[0:2 * keep:2]
+    U = Cx(ops.copy_strided(V[:, :m].t()), ops.copy_strided(V[:, m:].t()))          # (m, keep): column j = x_j + i y_j
+    dev = gram_deviation(U)
+    d = float(dev.item())
+    if d > 1e-3:
+        # degenerate singular values: the Jacobi basis of a cluster is an arbitrary real rotation of the (v, Jv) pairs, so the
+        # even rows need not be complex-independent.  Mix ALL 2 keep rows with a fixed well-conditioned real matrix (the span is
+        # the same complex subspace) and orthonormalise.
+        W = Ut[0:2 * keep]
+        C = Cx(ops.copy_strided(W[:, :m].t()), ops.copy_strided(W[:, m:].t()))      # (m, 2 keep)
+        g = torch.Generator(device="cpu").manual_seed(keep)
+        mix = torch.randn((2 * keep, keep), dtype=F64, generator=g).to(M.device) / (2.0 * float(2 * keep) ** 0.5)
+        U = matmul(C, Cx(mix, torch.zeros_like(mix)))
+        U = polish_columns(U)
+    else:
+        U = polish_columns(U, dev=dev)
+    return U, keep, sigma, discarded

@@ -1,0 +1,39 @@
+"""GPU: complex128 cores and gates (BASELINE configs[2]) on the real FP64 kernels -- the scenarios of
+tests/complex_cases.py through the CUDA product, plus a larger brick-wall circuit whose bond SVDs run the multi-CTA Jacobi."""
+import numpy as np
+import pytest
+
+import complex_cases as cc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(cc.CASES))
+def test_complex_case(name):
+    cc.CASES[name]()
+
+
+def test_brickwall_12_qubits_chi_64_against_state_vector():
+    """12 qubits, depth 8, Haar-random gates: exact up to bond 64 (embedded eigenproblems up to 256 x 256: Cholesky + ring Jacobi)."""
+    from syngular.quantum import Circuit
+    rng = np.random.default_rng(11)
+    n, depth = 12, 8
+    structure, psi = [], np.zeros(2 ** n, dtype=complex)
+    psi[0] = 1.0
+    for layer in range(depth):
+        for i in range(layer % 2, n - 1, 2):
+            g = cc.haar(rng, 4).reshape(2, 2, 2, 2)
+            structure.append((g, i))
+            psi = cc._dense_apply(psi, g, i, n)
+    c = Circuit(n, structure=structure, chi_max=64)
+    c.run()
+    st = c.get().state
+    assert max(s.shape[2] for s in st.sites[:-1]) == 64
+    assert np.max(np.abs(c.get().to_tensor() - psi)) < 1e-10
+    assert abs((st.conj() | st) - 1.0) < 1e-10
+    # truncated: chi 16 keeps the norm below one and the fidelity with the exact state high but not perfect
+    c2 = Circuit(n, structure=structure, chi_max=16)
+    c2.run()
+    got = c2.get().to_tensor()
+    f = abs(np.vdot(psi, got)) ** 2
+    assert np.linalg.norm(got) <= 1.0 + 1e-12 and 0.05 < f < 1.0
