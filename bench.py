@@ -368,6 +368,38 @@ def run_ours(args):
         except Exception as exc:                     # never let the side measurement break the headline line
             c1 = {"error": repr(exc)}
 
+    # BASELINE configs[2]: 50-qubit brick-wall circuit of Haar-random two-qubit unitaries, depth 20 (seed 3), complex128
+    # through the planar compositions on the FP64 kernels.  The embedded bond eigenproblem is 4 chi x 4 chi real and the Jacobi kernel
+    # stops at 1024, so chi_max <= 256 is what runs today (configs[2] names 512); the default bench line uses chi_max = 64 to stay short.
+    c3 = None
+    if rank == 0:
+        try:
+            from syngular.quantum import Circuit
+            rng3 = np.random.default_rng(3)
+
+            def haar4():
+                z = rng3.normal(size=(4, 4)) + 1j * rng3.normal(size=(4, 4))
+                q, r = np.linalg.qr(z)
+                return (q * (np.diag(r) / np.abs(np.diag(r)))).reshape(2, 2, 2, 2)
+            nq, depth, chi3 = 50, 20, 64
+            structure = [(haar4(), i) for layer in range(depth) for i in range(layer % 2, nq - 1, 2)]
+            Circuit(8, structure=[(g, i % 7) for g, i in structure[:40]], chi_max=16).run()         # warm-up of every code path
+            torch.cuda.synchronize()
+            l0 = ops.lib.syn_launch_count()
+            t0 = time.perf_counter()
+            circ = Circuit(nq, structure=structure, chi_max=chi3)
+            circ.run()
+            torch.cuda.synchronize()
+            sec3 = time.perf_counter() - t0
+            st3 = circ.get().state
+            c3 = {"gates_per_s": len(structure) / sec3, "seconds_per_circuit": sec3, "gates": len(structure), "qubits": nq, "depth": depth,
+                  "chi_max": chi3, "max_bond": int(max(c.shape[2] for c in st3.sites[:-1])), "norm2": float(np.real(st3.conj() | st3)),
+                  "kernel_launches": int(ops.lib.syn_launch_count() - l0),
+                  "note": "configs[2] at chi_max=64 (complex128 planar on the real FP64 kernels; chi_max <= 256 supported, 512 needs a "
+                          "native complex Jacobi); norm2 < 1 is the truncation loss"}
+        except Exception as exc:
+            c3 = {"error": repr(exc)}
+
     line = None
     if rank == 0:
         # roofline of the dominant kernel: profile one sweep with per-launch CUDA events on the launching stream
@@ -420,7 +452,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "extra": {"c1_readme_chain": c1, "c4_batched_overlaps_states_per_s": c4_value, "c4_ms_per_batch": ms_c4 / c4_reps,
+            "extra": {"c1_readme_chain": c1, "c3_circuit": c3, "c4_batched_overlaps_states_per_s": c4_value, "c4_ms_per_batch": ms_c4 / c4_reps,
                       "c4_note": "BASELINE configs[3]: 8192 x (N=32, d=2, chi=64) overlaps, batch-sharded over %d GPU(s), one all-gather of 8192 "
                                  "float64; %.2f TFLOP/s FP64, %.0f GB/s of core traffic; gathered %s" % (
                                      world, c4_flops / (ms_c4 / c4_reps * 1e-3) / 1e12, c4_bytes / (ms_c4 / c4_reps * 1e-3) / 1e9,

@@ -193,6 +193,42 @@ def mps_apply(cores, gate, index):
     return cores
 
 
+def mpo_apply(cores, op_cores, indices):
+    """`MatrixProductOperator.apply(operator, indices)` for an MPO operator (matrix_product_operator.py:582-626), literal:
+    contract the target cores `indices` with the operator cores (target OUT leg with operator IN leg, both bond chains summed,
+    the operator's outer bonds must be 1: np.squeeze at :602), giving T[l, in_0..in_{m-1}, out'_0..out'_{m-1}, r]; then re-split
+    left to right with the qrt step, keeping the target's existing right bonds.  The reference reshapes T as
+    (l * in_k * out'_k, -1) although its legs are NOT interleaved (:609), so for m >= 2 the result is a fixed scramble of the
+    product, not the product -- replicated as is (pinned by tests/golden/mpo_apply.npz).  Returns the new list of cores."""
+    cores = [np.array(c, copy=True) for c in cores]
+    m = len(indices)
+    T = None
+    for idx, jdx in enumerate(indices):
+        c = np.einsum("lixr,mxon->lmiorn", cores[jdx], op_cores[idx])           # (l, l', in, out', r, r')
+        if T is None:
+            if c.shape[1] != 1:
+                raise ValueError("cannot select an axis to squeeze out which has size not equal to one")
+            T = c[:, 0]                                                          # (l, in, out', r, r')
+        else:
+            T = np.tensordot(T, c, axes=([T.ndim - 2, T.ndim - 1], [0, 1]))     # (..., in, out', r, r')
+    if T.shape[-1] != 1:
+        raise ValueError("cannot select an axis to squeeze out which has size not equal to one")
+    T = T[..., 0]                                                                # (l, in_0, out_0, in_1, out_1, ..., r)
+    perm = [0] + [1 + 2 * k for k in range(m)] + [2 + 2 * k for k in range(m)] + [T.ndim - 1]
+    T = np.ascontiguousarray(T.transpose(perm))                                  # (l, in..., out'..., r) as contract() returns it
+    for idx in range(m - 1):
+        jdx = indices[idx]
+        l, i = cores[jdx].shape[0], cores[jdx].shape[1]
+        o = op_cores[idx].shape[2]
+        L = T.reshape(l * i * o, -1)
+        Q, R = qrt(L, cores[jdx].shape[3])
+        cores[jdx] = Q.reshape(l, i, o, Q.shape[1])
+        T = R
+    jdx = indices[-1]
+    cores[jdx] = T.reshape(cores[jdx].shape[0], cores[jdx].shape[1], op_cores[m - 1].shape[2], cores[jdx].shape[3])
+    return cores
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step, left to right (matrix_product_state.py:298-319,
     matrix_product_operator.py:430-450).  `T` is the (interleaved, for an MPO) dense tensor and `shapes` the
@@ -439,6 +475,11 @@ class MPO(_Chain):
         if isinstance(other, MPO):
             sites = [site_mpo_mpo(a, b) for a, b in zip(self.sites, other.sites)]
             return MPO.from_sites(sites) >> m                          # :289
+        return None
+
+    def apply(self, operator, indices):
+        """In place, returns None (matrix_product_operator.py:582-626)."""
+        self.sites = mpo_apply(self.sites, operator.sites, list(indices))
         return None
 
     def __getitem__(self, key):

@@ -313,6 +313,34 @@ def apply_gate(sites, gate, index, mode="compress", chi_max=None, cutoff=0.0):
 
 
 @complex_aware
+def mpo_apply_range(sites, op_sites, indices):
+    """`MatrixProductOperator.apply(operator, indices)` with an MPO operator (MPO:582-626): one strided GEMM per site forms the
+    product cores, a chain of GEMMs contracts the range, and the block is re-split by the qrt step keeping the target's right
+    bonds.  The reference re-splits the block with its legs ordered (l, in..., out..., r) as if they were interleaved (MPO:609):
+    that literal behaviour is what is computed (golden: tests/golden/mpo_apply.npz).  Returns the new list of cores."""
+    out = list(sites)
+    m = len(indices)
+    if op_sites[0].shape[0] != 1 or op_sites[-1].shape[-1] != 1:
+        raise ValueError("cannot select an axis to squeeze out which has size not equal to one")      # np.squeeze, MPO:602
+    T, dims = None, []
+    for idx, jdx in enumerate(indices):
+        c = site_mpo_mpo(out[jdx], op_sites[idx])                       # ((l,l'), in, out', (r,r'))
+        T = c.reshape(-1, c.shape[-1]) if T is None else ops.matmul(T, c.reshape(c.shape[0], -1)).reshape(-1, c.shape[-1])
+        dims += [c.shape[1], c.shape[2]]
+    l0, r_last = out[indices[0]].shape[0], out[indices[-1]].shape[-1]
+    T = T.reshape([l0] + dims + [r_last])
+    T = T.permute([0] + [1 + 2 * k for k in range(m)] + [2 + 2 * k for k in range(m)] + [2 * m + 1]).contiguous()
+    for idx in range(m - 1):
+        jdx = indices[idx]
+        l, i, o = out[jdx].shape[0], out[jdx].shape[1], op_sites[idx].shape[2]
+        Q, S = ops.qrt(T.reshape(l * i * o, -1), int(out[jdx].shape[3]))
+        out[jdx] = Q.reshape(l, i, o, Q.shape[1])
+        T = S
+    jdx = indices[-1]
+    out[jdx] = T.reshape(out[jdx].shape[0], out[jdx].shape[1], op_sites[m - 1].shape[2], out[jdx].shape[3])
+    return out
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step (MPS:298-319, MPO:430-450)."""
     cores, l, n = [], 1, len(shapes)

@@ -133,7 +133,15 @@ class MatrixProductOperator(_MatrixProduct):
         return self
 
     def apply(self, operator, indices):
-        raise NotImplementedError("MatrixProductOperator.apply (MPO:582-651) is a 'next' row of the scope table")
+        """Apply an MPO `operator` to the sites `indices` of this chain, in place, returns None (MPO:582-626).  One site: the
+        exact product.  Several sites: the reference's literal re-split (see _sweeps.mpo_apply_range)."""
+        if not self.decomposed:
+            raise Exception("MatrixProductState not decomposed")                     # MPO:650 (message as in the reference)
+        if not isinstance(operator, MatrixProductOperator):
+            raise NotImplementedError("MatrixProductOperator.apply with a dense operator is unfinished in the reference (MPO:627-647)")
+        self.sites = sw.mpo_apply_range(self.sites, operator.sites, [int(i) for i in indices])
+        self._refresh_from_cores(bonds=False)
+        return None
 
     def transpose(self):
         return MatrixProductOperator.from_sites([s.permute(0, 2, 1, 3).contiguous() for s in self.sites])

@@ -307,7 +307,23 @@ def case_quantum_circuits(be):
     close(be.run_circuit(3, QUANTUM_CIRCUITS["toffoli_110"][1]), np.eye(8)[7], rtol=1e-12, what="Toffoli |110> -> |111>")
 
 
+def case_mpo_apply_range(be):
+    """MatrixProductOperator.apply(operator, indices) (MPO:582-626): exact for one site, the reference's literal re-split beyond."""
+    g = load("mpo_apply")
+    for name in [str(n) for n in g["names"]]:
+        A = be.mpo_sites(chain(g, name + "/A"))
+        O = be.mpo_sites(chain(g, name + "/op"))
+        ret = A.apply(O, [int(i) for i in g[name + "/indices"]])
+        assert ret is None
+        assert [tuple(int(x) for x in s.shape) for s in be.sites(A)] == [tuple(int(x) for x in r) for r in g[name + "/after_shapes"]]
+        T = None
+        for c in be.sites(A):                              # raw chain product (l, in_0, out_0, in_1, out_1, ..., r), as the golden
+            T = c if T is None else np.tensordot(T, c, axes=(T.ndim - 1, 0))
+        close(T, g[name + "/after_dense"], what="apply " + name)
+
+
 ALL_CASES = [
+    case_mpo_apply_range,
     case_matmul_known_answers,
     case_mps_dot_compress_normalize,
     case_mps_add_augment,
