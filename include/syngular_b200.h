@@ -135,6 +135,18 @@ typedef struct {
 int syn_overlap_batched_fits(const syn_overlap_site_t* sites, int n_sites);
 int syn_overlap_batched_f64(const syn_overlap_site_t* sites, int n_sites, int batch, const double* E_in, double* E_out, void* stream);
 
+/* ---- dominant invariant subspace by spectral projection (GEMM-bound eigen-solver of the density-matrix rounding) ------------
+ * U (n x ne, row-major) = orthonormal basis of the span of the ne dominant eigenvectors of the symmetric PSD matrix A (n x n,
+ * contiguous, not modified): `sp2_iters` trace-steered SP2 steps X <- X^2 | 2X - X^2 from X = A / |A|_F (one DMMA GEMM + one
+ * elementwise kernel each, branch chosen on the device), then `ns_iters` Newton-Schulz steps on P[:, :ne].  No host round trip.
+ * Stands where the reference's unfinished density-matrix branch calls np.linalg.eigh (MPO:228) and keeps eigvecs[:, :min_bond].
+ * info (device, 8 doubles): [0] tr P, [1] |P|_F^2 (both = ne when converged), [2] sum A o P = kept weight, [3] |A|_F,
+ * [4] max |U^T U - I|, [5] tr A, [6] tr(X - X^2) one step before the end.  The caller decides (and falls back to
+ * syn_jacobi_rows_f64 when the spectrum has no gap at ne). */
+size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_iters);
+int syn_dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_iters, double* U, void* ws, size_t ws_bytes,
+                              double* info, void* stream);
+
 /* ---- block assembly and elementwise kernels ---------------------------------------------------------------- */
 /* `A + B` site: direct sum of the bond spaces, self's block first; cores as (l, phys, r) with the physical legs flattened
  * (np.block / scipy.linalg.block_diag loops of MPS:82-96 and MPO:90-106). */

@@ -201,6 +201,25 @@ def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shi
     return Ut, sigma, info, winfo
 
 
+lib.syn_dominant_subspace_workspace_f64.restype = ctypes.c_size_t
+lib.syn_dominant_subspace_workspace_f64.argtypes = [_i32, _i32, _i32]
+
+
+def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20):
+    """Orthonormal basis U (n x ne) of the span of the `ne` dominant eigenvectors of the symmetric PSD matrix A (n x n contiguous,
+    not modified) by SP2 spectral projection + Newton-Schulz (csrc/purify.cu): GEMM-bound, one fixed sequence of launches.
+    Returns (U, info) with info a DEVICE vector of 8 doubles (see syngular_b200.h); nothing is synchronised here."""
+    require_cuda_f64(A)
+    n = A.shape[0]
+    assert A.dim() == 2 and A.shape[1] == n and A.is_contiguous()
+    U = torch.empty((n, int(ne)), dtype=torch.float64, device=A.device)
+    info = torch.zeros((8,), dtype=torch.float64, device=A.device)
+    ws = workspace(lib.syn_dominant_subspace_workspace_f64(n, int(ne), int(sp2_iters)), A.device, tag="purify")
+    check(lib.syn_dominant_subspace_f64(ptr(A), _i32(n), _i32(int(ne)), _i32(int(sp2_iters)), _i32(int(ns_iters)), ptr(U), ptr(ws),
+                                        _sz(ws.numel() * 8), ptr(info), stream_ptr()), "syn_dominant_subspace_f64")
+    return U, info
+
+
 def add_site(A, B, first, last):
     """Block assembly of `A + B` for one site (MPS:82-96, MPO:90-106).  Cores contiguous, physical legs flattened by the kernel."""
     require_cuda_f64(A, B)

@@ -140,6 +140,28 @@ def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shi
             torch.tensor([disc, sv[0]], dtype=F64))
 
 
+def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20):
+    """csrc/purify.cu restated: SP2 from A / |A|_F with the trace-steered branch, then Newton-Schulz on P[:, :ne]."""
+    a = A.numpy()
+    n = a.shape[0]
+    fro = float(np.sqrt((a * a).sum()))
+    x = a / fro if fro > 0 else a * 0
+    tr0 = float(np.trace(x))
+    hist = [(tr0, float((x * x).sum()))]
+    for _ in range(int(sp2_iters)):
+        tr, f2 = hist[-1]
+        y = x @ x
+        y = 0.5 * (y + y.T)
+        x = y if abs(f2 - ne) < abs(2 * tr - f2 - ne) else 2 * x - y
+        hist.append((float(np.trace(x)), float((x * x).sum())))
+    u = x[:, :ne].copy()
+    for _ in range(int(ns_iters)):
+        u = u @ (1.5 * np.eye(ne) - 0.5 * (u.T @ u))
+    dev = float(np.max(np.abs(u.T @ u - np.eye(ne))))
+    info = np.array([hist[-1][0], hist[-1][1], float((a * x).sum()), fro, dev, tr0 * fro, hist[-2][0] - hist[-2][1], 0.0])
+    return torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(info)
+
+
 def identity_deviation(X):
     x = X.numpy()
     return torch.tensor([float(np.max(np.abs(x - np.eye(x.shape[0]))))], dtype=F64)
@@ -176,7 +198,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

@@ -1,0 +1,74 @@
+"""GPU: the spectral-projection eigen-subspace solver (csrc/purify.cu) against numpy, and the density-matrix rounding sweep that
+uses it against the textbook-SVD oracle and against the Jacobi path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _psd(rng, n, decay):
+    """Symmetric PSD test matrix with a smooth, gapped-everywhere spectrum lam_i = exp(-decay i / n) (like a bond's squared
+    singular values) and a Haar-random eigenbasis."""
+    q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    lam = np.exp(-decay * np.arange(n) / n)
+    return (q * lam) @ q.T, q, lam
+
+
+@pytest.mark.parametrize("n,ne,decay", [(64, 32, 6.0), (256, 128, 10.0), (512, 256, 12.0), (512, 100, 8.0), (384, 256, 9.0)])
+def test_dominant_subspace_matches_eigh(n, ne, decay):
+    from syngular_b200 import ops
+    rng = np.random.default_rng(n + ne)
+    A, q, lam = _psd(rng, n, decay)
+    U, info = ops.dominant_subspace(torch.from_numpy(A).cuda(), ne, sp2_iters=48, ns_iters=30)
+    h = info.cpu().numpy()
+    Un = U.cpu().numpy()
+    assert abs(h[0] - ne) < 1e-9 * ne and abs(h[1] - ne) < 1e-9 * ne, h
+    assert h[4] < 1e-13 and np.max(np.abs(Un.T @ Un - np.eye(ne))) < 1e-13
+    P = q[:, :ne] @ q[:, :ne].T
+    assert np.max(np.abs(Un @ Un.T - P)) < 1e-11
+    assert abs(h[2] - lam[:ne].sum()) < 1e-12 * lam.sum() and abs(h[5] - lam.sum()) < 1e-12 * lam.sum()
+    assert abs(h[3] - np.linalg.norm(A)) < 1e-12 * np.linalg.norm(A)
+
+
+def test_no_gap_is_reported_not_hidden():
+    """Rank 40 < ne = 64: there is no projector of trace 64 to converge to; the info vector says so and the sweep falls back."""
+    from syngular_b200 import ops
+    rng = np.random.default_rng(1)
+    B = rng.normal(size=(128, 40))
+    A = B @ B.T
+    U, info = ops.dominant_subspace(torch.from_numpy(A).cuda(), 64, sp2_iters=44, ns_iters=22)
+    h = info.cpu().numpy()
+    assert not (abs(h[0] - 64) < 1e-9 * 64 and abs(h[1] - 64) < 1e-9 * 64 and h[4] < 1e-12)
+
+
+@pytest.mark.parametrize("n,chi,chiw", [(14, 16, 4), (16, 32, 8)])
+def test_sweep_with_projection_solver_matches_oracle(n, chi, chiw):
+    import bench
+    from syngular.tensor import _sweeps as sw
+    from oracle import ref_numpy as R, svd_numpy as S
+    X, W = bench.make_chain(5, n=n, chi=chi, chiw=chiw)
+    ref, spectra, discarded = S.apply_round_svd(X, W, chi)
+    Xd, Wd = [sw.as_core(c) for c in X], [sw.as_core(c) for c in W]
+    saved = sw.PURIFY_MIN_N
+    try:
+        sw.PURIFY_MIN_N = chi                      # every plateau bond (Gram matrices 2 chi x 2 chi) takes the projection solver
+        sw.PURIFY_STATS.update(taken=0, fallback=0)
+        out, trunc = sw.apply_round_dm(Xd, Wd, chi)
+        taken = sw.PURIFY_STATS["taken"]
+        sw.PURIFY_MIN_N = 0
+        out_j, _ = sw.apply_round_dm(Xd, Wd, chi)
+    finally:
+        sw.PURIFY_MIN_N = saved
+    assert taken >= 4
+    got, got_j = [c.cpu().numpy() for c in out], [c.cpu().numpy() for c in out_j]
+    dense_ref = R.to_dense(ref)
+    scale = np.max(np.abs(dense_ref))
+    assert np.max(np.abs(R.to_dense(got) - dense_ref)) < 1e-10 * scale
+    assert np.max(np.abs(R.to_dense(got) - R.to_dense(got_j))) < 1e-10 * scale
+    sig, keep, disc = trunc.host()
+    for k in range(n - 1):
+        kk = ref[k].shape[-1]
+        assert keep[k] == kk
+        assert np.max(np.abs(sig[k][:kk] - spectra[k][:kk])) < 1e-10 * spectra[k][0]
+        assert abs(disc[k] - discarded[k]) < 1e-10 * spectra[k][0] ** 2 * len(spectra[k])
