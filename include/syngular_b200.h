@@ -146,6 +146,14 @@ int syn_overlap_batched_f64(const syn_overlap_site_t* sites, int n_sites, int ba
 size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_iters);
 int syn_dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_iters, double* U, void* ws, size_t ws_bytes,
                               double* info, void* stream);
+/* The same solver as ONE persistent cooperative kernel (one CTA per SM, iterates resident in L2, 32 x 32 DMMA tiles from a cp.async
+ * ring, symmetric products computed on their lower tiles only, grid barrier per step).  The iteration counts adapt on the device:
+ * SP2 stops two steps after tr(X - X^2) < 1e-11 ne (at most sp2_max steps), Newton-Schulz when max |U^T U - I| < 1e-13 (at most
+ * ns_max).  Needs n and ne multiples of 64 (syn_dominant_subspace_fused_fits).  info as above, plus [7] = sp2 steps + 1000 * NS steps. */
+size_t syn_dominant_subspace_fused_workspace_f64(int n, int ne, int sp2_max, int ns_max);
+int syn_dominant_subspace_fused_fits(int n, int ne);
+int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
+                                    double* info, void* stream);
 
 /* ---- block assembly and elementwise kernels ---------------------------------------------------------------- */
 /* `A + B` site: direct sum of the bond spaces, self's block first; cores as (l, phys, r) with the physical legs flattened

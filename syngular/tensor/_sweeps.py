@@ -620,15 +620,17 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
 # GEMM-bound (~1 ms at n = 512 against 6.3 ms), same kept subspace.  0 = off.  Needs a spectral gap at the cut, no cutoff, and
 # chi_max < n; otherwise (or when its own checks fail) the Jacobi path runs.
 PURIFY_MIN_N = 256
-PURIFY_SP2_ITERS = 52
+PURIFY_SP2_ITERS = 52          # multi-launch variant: fixed counts
 PURIFY_NS_ITERS = 26
+PURIFY_SP2_MAX = 90            # fused kernel: upper limits (it stops by itself); 90 steps resolve gaps down to ~1e-12 |A|
+PURIFY_NS_MAX = 60
 PURIFY_STATS = {"taken": 0, "fallback": 0}
 
 
 def dominant_subspace(A, chi_max):
     """(U (n x chi_max) orthonormal, discarded weight) by spectral projection, or None when the iteration did not reach a projector
     of trace chi_max that is orthonormalised to 1e-12 (no gap at the cut: rank-deficient bonds) -- one host read of 8 doubles."""
-    U, info = ops.dominant_subspace(A, chi_max, PURIFY_SP2_ITERS, PURIFY_NS_ITERS)
+    U, info = ops.dominant_subspace(A, chi_max, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
     h = info.cpu().numpy()
     tr, f2, kept_w, dev, tr_a, idem = h[0], h[1], h[2], h[4], h[5], h[6]
     ok = (abs(tr - chi_max) < 1e-9 * chi_max and abs(f2 - chi_max) < 1e-9 * chi_max and abs(idem) < 1e-11 * chi_max and dev < 1e-12
@@ -649,6 +651,9 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
     trunc = Truncation()
     out = []
     T = torch.ones((1, 1, 1), dtype=F64, device=X[0].device)
+    right_dim = [1] * (n + 1)                 # dimension of the physical space to the right of bond k: bounds the rank of that bond
+    for k in range(n - 1, -1, -1):
+        right_dim[k] = min(right_dim[k + 1] * int(W[k].shape[2]), 1 << 40)
     for k in range(n - 1):
         M = contract_carry(T, X[k], W[k])
         s, o, D = M.shape
@@ -656,13 +661,16 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
         M2 = M.reshape(s * o, D)
         A = gram_with_environment(M2, E[k + 1], b, r)
         nA = s * o
-        if PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and chi_max < nA and A.is_contiguous():
-            got = dominant_subspace(A, chi_max)
+        # structural rank of the bond: when it is below chi_max nothing is truncated and the kept space is the range of A -- the
+        # projection solver then finds it at the (huge) gap between the last non-zero eigenvalue and the null space
+        ne = min(chi_max, D, right_dim[k + 1])
+        if PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
+            got = dominant_subspace(A, ne)
             if got is not None:
                 U, disc = got
-                trunc.sigma.append(LazySpectrum(A, U)); trunc.keep.append(chi_max); trunc.discarded.append(disc)
-                out.append(U.reshape(s, o, chi_max))
-                T = _carry_from(U, M2, chi_max, b, r, transposed_basis=False)
+                trunc.sigma.append(LazySpectrum(A, U)); trunc.keep.append(ne); trunc.discarded.append(disc)
+                out.append(U.reshape(s, o, ne))
+                T = _carry_from(U, M2, ne, b, r, transposed_basis=False)
                 continue
         if nA > 1024:
             raise NotImplementedError("density-matrix rounding needs chi*d <= 1024 (got %d)" % nA)

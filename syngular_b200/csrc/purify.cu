@@ -241,11 +241,379 @@ int dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_
     return 0;
 }
 
+
+// =====================================================================================================================================
+// Fused variant: the WHOLE solver in one persistent cooperative kernel.
+//
+// The multi-launch sequence above is launch- and latency-bound (every product is a 512^3 GEMM of ~10 us of math behind ~25 us of
+// launch gaps, pipeline fill and partial-sum traffic).  Here one CTA per SM stays resident, the iterates live in L2 (2 MB each), and
+// a step is: every CTA forms its 32 x 32 output tiles with DMMA from a 3-stage cp.async ring, applies the step's epilogue, and meets
+// the others at a grid barrier (one atomic + acquire poll).  All three products are arranged as  C = R1 R2^T  with both operands read
+// along contiguous rows ("NT"), so one tile routine serves them:
+//     SP2:     Y = X X^T (X symmetric)            -- only the 136 lower tiles are computed, the mirror image is written with them;
+//              epilogue X' = Y or 2X - Y by the trace rule, and the new trace / Frobenius norm are accumulated for the next rule
+//     Gram:    G = V V^T  with V = U^T kept alongside U          -- lower tiles + mirror, epilogue max |G - I|
+//     update:  U' = a U + b U G^T (G symmetric)    -- epilogue writes U' and its transpose V'
+// Convergence is decided INSIDE the kernel from the accumulated scalars (every CTA reads the same values after the barrier), so the
+// iteration counts adapt to the spectrum with no host round trip: SP2 stops two steps after tr(X - X^2) < 1e-11 ne, Newton-Schulz when
+// max |U^T U - I| < 1e-13.  While the smallest singular value of U is still far from 1 the steeper map 2x - x^3 replaces 1.5x - 0.5x^3.
+constexpr int PF_THREADS = 256, PF_BK = 64, PF_STAGES = 3, PF_LD = PF_BK + 4, PF_T = 32, PF_STEEP = 6;
+constexpr size_t PF_SMEM = (size_t)PF_STAGES * 2 * PF_T * PF_LD * sizeof(double);
+
+struct PurifyArgs {
+    const double* A;
+    double *X0, *X1, *Ua, *Ub, *Va, *Vb, *G, *Uout, *ctrl, *info;
+    unsigned* bar;
+    int n, ne, sp2_max, ns_max;
+};
+
+__device__ __forceinline__ unsigned pf_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void pf_grid_barrier(unsigned* ctr, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        for (unsigned spin = 0; pf_ld_acquire(ctr) < target; ++spin)
+            if (spin > (1u << 23)) __trap();        // a lost CTA would otherwise hang the GPU
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// acc[i][j][0..1] of this warp's 16 x 16 sub-tile of  C(32 x 32) = R1[i0.., :K] R2[j0.., :K]^T ; warps 4..7 take the odd 32-wide
+// k-halves of every stage and are folded into warps 0..3 through shared memory at the end.  Returns true for the warps that own
+// the result.  K % PF_BK == 0, rows 16-byte aligned.
+__device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_t ld1, const double* __restrict__ R2, int64_t ld2, int i0, int j0, int K,
+                                           double* smem, double (&acc)[2][2][2]) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wg = warp >> 2, q = warp & 3, wm0 = (q >> 1) * 16, wn0 = (q & 1) * 16;
+    constexpr int TILE = PF_T * PF_LD;                       // doubles per operand tile
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    auto fill = [&](int stage, int k0) {
+        double* sa = smem + (size_t)stage * 2 * TILE;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            const int c = tid + PF_THREADS * p;              // 2048 16-byte chunks: operand | row | chunk
+            const int op = c >> 10, row = (c >> 5) & 31, ch = c & 31;
+            const double* src = op ? (R2 + (int64_t)(j0 + row) * ld2 + k0 + ch * 2) : (R1 + (int64_t)(i0 + row) * ld1 + k0 + ch * 2);
+            cp_async<16>(sa + op * TILE + row * PF_LD + ch * 2, src, true);
+        }
+    };
+    const int KT = K / PF_BK;
+    __syncthreads();                                          // the previous user of the ring is done
+#pragma unroll
+    for (int s = 0; s < PF_STAGES - 1; s++) {
+        if (s < KT) fill(s, s * PF_BK);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<PF_STAGES - 2>();
+        __syncthreads();
+        const int nk = kt + PF_STAGES - 1;
+        if (nk < KT) fill(nk % PF_STAGES, nk * PF_BK);
+        cp_async_commit();
+        const double* a_s = smem + (size_t)(kt % PF_STAGES) * 2 * TILE;
+        const double* b_s = a_s + TILE;
+        const int kb = wg * 32;
+        double af[2][2], bf[2][2];
+        auto frags = [&](int buf, int kk) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) af[buf][i] = a_s[(wm0 + i * 8 + g) * PF_LD + kb + kk + t];
+#pragma unroll
+            for (int j = 0; j < 2; j++) bf[buf][j] = b_s[(wn0 + j * 8 + g) * PF_LD + kb + kk + t];
+        };
+        frags(0, 0);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 4) {
+            const int cur = (kk >> 2) & 1;
+            if (kk + 4 < 32) frags(cur ^ 1, kk + 4);
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                          // ring free: reuse its head for the k-half reduction
+    double* red = smem;                                       // [4 warps][8 values][32 lanes]
+    if (wg == 1) {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                red[(q * 8 + (i * 2 + j) * 2 + 0) * 32 + lane] = acc[i][j][0];
+                red[(q * 8 + (i * 2 + j) * 2 + 1) * 32 + lane] = acc[i][j][1];
+            }
+    }
+    __syncthreads();
+    if (wg == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                acc[i][j][0] += red[(q * 8 + (i * 2 + j) * 2 + 0) * 32 + lane];
+                acc[i][j][1] += red[(q * 8 + (i * 2 + j) * 2 + 1) * 32 + lane];
+            }
+    }
+    return wg == 0;
+}
+
+__device__ __forceinline__ void pf_lower_tile(int idx, int& ti, int& tj) {
+    int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+    while (r * (r + 1) / 2 > idx) --r;
+    ti = r;
+    tj = idx - r * (r + 1) / 2;
+}
+
+__device__ __forceinline__ void pf_atomic_max(double* addr, double v) {       // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// ctrl layout (doubles, zeroed by the host): [0] |A|_F^2  [1] sum A o P  [2..3] unused  [4 + 2 it] tr X_it  [5 + 2 it] |X_it|_F^2
+//                                            [4 + 2 (sp2_max + 2) + it] max |G_it - I|
+__global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const PurifyArgs a) {
+    extern __shared__ __align__(16) double pf_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3, q = (tid >> 5) & 3;
+    const int wm0 = (q >> 1) * 16, wn0 = (q & 1) * 16;
+    const int n = a.n, ne = a.ne;
+    const int64_t nn = (int64_t)n * n;
+    unsigned target = 0;
+    double* ctrl = a.ctrl;
+    double* trf = ctrl + 4;
+    double* devs = ctrl + 4 + 2 * (a.sp2_max + 2);
+    const int64_t gstride = (int64_t)gridDim.x * PF_THREADS, gid = (int64_t)blockIdx.x * PF_THREADS + tid;
+
+    // ---- |A|_F^2 -------------------------------------------------------------------------------------------------------------------
+    {
+        double s = 0.0;
+        for (int64_t i = gid; i < nn; i += gstride) { const double x = a.A[i]; s = fma(x, x, s); }
+        block_accumulate(s, 0.0, ctrl, nullptr);
+    }
+    pf_grid_barrier(a.bar, target);
+    // ---- X0 = A / |A|_F ------------------------------------------------------------------------------------------------------------
+    {
+        const double f = __ldcg(ctrl);
+        const double inv = f > 0.0 ? rsqrt(f) : 0.0;
+        double tr = 0.0, f2 = 0.0;
+        for (int64_t i = gid; i < nn; i += gstride) {
+            const double x = a.A[i] * inv;
+            a.X0[i] = x;
+            f2 = fma(x, x, f2);
+            if (i / n == i % n) tr += x;
+        }
+        block_accumulate(tr, f2, trf, trf + 1);
+    }
+    pf_grid_barrier(a.bar, target);
+
+    // ---- SP2 -----------------------------------------------------------------------------------------------------------------------
+    double* Xc = a.X0;
+    double* Xn = a.X1;
+    const int T = n / PF_T, lower = T * (T + 1) / 2;
+    int it = 0;
+    int extra = 0;
+    double tr0 = 0.0, f0 = 0.0;
+    for (; it < a.sp2_max; ++it) {
+        tr0 = __ldcg(trf + 2 * it);
+        f0 = __ldcg(trf + 2 * it + 1);
+        // a step squares the distance to {0, 1} of the eigenvalues on one side and doubles it on the other, so the defect tr(X - X^2) is
+        // dominated by the side that was just doubled: two more steps (one of each kind follows from the trace rule) finish both
+        const bool conv = fabs(tr0 - ne) < 1e-11 * ne && fabs(tr0 - f0) < 1e-11 * ne;
+        if (conv || extra) {
+            if (extra == 2) break;
+            ++extra;
+        }
+        const bool square = fabs(f0 - ne) < fabs(2.0 * tr0 - f0 - ne);
+        double tr = 0.0, f2 = 0.0;
+        for (int tile = blockIdx.x; tile < lower; tile += gridDim.x) {
+            int ti, tj;
+            pf_lower_tile(tile, ti, tj);
+            double acc[2][2][2];
+            const bool owner = pf_tile_nt(Xc, n, Xc, n, ti * PF_T, tj * PF_T, n, pf_smem, acc);
+            if (owner) {
+                const double w = (ti == tj) ? 1.0 : 2.0;
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int r = ti * PF_T + wm0 + i * 8 + g, c = tj * PF_T + wn0 + j * 8 + 2 * t + e;
+                            const double y = acc[i][j][e];
+                            const double xn = square ? y : fma(2.0, __ldcg(Xc + (int64_t)r * n + c), -y);
+                            Xn[(int64_t)r * n + c] = xn;
+                            if (ti != tj) Xn[(int64_t)c * n + r] = xn;
+                            f2 = fma(w * xn, xn, f2);
+                            if (r == c) tr += xn;
+                        }
+            }
+        }
+        block_accumulate(tr, f2, trf + 2 * (it + 1), trf + 2 * (it + 1) + 1);
+        pf_grid_barrier(a.bar, target);
+        double* s = Xc; Xc = Xn; Xn = s;
+    }
+    const int sp2_used = it;
+    tr0 = __ldcg(trf + 2 * it);
+    f0 = __ldcg(trf + 2 * it + 1);
+    // Xc = P.  kept weight sum A o P (no barrier needed before the Gram phase: different outputs)
+    {
+        double s = 0.0;
+        for (int64_t i = gid; i < nn; i += gstride) s = fma(a.A[i], __ldcg(Xc + i), s);
+        block_accumulate(s, 0.0, ctrl + 1, nullptr);
+    }
+
+    // ---- Newton-Schulz on U = P[:, :ne]  (V = U^T = P[:ne, :]) -----------------------------------------------------------------------
+    const double* U = Xc;  int64_t ldu = n;
+    const double* V = Xc;                                     // (ne x n), ld n
+    double* Un = a.Ua;  double* Vn = a.Va;
+    const int TG = ne / PF_T, lower_g = TG * (TG + 1) / 2, tiles_u = (n / PF_T) * TG;
+    int ns = 0;
+    double dev = 0.0;
+    for (;; ++ns) {
+        // G = V V^T (lower tiles + mirror), dev = max |G - I|
+        double dmax = 0.0;
+        for (int tile = blockIdx.x; tile < lower_g; tile += gridDim.x) {
+            int ti, tj;
+            pf_lower_tile(tile, ti, tj);
+            double acc[2][2][2];
+            const bool owner = pf_tile_nt(V, n, V, n, ti * PF_T, tj * PF_T, n, pf_smem, acc);
+            if (owner) {
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int r = ti * PF_T + wm0 + i * 8 + g, c = tj * PF_T + wn0 + j * 8 + 2 * t + e;
+                            const double gv = acc[i][j][e];
+                            a.G[(int64_t)r * ne + c] = gv;
+                            if (ti != tj) a.G[(int64_t)c * ne + r] = gv;
+                            dmax = fmax(dmax, fabs(gv - (r == c ? 1.0 : 0.0)));
+                        }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        if (lane == 0 && dmax > 0.0) pf_atomic_max(devs + ns, dmax);
+        pf_grid_barrier(a.bar, target);
+        dev = __ldcg(devs + ns);
+        if (dev < 1e-13 || ns >= a.ns_max) break;
+        // U' = ca U + cb U G   (G symmetric: rows of G are its columns), V' = U'^T
+        // the first steps use x -> 2x - x^3 (slope 2 at 0 instead of 1.5; values near 1 stay within [0.88, 1.09]): the smallest
+        // singular values of P[:, :ne] (1e-3 .. 1e-1 on the C2 chain) reach the quadratic region in half the steps
+        const bool steep = ns < PF_STEEP && dev > 0.5;
+        const double ca = steep ? 2.0 : 1.5, cb = steep ? -1.0 : -0.5;
+        for (int tile = blockIdx.x; tile < tiles_u; tile += gridDim.x) {
+            const int ti = tile / TG, tj = tile - ti * TG;
+            double acc[2][2][2];
+            const bool owner = pf_tile_nt(U, ldu, a.G, ne, ti * PF_T, tj * PF_T, ne, pf_smem, acc);
+            if (owner) {
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int r = ti * PF_T + wm0 + i * 8 + g, c = tj * PF_T + wn0 + j * 8 + 2 * t + e;
+                            const double un = fma(ca, __ldcg(U + (int64_t)r * ldu + c), cb * acc[i][j][e]);
+                            Un[(int64_t)r * ne + c] = un;
+                            Vn[(int64_t)c * n + r] = un;
+                        }
+            }
+        }
+        pf_grid_barrier(a.bar, target);
+        U = Un; ldu = ne; V = Vn;
+        Un = (Un == a.Ua) ? a.Ub : a.Ua;
+        Vn = (Vn == a.Va) ? a.Vb : a.Va;
+    }
+    // ---- results -------------------------------------------------------------------------------------------------------------------
+    for (int64_t i = gid; i < (int64_t)n * ne; i += gstride) {
+        const int64_t r = i / ne, c = i - r * ne;
+        a.Uout[i] = __ldcg(U + r * ldu + c);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        const double f = __ldcg(ctrl);
+        a.info[0] = tr0;
+        a.info[1] = f0;
+        a.info[2] = __ldcg(ctrl + 1);
+        a.info[3] = sqrt(f);
+        a.info[4] = dev;
+        a.info[5] = __ldcg(trf) * sqrt(f);
+        a.info[6] = tr0 - f0;
+        a.info[7] = (double)(sp2_used + 1000 * ns);
+    }
+}
+
+static size_t purify_fused_ws_doubles(int n, int ne, int sp2_max, int ns_max) {
+    return (size_t)2 * n * n + (size_t)4 * n * ne + (size_t)ne * ne + 4 + 2 * (sp2_max + 2) + (ns_max + 2) + 64;
+}
+
+static bool purify_fused_fits(int n, int ne) { return n % PF_BK == 0 && ne % PF_BK == 0 && n >= 128 && ne >= 64 && ne < n; }
+
+int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, double* ws, size_t ws_bytes, double* info,
+                                cudaStream_t st) {
+    SYN_REQUIRE(A && U && ws && info, "syn_dominant_subspace_f64: null argument");
+    SYN_REQUIRE(purify_fused_fits(n, ne), "syn_dominant_subspace_f64 (fused): n and ne must be multiples of 64 (n=%d ne=%d)", n, ne);
+    SYN_REQUIRE(sp2_max >= 1 && sp2_max <= 400 && ns_max >= 0 && ns_max <= 400, "syn_dominant_subspace_f64: bad iteration limits");
+    SYN_REQUIRE(ws_bytes >= purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double), "syn_dominant_subspace_f64: workspace too small");
+    SYN_REQUIRE(((((uintptr_t)ws) | ((uintptr_t)A)) & 15) == 0, "syn_dominant_subspace_f64: A and the workspace must be 16-byte aligned");
+    auto kern = purify_fused_kernel;
+    static bool configured = false;
+    static int max_ctas = 0;
+    if (!configured) {
+        SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
+        int per_sm = 0;
+        SYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_THREADS, PF_SMEM));
+        max_ctas = per_sm * sm_count();
+        configured = true;
+    }
+    SYN_REQUIRE(max_ctas >= 1, "syn_dominant_subspace_f64: the fused kernel does not fit this device");
+    const int64_t nn = (int64_t)n * n, nk = (int64_t)n * ne;
+    PurifyArgs a;
+    a.A = A;
+    a.X0 = ws; a.X1 = a.X0 + nn;
+    a.Ua = a.X1 + nn; a.Ub = a.Ua + nk; a.Va = a.Ub + nk; a.Vb = a.Va + nk;
+    a.G = a.Vb + nk;
+    a.ctrl = a.G + (int64_t)ne * ne;
+    const size_t ctrl_doubles = 4 + 2 * (sp2_max + 2) + (ns_max + 2);
+    a.bar = reinterpret_cast<unsigned*>(a.ctrl + ctrl_doubles);
+    a.Uout = U; a.info = info;
+    a.n = n; a.ne = ne; a.sp2_max = sp2_max; a.ns_max = ns_max;
+    SYN_CUDA(cudaMemsetAsync(a.ctrl, 0, sizeof(double) * (ctrl_doubles + 2), st));
+    const int T = n / PF_T, lower = T * (T + 1) / 2;
+    int grid = lower < max_ctas ? lower : max_ctas;
+    void* args[] = {&a};
+    SYN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(PF_THREADS), args, PF_SMEM, st));
+    note_launch();
+    return 0;
+}
+
 }  // namespace syn
 
 extern "C" size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_iters) {
     if (n < 2 || ne < 1 || sp2_iters < 1) return 0;
     return syn::purify_ws_doubles(n, ne, sp2_iters) * sizeof(double);
+}
+
+extern "C" size_t syn_dominant_subspace_fused_workspace_f64(int n, int ne, int sp2_max, int ns_max) {
+    if (n < 2 || ne < 1 || sp2_max < 1 || ns_max < 0) return 0;
+    return syn::purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double);
+}
+
+extern "C" int syn_dominant_subspace_fused_fits(int n, int ne) { return syn::purify_fused_fits(n, ne) ? 1 : 0; }
+
+extern "C" int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
+                                               double* info, void* stream) {
+    return syn::dominant_subspace_fused_f64(A, n, ne, sp2_max, ns_max, U, (double*)ws, ws_bytes, info, (cudaStream_t)stream);
 }
 
 extern "C" int syn_dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_iters, double* U, void* ws, size_t ws_bytes,

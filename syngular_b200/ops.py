@@ -205,15 +205,29 @@ lib.syn_dominant_subspace_workspace_f64.restype = ctypes.c_size_t
 lib.syn_dominant_subspace_workspace_f64.argtypes = [_i32, _i32, _i32]
 
 
-def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20):
+lib.syn_dominant_subspace_fused_workspace_f64.restype = ctypes.c_size_t
+lib.syn_dominant_subspace_fused_workspace_f64.argtypes = [_i32, _i32, _i32, _i32]
+PURIFY_FUSED = os.environ.get("SYN_PURIFY_FUSED", "1") != "0"        # experiment knob: 0 = the multi-launch sequence only
+
+
+def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160, ns_max=80):
     """Orthonormal basis U (n x ne) of the span of the `ne` dominant eigenvectors of the symmetric PSD matrix A (n x n contiguous,
-    not modified) by SP2 spectral projection + Newton-Schulz (csrc/purify.cu): GEMM-bound, one fixed sequence of launches.
+    not modified) by SP2 spectral projection + Newton-Schulz (csrc/purify.cu): GEMM-bound, no host round trip.
+    fused (default when n, ne are multiples of 64): one persistent cooperative kernel, iteration counts adapt on the device (at most
+    sp2_max / ns_max); otherwise a fixed sequence of sp2_iters / ns_iters launches.
     Returns (U, info) with info a DEVICE vector of 8 doubles (see syngular_b200.h); nothing is synchronised here."""
     require_cuda_f64(A)
     n = A.shape[0]
     assert A.dim() == 2 and A.shape[1] == n and A.is_contiguous()
     U = torch.empty((n, int(ne)), dtype=torch.float64, device=A.device)
     info = torch.zeros((8,), dtype=torch.float64, device=A.device)
+    if fused is None:
+        fused = PURIFY_FUSED
+    if fused and lib.syn_dominant_subspace_fused_fits(_i32(n), _i32(int(ne))):
+        ws = workspace(lib.syn_dominant_subspace_fused_workspace_f64(n, int(ne), int(sp2_max), int(ns_max)), A.device, tag="purify_fused")
+        check(lib.syn_dominant_subspace_fused_f64(ptr(A), _i32(n), _i32(int(ne)), _i32(int(sp2_max)), _i32(int(ns_max)), ptr(U), ptr(ws),
+                                                  _sz(ws.numel() * 8), ptr(info), stream_ptr()), "syn_dominant_subspace_fused_f64")
+        return U, info
     ws = workspace(lib.syn_dominant_subspace_workspace_f64(n, int(ne), int(sp2_iters)), A.device, tag="purify")
     check(lib.syn_dominant_subspace_f64(ptr(A), _i32(n), _i32(int(ne)), _i32(int(sp2_iters)), _i32(int(ns_iters)), ptr(U), ptr(ws),
                                         _sz(ws.numel() * 8), ptr(info), stream_ptr()), "syn_dominant_subspace_f64")

@@ -140,7 +140,7 @@ def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shi
             torch.tensor([disc, sv[0]], dtype=F64))
 
 
-def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20):
+def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160, ns_max=80):
     """csrc/purify.cu restated: SP2 from A / |A|_F with the trace-steered branch, then Newton-Schulz on P[:, :ne]."""
     a = A.numpy()
     n = a.shape[0]

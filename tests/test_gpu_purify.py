@@ -15,12 +15,14 @@ def _psd(rng, n, decay):
     return (q * lam) @ q.T, q, lam
 
 
-@pytest.mark.parametrize("n,ne,decay", [(64, 32, 6.0), (256, 128, 10.0), (512, 256, 12.0), (512, 100, 8.0), (384, 256, 9.0)])
-def test_dominant_subspace_matches_eigh(n, ne, decay):
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("n,ne,decay", [(64, 32, 6.0), (256, 128, 10.0), (512, 256, 12.0), (512, 100, 8.0), (384, 256, 9.0), (512, 192, 20.0),
+                                        (1024, 512, 14.0), (128, 64, 3.0)])
+def test_dominant_subspace_matches_eigh(n, ne, decay, fused):
     from syngular_b200 import ops
     rng = np.random.default_rng(n + ne)
     A, q, lam = _psd(rng, n, decay)
-    U, info = ops.dominant_subspace(torch.from_numpy(A).cuda(), ne, sp2_iters=48, ns_iters=30)
+    U, info = ops.dominant_subspace(torch.from_numpy(A).cuda(), ne, sp2_iters=56, ns_iters=30, fused=fused)
     h = info.cpu().numpy()
     Un = U.cpu().numpy()
     assert abs(h[0] - ne) < 1e-9 * ne and abs(h[1] - ne) < 1e-9 * ne, h
@@ -37,9 +39,10 @@ def test_no_gap_is_reported_not_hidden():
     rng = np.random.default_rng(1)
     B = rng.normal(size=(128, 40))
     A = B @ B.T
-    U, info = ops.dominant_subspace(torch.from_numpy(A).cuda(), 64, sp2_iters=44, ns_iters=22)
-    h = info.cpu().numpy()
-    assert not (abs(h[0] - 64) < 1e-9 * 64 and abs(h[1] - 64) < 1e-9 * 64 and h[4] < 1e-12)
+    for fused in (False, True):
+        U, info = ops.dominant_subspace(torch.from_numpy(A).cuda(), 64, sp2_iters=44, ns_iters=22, fused=fused, sp2_max=60, ns_max=30)
+        h = info.cpu().numpy()
+        assert not (abs(h[0] - 64) < 1e-9 * 64 and abs(h[1] - 64) < 1e-9 * 64 and h[4] < 1e-12)
 
 
 @pytest.mark.parametrize("n,chi,chiw", [(14, 16, 4), (16, 32, 8)])

@@ -38,11 +38,16 @@ for idx in (7, 8, 9, 20, 32, 50, 55, 56, 57):
     lam = torch.linalg.eigvalsh(A).flip(0)
     gap = ((lam[ne - 1] - lam[ne]) / lam[0]).item() if ne < n else float("nan")
     line = "site %2d n=%4d lam[ne]/lam0 %.1e gap/lam0 %.1e |" % (idx, n, (lam[ne - 1] / lam[0]).item(), gap)
-    for sp2, ns in ((36, 18), (44, 22), (52, 26), (64, 30), (80, 30)):
-        U, info = ops.dominant_subspace(A, ne, sp2, ns)
+    for sp2, ns in ((52, 26),):
+        U, info = ops.dominant_subspace(A, ne, sp2, ns, fused=False)
         h = info.cpu().numpy()
-        ms = time_it(lambda: ops.dominant_subspace(A, ne, sp2, ns))
+        ms = time_it(lambda: ops.dominant_subspace(A, ne, sp2, ns, fused=False))
         line += " [%d/%d: %.3f ms tr-ne %.1e idem %.1e dev %.1e]" % (sp2, ns, ms, h[0] - ne, h[6], h[4])
+    Uf, info = ops.dominant_subspace(A, ne, fused=True)
+    h = info.cpu().numpy()
+    ms = time_it(lambda: ops.dominant_subspace(A, ne, fused=True))
+    pdiff = (Uf @ Uf.t() - U @ U.t()).abs().max().item()
+    line += " [FUSED: %.3f ms iters %d tr-ne %.1e idem %.1e dev %.1e |P-P_unfused| %.1e]" % (ms, int(h[7]), h[0] - ne, h[6], h[4], pdiff)
     work = A.clone()
     def jac():
         work.copy_(A)
@@ -54,4 +59,4 @@ for idx in (7, 8, 9, 20, 32, 50, 55, 56, 57):
 # phases of one call at n = 512
 A = captured[32]
 for sp2, ns in ((44, 0), (1, 22), (1, 0)):
-    print("n=512 sp2=%d ns=%d: %.3f ms" % (sp2, ns, time_it(lambda: ops.dominant_subspace(A, 256, sp2, ns))))
+    print("n=512 sp2=%d ns=%d: %.3f ms" % (sp2, ns, time_it(lambda: ops.dominant_subspace(A, 256, sp2, ns, fused=False))))
