@@ -442,7 +442,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rounding": "SVD truncation by the density-matrix algorithm (Gram environments + one-sided Jacobi)",
+            "config": {"workload": WORKLOAD, "rounding": "SVD truncation by the density-matrix algorithm (Gram environments; dominant eigenspace of every bond by the fused SP2 spectral-projection kernel, one-sided Jacobi below 256 or without a gap)",
                        "l2": "inputs larger than L2: 63 right environments of up to 134 MB (8.5 GB) are streamed every sweep",
                        "multi_gpu": "replicas only: one independent chain per rank, no collective on the data path",
                        "left_gram_err_site20": gram_err},

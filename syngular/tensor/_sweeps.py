@@ -625,6 +625,7 @@ PURIFY_NS_ITERS = 26
 PURIFY_SP2_MAX = 90            # fused kernel: upper limits (it stops by itself); 90 steps resolve gaps down to ~1e-12 |A|
 PURIFY_NS_MAX = 60
 PURIFY_STATS = {"taken": 0, "fallback": 0}
+IDENTITY_WHEN_FULL = True      # bonds that keep their whole space skip the eigen-solve (gauge: identity core)
 
 
 def dominant_subspace(A, chi_max):
@@ -664,6 +665,14 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
         # structural rank of the bond: when it is below chi_max nothing is truncated and the kept space is the range of A -- the
         # projection solver then finds it at the (huge) gap between the last non-zero eigenvalue and the null space
         ne = min(chi_max, D, right_dim[k + 1])
+        if IDENTITY_WHEN_FULL and cutoff == 0.0 and ne >= nA:
+            # nothing to truncate and (structurally) nothing rank-deficient: every orthonormal basis of the whole space is a valid gauge,
+            # so the core is the identity and the unfolding itself is carried -- no eigen-solve (ramp-up sites of a chain)
+            eye = torch.eye(nA, dtype=F64, device=A.device)
+            trunc.sigma.append(LazySpectrum(A, eye)); trunc.keep.append(nA); trunc.discarded.append(0.0)
+            out.append(eye.reshape(s, o, nA))
+            T = _carry_from(eye, M2, nA, b, r, transposed_basis=False)        # = M2 with its columns re-ordered to (r, b)
+            continue
         if PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
             got = dominant_subspace(A, ne)
             if got is not None:
