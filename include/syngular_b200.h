@@ -155,6 +155,15 @@ int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
                                     double* info, void* stream);
 
+/* ---- fused W-sandwich of the right-environment update (density-matrix rounding) -------------------------------------------------
+ * Z[a, l, (l',i'), b'] = sum_{(o,r')} W[l',i',o,r'] ( sum_{(i,r)} W[l,i,o,r] P1[a, (i,r), (r',b')] ):  the two small-K contractions
+ * with the MPO core W (l,i,o,r) on either side of the large intermediate in ONE kernel, the intermediate staying in shared memory
+ * (two np.tensordot calls in the restated oracle, oracle/svd_numpy.py:107-110; the reference's unfinished counterpart is MPO:193-260).
+ * P1 (a, i*r, r, b), Z (a, l, l*i, b) contiguous.  Covered shapes: (l,i,o,r) = (16,2,2,16), b % 16 == 0 (syn_env_sandwich_fits);
+ * anything else takes two syn_gemm_f64 calls. */
+int syn_env_sandwich_fits(int l, int i, int o, int r, int b);
+int syn_env_sandwich_f64(const double* P1, const double* W, double* Z, int na, int l, int i, int o, int r, int b, void* stream);
+
 /* ---- block assembly and elementwise kernels ---------------------------------------------------------------- */
 /* `A + B` site: direct sum of the bond spaces, self's block first; cores as (l, phys, r) with the physical legs flattened
  * (np.block / scipy.linalg.block_diag loops of MPS:82-96 and MPO:90-106). */

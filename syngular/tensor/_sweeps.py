@@ -517,7 +517,7 @@ def round_svd(sites, chi_max, cutoff=0.0, canonicalize=True):
 
 def right_environments(X, W):
     """E[k] = Gram matrix of the product chain to the right of bond k (D_k x D_k), k = 1..n-1, without forming product cores:
-    four strided GEMMs per site (finished form of MPO:193-260).
+    two large strided GEMMs around the fused W-sandwich kernel per site (finished form of MPO:193-260).
     Storage: rows indexed (b, r) MPS-bond major, COLUMNS indexed (r', b') MPO-bond major -- so that the last GEMM of every
     site writes unit-stride rows (its batch index l' becomes the outer column index) and every consumer reads unit strides."""
     n = len(X)
@@ -531,20 +531,31 @@ def right_environments(X, W):
         # P1[(a,i),(r,y)] = sum_b X[(a,i),b] E[b,(r,y)]                       y = (r', b')
         P1 = empty(a, i, r, D)
         ops.gemm(Xk, En, P1, M=a * i, N=r * D, K=b, a_m=b, a_k=1, b_k=r * D, b_n=1, c_m=r * D, c_n=1)
-        # P2[a,(l,o),y] = sum_{(i,r)} W[l,i,o,r] P1[a,(i,r),y]                batch over a
-        P2 = empty(a, l, o, D)
-        ops.gemm(Wk, P1, P2, M=l * o, N=D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=1, c_m=D, c_n=1,
-                 batch=a, a_b=0, b_b=i * r * D, c_b=l * o * D)
-        # Z[(a,l), l', i', b'] = sum_{(o,r')} P2[(a,l), o, (r',b')] W[l', i', o, r']  batch over (a,l)
-        Z = empty(a * l, l, i, b)
-        ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=1, a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
-                 batch=a * l, a_b=o * D, b_b=0, c_b=l * i * b)
+        if ops.env_sandwich_fits(l, i, o, r, b) and Wk.is_contiguous():
+            # both W contractions in one kernel, the (a, l, o, D) intermediate never reaches HBM (csrc/env.cu)
+            Z = empty(a * l, l, i, b)
+            ops.env_sandwich(P1, Wk, Z, a, b)
+        else:
+            Z = _w_sandwich_gemms(P1, Wk, a, i, b, l, o, r, D)
         # E[(a,l),(l',a')] = sum_{(i',b')} Z[(a,l), l', (i',b')] X[a',(i',b')]        batch over l'
         Ek = empty(a * l, l * a)
         ops.gemm(Z, Xk, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
                  batch=l, a_b=i * b, b_b=0, c_b=a)
         E[k] = Ek
     return E
+
+
+def _w_sandwich_gemms(P1, Wk, a, i, b, l, o, r, D):
+    """The two W contractions of the environment update as two strided GEMMs (shapes the fused kernel does not cover)."""
+    # P2[a,(l,o),y] = sum_{(i,r)} W[l,i,o,r] P1[a,(i,r),y]                batch over a
+    P2 = empty(a, l, o, D)
+    ops.gemm(Wk, P1, P2, M=l * o, N=D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=1, c_m=D, c_n=1,
+             batch=a, a_b=0, b_b=i * r * D, c_b=l * o * D)
+    # Z[(a,l), l', i', b'] = sum_{(o,r')} P2[(a,l), o, (r',b')] W[l', i', o, r']  batch over (a,l)
+    Z = empty(a * l, l, i, b)
+    ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=1, a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
+             batch=a * l, a_b=o * D, b_b=0, c_b=l * i * b)
+    return Z
 
 
 _ONES = {}

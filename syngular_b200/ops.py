@@ -234,6 +234,23 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return U, info
 
 
+ENV_FUSED = os.environ.get("SYN_ENV_FUSED", "1") != "0"              # experiment knob: 0 = two GEMM launches
+
+
+def env_sandwich_fits(l, i, o, r, b):
+    return ENV_FUSED and bool(lib.syn_env_sandwich_fits(_i32(l), _i32(i), _i32(o), _i32(r), _i32(b)))
+
+
+def env_sandwich(P1, W, Z, na, b):
+    """Z[a,l,(l',i'),b'] = sum W[l',i',o,r'] W[l,i,o,r] P1[a,(i,r),(r',b')] in one kernel (csrc/env.cu); all operands contiguous."""
+    require_cuda_f64(P1, W, Z)
+    assert P1.is_contiguous() and W.is_contiguous() and Z.is_contiguous()
+    l, i, o, r = W.shape
+    check(lib.syn_env_sandwich_f64(ptr(P1), ptr(W), ptr(Z), _i32(int(na)), _i32(l), _i32(i), _i32(o), _i32(r), _i32(int(b)), stream_ptr()),
+          "syn_env_sandwich_f64")
+    return Z
+
+
 def add_site(A, B, first, last):
     """Block assembly of `A + B` for one site (MPS:82-96, MPO:90-106).  Cores contiguous, physical legs flattened by the kernel."""
     require_cuda_f64(A, B)

@@ -162,6 +162,20 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(info)
 
 
+def env_sandwich_fits(l, i, o, r, b):
+    return (l, i, o, r) == (16, 2, 2, 16) and b % 16 == 0
+
+
+def env_sandwich(P1, W, Z, na, b):
+    w = W.numpy()
+    l, i, o, r = w.shape
+    p1 = P1.numpy().reshape(na, i, r, r, b)                        # [a][i][r][r'][b']
+    p2 = np.einsum("lior,airqb->aloqb", w, p1)                     # [a][l][o][r'][b']
+    z = np.einsum("aloqb,mjoq->almjb", p2, w)                      # [a][l][l'][i'][b']
+    Z.copy_(torch.from_numpy(np.ascontiguousarray(z)).reshape(Z.shape))
+    return Z
+
+
 def identity_deviation(X):
     x = X.numpy()
     return torch.tensor([float(np.max(np.abs(x - np.eye(x.shape[0]))))], dtype=F64)
@@ -198,7 +212,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "env_sandwich_fits", "env_sandwich", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

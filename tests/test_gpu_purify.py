@@ -75,3 +75,25 @@ def test_sweep_with_projection_solver_matches_oracle(n, chi, chiw):
         assert keep[k] == kk
         assert np.max(np.abs(sig[k][:kk] - spectra[k][:kk])) < 1e-10 * spectra[k][0]
         assert abs(disc[k] - discarded[k]) < 1e-10 * spectra[k][0] ** 2 * len(spectra[k])
+
+
+@pytest.mark.parametrize("na,b", [(3, 16), (20, 64), (256, 256)])
+def test_env_sandwich_matches_two_gemms(na, b):
+    """csrc/env.cu against the two strided GEMMs it replaces and against numpy (einsum of the restated oracle)."""
+    from syngular.tensor import _sweeps as sw
+    from syngular_b200 import ops
+    rng = np.random.default_rng(na + b)
+    l, i, o, r = 16, 2, 2, 16
+    D = r * b
+    P1 = torch.from_numpy(rng.normal(size=(na, i, r, D))).cuda()
+    W = torch.from_numpy(rng.normal(size=(l, i, o, r))).cuda()
+    assert ops.env_sandwich_fits(l, i, o, r, b)
+    Z = torch.empty((na * l, l, i, b), dtype=torch.float64, device="cuda")
+    ops.env_sandwich(P1, W, Z, na, b)
+    Zg = sw._w_sandwich_gemms(P1, W, na, i, b, l, o, r, D)
+    scale = Zg.abs().max().item()
+    assert (Z - Zg).abs().max().item() < 1e-12 * scale
+    if na <= 20:
+        w, p1 = W.cpu().numpy(), P1.cpu().numpy().reshape(na, i, r, r, b)
+        ref = np.einsum("aloqb,mjoq->almjb", np.einsum("lior,airqb->aloqb", w, p1), w).reshape(na * l, l, i, b)
+        assert np.max(np.abs(Z.cpu().numpy() - ref)) < 1e-12 * scale
