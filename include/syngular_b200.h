@@ -161,6 +161,9 @@ int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max,
  * (two np.tensordot calls in the restated oracle, oracle/svd_numpy.py:107-110; the reference's unfinished counterpart is MPO:193-260).
  * P1 (a, i*r, r, b), Z (a, l, l*i, b) contiguous.  Covered shapes: (l,i,o,r) = (16,2,2,16), b % 16 == 0 (syn_env_sandwich_fits);
  * anything else takes two syn_gemm_f64 calls. */
+/* E[(a,l),(l',a')] (na*L x L*na, contiguous) is symmetric under (a,l) <-> (a',l'): fill the blocks with a' in a LATER block of `ab`
+ * values than a from their mirror images (the last GEMM of the environment update then only forms the block-lower part). */
+int syn_env_mirror_f64(double* E, int na, int L, int ab, void* stream);
 int syn_env_sandwich_fits(int l, int i, int o, int r, int b);
 int syn_env_sandwich_f64(const double* P1, const double* W, double* Z, int na, int l, int i, int o, int r, int b, void* stream);
 

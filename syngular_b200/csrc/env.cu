@@ -140,7 +140,40 @@ int env_sandwich_f64(const double* P1, const double* W, double* Z, int na, int l
     return launch_status("env_sandwich_kernel");
 }
 
+// The environment E[(a,l),(l',a')] is symmetric under (a,l) <-> (a',l').  Its last GEMM only forms the block-lower part (a' in the
+// same or an earlier block of `ab` values than a); this kernel fills the strictly upper blocks: for every pair (l, l') the 32 x 32
+// tile (a, a') of plane (l, l') is the transpose of tile (a', a) of plane (l', l) -- read and written along contiguous a through
+// shared memory.
+__global__ void __launch_bounds__(256) env_mirror_kernel(double* __restrict__ E, int na, int L, int ab) {
+    __shared__ double tile[32][33];
+    const int ja = blockIdx.x, ia = blockIdx.y;
+    if ((ja * 32) / ab <= (ia * 32) / ab) return;
+    const int l = blockIdx.z / L, lp = blockIdx.z - l * L;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t row = (int64_t)L * na;
+    for (int r = ty; r < 32; r += 8) {
+        const int as = ja * 32 + r, ac = ia * 32 + tx;             // source element (a'' = as, l') x (l, a = ac)
+        tile[r][tx] = E[((int64_t)as * L + lp) * row + (int64_t)l * na + ac];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int a = ia * 32 + r, ap = ja * 32 + tx;
+        E[((int64_t)a * L + l) * row + (int64_t)lp * na + ap] = tile[tx][r];
+    }
+}
+
+int env_mirror_f64(double* E, int na, int L, int ab, cudaStream_t st) {
+    SYN_REQUIRE(E && na >= 32 && na % 32 == 0 && L >= 1 && ab >= 32 && ab % 32 == 0 && na % ab == 0,
+                "syn_env_mirror_f64: na=%d must be a multiple of the block ab=%d, both multiples of 32", na, ab);
+    SYN_REQUIRE((int64_t)L * L <= 65535, "syn_env_mirror_f64: MPO bond too large");
+    dim3 grid(na / 32, na / 32, L * L);
+    env_mirror_kernel<<<grid, 256, 0, st>>>(E, na, L, ab);
+    return launch_status("env_mirror_kernel");
+}
+
 }  // namespace syn
+
+extern "C" int syn_env_mirror_f64(double* E, int na, int L, int ab, void* stream) { return syn::env_mirror_f64(E, na, L, ab, (cudaStream_t)stream); }
 
 extern "C" int syn_env_sandwich_fits(int l, int i, int o, int r, int b) {
     return (l == syn::EV_L && r == syn::EV_R && i == 2 && o == 2 && b >= syn::EV_TB && b % syn::EV_TB == 0) ? 1 : 0;

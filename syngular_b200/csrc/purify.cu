@@ -257,7 +257,7 @@ int dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_
 // Convergence is decided INSIDE the kernel from the accumulated scalars (every CTA reads the same values after the barrier), so the
 // iteration counts adapt to the spectrum with no host round trip: SP2 stops two steps after tr(X - X^2) < 1e-11 ne, Newton-Schulz when
 // max |U^T U - I| < 1e-13.  While the smallest singular value of U is still far from 1 the steeper map 2x - x^3 replaces 1.5x - 0.5x^3.
-constexpr int PF_THREADS = 256, PF_BK = 64, PF_STAGES = 3, PF_LD = PF_BK + 4, PF_T = 32, PF_STEEP = 6;
+constexpr int PF_THREADS = 256, PF_BK = 64, PF_STAGES = 3, PF_LD = PF_BK + 4, PF_T = 32, PF_STEEP = 8;
 constexpr size_t PF_SMEM = (size_t)PF_STAGES * 2 * PF_T * PF_LD * sizeof(double);
 
 struct PurifyArgs {
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     double* Un = a.Ua;  double* Vn = a.Va;
     const int TG = ne / PF_T, lower_g = TG * (TG + 1) / 2, tiles_u = (n / PF_T) * TG;
     int ns = 0;
-    double dev = 0.0;
+    double dev = 0.0, dev0 = 0.0;
     for (;; ++ns) {
         // G = V V^T (lower tiles + mirror), dev = max |G - I|
         double dmax = 0.0;
@@ -506,11 +506,12 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
         if (lane == 0 && dmax > 0.0) pf_atomic_max(devs + ns, dmax);
         pf_grid_barrier(a.bar, target);
         dev = __ldcg(devs + ns);
+        if (ns == 0) dev0 = dev;      // max |1 - |P e_i||^2|: close to 1 unless the leading coordinates already span the subspace
         if (dev < 1e-13 || ns >= a.ns_max) break;
         // U' = ca U + cb U G   (G symmetric: rows of G are its columns), V' = U'^T
         // the first steps use x -> 2x - x^3 (slope 2 at 0 instead of 1.5; values near 1 stay within [0.88, 1.09]): the smallest
         // singular values of P[:, :ne] (1e-3 .. 1e-1 on the C2 chain) reach the quadratic region in half the steps
-        const bool steep = ns < PF_STEEP && dev > 0.5;
+        const bool steep = ns < PF_STEEP && dev0 > 0.5;
         const double ca = steep ? 2.0 : 1.5, cb = steep ? -1.0 : -0.5;
         for (int tile = blockIdx.x; tile < tiles_u; tile += gridDim.x) {
             const int ti = tile / TG, tj = tile - ti * TG;

@@ -251,6 +251,14 @@ def env_sandwich(P1, W, Z, na, b):
     return Z
 
 
+def env_mirror(E, na, L, ab):
+    """Fill the strictly upper a-blocks of the symmetric environment E[(a,l),(l',a')] from the lower ones (csrc/env.cu), in place."""
+    require_cuda_f64(E)
+    assert E.is_contiguous()
+    check(lib.syn_env_mirror_f64(ptr(E), _i32(int(na)), _i32(int(L)), _i32(int(ab)), stream_ptr()), "syn_env_mirror_f64")
+    return E
+
+
 def add_site(A, B, first, last):
     """Block assembly of `A + B` for one site (MPS:82-96, MPO:90-106).  Cores contiguous, physical legs flattened by the kernel."""
     require_cuda_f64(A, B)

@@ -176,6 +176,16 @@ def env_sandwich(P1, W, Z, na, b):
     return Z
 
 
+def env_mirror(E, na, L, ab):
+    e = E.numpy().reshape(na, L, L, na)                            # [a][l][l'][a']
+    blk = np.arange(na) // ab
+    upper = blk[None, :] > blk[:, None]                            # [a][a']: a' in a later block
+    src = e.transpose(3, 2, 1, 0)                                  # src[a][l][l'][a'] = e[a'][l'][l][a]
+    mask = np.broadcast_to(upper[:, None, None, :], e.shape)
+    e[mask] = src[mask]
+    return E
+
+
 def identity_deviation(X):
     x = X.numpy()
     return torch.tensor([float(np.max(np.abs(x - np.eye(x.shape[0]))))], dtype=F64)
@@ -212,7 +222,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "env_sandwich_fits", "env_sandwich", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "env_sandwich_fits", "env_sandwich", "env_mirror", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

@@ -97,3 +97,22 @@ def test_env_sandwich_matches_two_gemms(na, b):
         w, p1 = W.cpu().numpy(), P1.cpu().numpy().reshape(na, i, r, r, b)
         ref = np.einsum("aloqb,mjoq->almjb", np.einsum("lior,airqb->aloqb", w, p1), w).reshape(na * l, l, i, b)
         assert np.max(np.abs(Z.cpu().numpy() - ref)) < 1e-12 * scale
+
+
+def test_symmetric_environment_build_matches_full_gemm():
+    """Block-lower GEMMs + env_mirror against the full last GEMM of the environment update, on a chain whose plateau triggers it."""
+    import bench
+    from syngular.tensor import _sweeps as sw
+    X, W = bench.make_chain(9, n=16, chi=128, chiw=4)
+    Xd, Wd = [sw.as_core(c) for c in X], [sw.as_core(c) for c in W]
+    saved = sw.ENV_SYMMETRIC_BLOCK
+    try:
+        sw.ENV_SYMMETRIC_BLOCK = 32
+        E1 = sw.right_environments(Xd, Wd)
+        sw.ENV_SYMMETRIC_BLOCK = 0
+        E0 = sw.right_environments(Xd, Wd)
+    finally:
+        sw.ENV_SYMMETRIC_BLOCK = saved
+    assert any(e.shape[0] >= 512 for e in E1[1:-1])
+    for a, b in zip(E1[1:-1], E0[1:-1]):
+        assert (a - b).abs().max().item() <= 1e-12 * b.abs().max().item()
