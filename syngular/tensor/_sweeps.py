@@ -458,7 +458,8 @@ class Truncation:
 
     def host(self):
         sig = [s.get() if isinstance(s, LazySpectrum) else s for s in self.sigma]
-        return ([s.detach().cpu().numpy() for s in sig], list(self.keep), [float(d) for d in self.discarded])
+        # None: the bond was cut by the spectral-projection solver on a complex unfolding (no spectrum is formed there)
+        return ([np.zeros(0) if s is None else s.detach().cpu().numpy() for s in sig], list(self.keep), [float(d) for d in self.discarded])
 
 
 def _svd_basis(M, chi_max, cutoff, trunc):

@@ -11,10 +11,12 @@ complex operations onto the same kernels:
     Householder QR of that matrix is the embedding of the complex QR, so the even columns of its Q are the complex basis;
   * the bond SVD diagonalises the embedded Hermitian Gram matrix (2m x 2m real symmetric, every eigenvalue doubled) with the
     Jacobi kernel; one vector per pair is kept and the result is polished by Newton-Schulz steps (complex GEMMs), which also
-    repairs the pairing when singular values are degenerate (Bell / GHZ states).
+    repairs the pairing when singular values are degenerate (Bell / GHZ states).  Large bonds (embedded size >= 256) with a gap at the
+    cut use the fused spectral-projection kernel on the interleaved embedding instead: its projector is an embedding by construction,
+    so the complex basis is read off directly and the Jacobi size limit does not apply.
 
 No arithmetic happens on the host or in PyTorch: torch is used for allocation, views, concatenation / interleaving copies and
-the host read-back of kept ranks.  Limits: embedded problems must fit the Jacobi kernel (2 * rows <= 1024)."""
+the host read-back of kept ranks.  Limit of the Jacobi route: embedded problems must fit the kernel (2 * rows <= 1024)."""
 import torch
 
 from . import ops
@@ -23,6 +25,9 @@ from ._lib import SynError
 F64 = torch.float64
 C128 = torch.complex128
 JACOBI_MAX_N = 1024
+PURIFY_MIN_N = 256             # embedded bond problems at least this large try the spectral-projection solver first (0 = off)
+PURIFY_SP2_MAX = 90
+PURIFY_NS_MAX = 60
 
 
 class Cx:
@@ -257,9 +262,21 @@ def svd_basis(M, chi_max, cutoff, eigh, rank_tol=3.2e-7):
     returns (U (m x keep) planar with orthonormal columns, keep, sigma (device, m values, descending), discarded weight).
     `eigh(S, chi, cutoff, rank_tol)` is the real symmetric eigen-solver (syngular.tensor._sweeps.eigh_gram)."""
     m, c = M.shape
-    if 2 * m > JACOBI_MAX_N:
-        raise NotImplementedError("complex bond SVD needs 2 * rows <= %d (got rows = %d)" % (JACOBI_MAX_N, m))
     H = matmul(M, M.h())                                         # Hermitian Gram matrix (squared singular values)
+    target = min(int(chi_max), m, c)
+    if PURIFY_MIN_N and 2 * m >= PURIFY_MIN_N and cutoff == 0.0 and target < m and ops.dominant_subspace_fused_fits(2 * m, 2 * target):
+        # Spectral projection on the INTERLEAVED embedding: the projector is a polynomial of the embedded matrix, hence itself an
+        # embedding, and its first 2*target columns are the pairs (P e_j, J P e_j) -- Newton-Schulz keeps that structure, so the even
+        # columns of the orthonormalised basis are the complex basis (no pairing problem, no size limit from the Jacobi kernel).
+        V, info = ops.dominant_subspace(embed(H), 2 * target, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
+        h = info.cpu()
+        tr, f2, kept_w, dev, tr_a, idem = (float(h[k]) for k in (0, 1, 2, 4, 5, 6))
+        if (abs(tr - 2 * target) < 2e-9 * target and abs(f2 - 2 * target) < 2e-9 * target and abs(idem) < 2e-11 * target and dev < 1e-12
+                and bool(torch.isfinite(h).all())):
+            U = polish_columns(unembed_columns(V, m, target))
+            return U, target, None, torch.tensor(max(0.5 * (tr_a - kept_w), 0.0), dtype=F64)
+    if 2 * m > JACOBI_MAX_N:
+        raise NotImplementedError("complex bond SVD without a spectral gap at the cut needs 2 * rows <= %d (got rows = %d)" % (JACOBI_MAX_N, m))
     S = _hermitian_embedding(H)
     Ut, sigma2, info, winfo = eigh(S, 2 * int(chi_max), cutoff, rank_tol)
     keep = max(1, int(info[0].item()) // 2)

@@ -210,6 +210,10 @@ lib.syn_dominant_subspace_fused_workspace_f64.argtypes = [_i32, _i32, _i32, _i32
 PURIFY_FUSED = os.environ.get("SYN_PURIFY_FUSED", "1") != "0"        # experiment knob: 0 = the multi-launch sequence only
 
 
+def dominant_subspace_fused_fits(n, ne):
+    return PURIFY_FUSED and bool(lib.syn_dominant_subspace_fused_fits(_i32(int(n)), _i32(int(ne))))
+
+
 def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160, ns_max=80):
     """Orthonormal basis U (n x ne) of the span of the `ne` dominant eigenvectors of the symmetric PSD matrix A (n x n contiguous,
     not modified) by SP2 spectral projection + Newton-Schulz (csrc/purify.cu): GEMM-bound, no host round trip.

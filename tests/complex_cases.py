@@ -275,3 +275,24 @@ def _round_svd_numpy(cores, chi):
 
 
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
+
+
+def case_large_complex_bond_takes_the_projection_solver():
+    """A (128 x 160) complex unfolding cut to 32: the embedded problem is 256 x 256, so the fused spectral-projection kernel runs on
+    the interleaved embedding and the complex basis is read off its even columns."""
+    from syngular_b200 import cplx
+    from syngular.tensor import _sweeps as sw
+    rng = np.random.default_rng(12)
+    m, c, chi = 128, 160, 32
+    u, v = haar(rng, m), haar(rng, c)
+    s = np.exp(-6.0 * np.arange(m) / m)
+    M = (u * s) @ v[:m]
+    U, keep, sigma, disc = cplx.svd_basis(_cx(M), chi, 0.0, sw.eigh_gram)
+    assert sigma is None and keep == chi                          # the projection route was taken (no spectrum is formed)
+    Un = _np(U)
+    assert np.max(np.abs(Un.conj().T @ Un - np.eye(chi))) < 1e-12
+    assert _rel(Un @ Un.conj().T, u[:, :chi] @ u[:, :chi].conj().T) < 1e-9
+    assert abs(float(disc) - float(np.sum(s[chi:] ** 2))) < 1e-10 * float(np.sum(s ** 2))
+
+
+CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}

@@ -162,6 +162,10 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(info)
 
 
+def dominant_subspace_fused_fits(n, ne):
+    return n % 64 == 0 and ne % 64 == 0 and n >= 128 and ne >= 64 and ne < n
+
+
 def env_sandwich_fits(l, i, o, r, b):
     return (l, i, o, r) == (16, 2, 2, 16) and b % 16 == 0
 
@@ -222,7 +226,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "env_sandwich_fits", "env_sandwich", "env_mirror", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

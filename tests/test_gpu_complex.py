@@ -37,3 +37,31 @@ def test_brickwall_12_qubits_chi_64_against_state_vector():
     got = c2.get().to_tensor()
     f = abs(np.vdot(psi, got)) ** 2
     assert np.linalg.norm(got) <= 1.0 + 1e-12 and 0.05 < f < 1.0
+
+
+def test_brickwall_16_qubits_truncated_to_chi_128_matches_numpy_tebd():
+    """Saturated complex bonds (unfoldings 256 x 256, embedded 512 x 512) are cut by the fused spectral-projection kernel; the whole
+    truncated evolution is compared with the same sequence of truncations done by numpy SVDs."""
+    from syngular.quantum import Circuit
+    from syngular_b200 import ops
+    rng = np.random.default_rng(13)
+    n, depth, chi = 16, 9, 128
+    structure = [(cc.haar(rng, 4).reshape(2, 2, 2, 2), i) for layer in range(depth) for i in range(layer % 2, n - 1, 2)]
+    calls = [0]
+    orig = ops.dominant_subspace
+
+    def spy(*a, **k):
+        calls[0] += 1
+        return orig(*a, **k)
+    ops.dominant_subspace = spy
+    try:
+        c = Circuit(n, structure=structure, chi_max=chi)
+        c.run()
+    finally:
+        ops.dominant_subspace = orig
+    st = c.get().state
+    assert max(s.shape[2] for s in st.sites[:-1]) == chi and calls[0] >= 1
+    ref = cc._tebd_numpy(n, structure, chi)
+    got = c.get().to_tensor()
+    assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref))
+    assert abs((st.conj() | st) - np.vdot(ref, ref)) < 1e-9
