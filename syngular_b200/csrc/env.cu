@@ -15,10 +15,13 @@
 namespace syn {
 
 constexpr int EV_THREADS = 256, EV_TB = 16, EV_K = 32, EV_R = 16, EV_L = 16;
-constexpr int EV_LDS1 = EV_R * EV_TB + 8;          // 264: slab row stride (k-major B operand: stride = 8 mod 16 doubles)
-constexpr int EV_LDW = EV_K + 4;                   // 36:  W rows (A operand: stride = 4 mod 16 doubles)
-constexpr int EV_RS = EV_TB + 8;                   // 24:  r' stride inside a P2 row
-constexpr int EV_LDP = EV_R * EV_RS;               // 384: P2 row stride
+// 64-bit fragment loads are served per half-warp (g in 0..3, t in 0..3): every stride that a fragment index multiplies must be
+// 4 (mod 16) doubles for the 16 lanes to hit 16 distinct bank pairs (first ncu capture: 43 % of the shared wavefronts were conflicts
+// with strides of 8 mod 16)
+constexpr int EV_LDS1 = EV_R * EV_TB + 4;          // 260: slab row stride (k-major B operand of stage 1: index t)
+constexpr int EV_LDW = EV_K + 4;                   // 36:  W rows (A operand: index g)
+constexpr int EV_RS = EV_TB + 4;                   // 20:  r' stride inside a P2 row (B operand of stage 2: index t)
+constexpr int EV_LDP = EV_R * EV_RS + 8;           // 328: P2 row stride (8 mod 16: the 128-bit stores of two rows g fill one wavefront)
 constexpr int EV_S1 = EV_K * EV_LDS1;              // doubles per slab buffer
 constexpr size_t EV_SMEM = sizeof(double) * (2 * EV_S1 + 8 * EV_LDP + 2 * EV_K * EV_LDW);
 
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1)
 env_sandwich_kernel(const double* __restrict__ P1, const double* __restrict__ W, double* __restrict__ Z, int na, int b) {
     extern __shared__ __align__(16) double ev_smem[];
     double* S1 = ev_smem;                           // [2][32][264]
-    double* S2 = S1 + 2 * EV_S1;                    // [8][16][24]   P2 rows of the current group of 4 l
+    double* S2 = S1 + 2 * EV_S1;                    // [8][16][20]   P2 rows of the current group of 4 l
     double* W1 = S2 + 8 * EV_LDP;                   // [(l,o)][(i,r)]
     double* W2 = W1 + EV_K * EV_LDW;                // [(l',i')][(o,r')]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
