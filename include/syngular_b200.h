@@ -141,7 +141,8 @@ int syn_overlap_batched_f64(const syn_overlap_site_t* sites, int n_sites, int ba
  * elementwise kernel each, branch chosen on the device), then `ns_iters` Newton-Schulz steps on P[:, :ne].  No host round trip.
  * Stands where the reference's unfinished density-matrix branch calls np.linalg.eigh (MPO:228) and keeps eigvecs[:, :min_bond].
  * info (device, 8 doubles): [0] tr P, [1] |P|_F^2 (both = ne when converged), [2] sum A o P = kept weight, [3] |A|_F,
- * [4] max |U^T U - I|, [5] tr A, [6] tr(X - X^2) one step before the end.  The caller decides (and falls back to
+ * [4] max |U^T U - I|, [5] tr A, [6] tr(X - X^2) one step before the end, [7] steps + 1e6 * (number of leading 2X - X^2 steps ~
+ * log2(|A|_F / lambda_cut): the subspace is accurate to ~eps |A| / gap, so callers reject cuts deep in a decaying spectrum).  The caller decides (and falls back to
  * syn_jacobi_rows_f64 when the spectrum has no gap at ne). */
 size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_iters);
 int syn_dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_iters, double* U, void* ws, size_t ws_bytes,
@@ -149,7 +150,7 @@ int syn_dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int
 /* The same solver as ONE persistent cooperative kernel (one CTA per SM, iterates resident in L2, 32 x 32 DMMA tiles from a cp.async
  * ring, symmetric products computed on their lower tiles only, grid barrier per step).  The iteration counts adapt on the device:
  * SP2 stops two steps after tr(X - X^2) < 1e-11 ne (at most sp2_max steps), Newton-Schulz when max |U^T U - I| < 1e-13 (at most
- * ns_max).  Needs n and ne multiples of 64 (syn_dominant_subspace_fused_fits).  info as above, plus [7] = sp2 steps + 1000 * NS steps. */
+ * ns_max).  Needs n and ne multiples of 64 (syn_dominant_subspace_fused_fits).  info as above, [7] = sp2 steps + 1000 * NS steps + 1e6 * leading lift steps. */
 size_t syn_dominant_subspace_fused_workspace_f64(int n, int ne, int sp2_max, int ns_max);
 int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,

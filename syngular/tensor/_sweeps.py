@@ -649,18 +649,26 @@ PURIFY_SP2_ITERS = 52          # multi-launch variant: fixed counts
 PURIFY_NS_ITERS = 26
 PURIFY_SP2_MAX = 90            # fused kernel: upper limits (it stops by itself); 90 steps resolve gaps down to ~1e-12 |A|
 PURIFY_NS_MAX = 60
+# Accuracy guard.  The projector is accurate normwise: the kept space tilts by ~3e-15 |A| / gap, i.e. the state moves by
+# ~3e-15 (lambda_0 / gap) sqrt(lambda_cut / lambda_0) (measured on a chain with a steeply decaying spectrum, tools/purify_diag.py),
+# whereas Jacobi on the Cholesky factor is accurate relative to each singular value.  The kernel reports lift = number of leading
+# 2X - X^2 steps ~ log2(|A|_F / lambda_cut); with gaps ~ lambda_cut / 100 (C2 plateau: lift 6-10) the 1e-10 parity bound needs
+# lift <= ~14; when the cut is the edge of the null space (target = structural rank, gap = lambda_cut) lift <= 24 is enough.
+PURIFY_MAX_LIFT = 14
+PURIFY_MAX_LIFT_RANK_GAP = 24
 PURIFY_STATS = {"taken": 0, "fallback": 0}
 IDENTITY_WHEN_FULL = True      # bonds that keep their whole space skip the eigen-solve (gauge: identity core)
 
 
-def dominant_subspace(A, chi_max):
+def dominant_subspace(A, chi_max, rank_gap=False):
     """(U (n x chi_max) orthonormal, discarded weight) by spectral projection, or None when the iteration did not reach a projector
-    of trace chi_max that is orthonormalised to 1e-12 (no gap at the cut: rank-deficient bonds) -- one host read of 8 doubles."""
+    of trace chi_max that is orthonormalised to 1e-12 (no gap at the cut: rank-deficient bonds) or the cut lies too deep in the
+    spectrum for its normwise accuracy (see PURIFY_MAX_LIFT) -- one host read of 8 doubles."""
     U, info = ops.dominant_subspace(A, chi_max, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
     h = info.cpu().numpy()
     tr, f2, kept_w, dev, tr_a, idem = h[0], h[1], h[2], h[4], h[5], h[6]
     ok = (abs(tr - chi_max) < 1e-9 * chi_max and abs(f2 - chi_max) < 1e-9 * chi_max and abs(idem) < 1e-11 * chi_max and dev < 1e-12
-          and np.isfinite(h).all())
+          and np.isfinite(h).all() and int(h[7]) // 1000000 <= (PURIFY_MAX_LIFT_RANK_GAP if rank_gap else PURIFY_MAX_LIFT))
     if not ok:
         PURIFY_STATS["fallback"] += 1
         return None
@@ -699,7 +707,7 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
             T = _carry_from(eye, M2, nA, b, r, transposed_basis=False)        # = M2 with its columns re-ordered to (r, b)
             continue
         if PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
-            got = dominant_subspace(A, ne)
+            got = dominant_subspace(A, ne, rank_gap=ne >= min(D, right_dim[k + 1]))
             if got is not None:
                 U, disc = got
                 trunc.sigma.append(LazySpectrum(A, U)); trunc.keep.append(ne); trunc.discarded.append(disc)

@@ -28,6 +28,8 @@ JACOBI_MAX_N = 1024
 PURIFY_MIN_N = 256             # embedded bond problems at least this large try the spectral-projection solver first (0 = off)
 PURIFY_SP2_MAX = 90
 PURIFY_NS_MAX = 60
+PURIFY_MAX_LIFT = 14           # see syngular/tensor/_sweeps.py: cuts deeper in the spectrum go to the Jacobi route (when it fits)
+PURIFY_MAX_LIFT_RANK_GAP = 24
 
 
 class Cx:
@@ -272,7 +274,8 @@ def svd_basis(M, chi_max, cutoff, eigh, rank_tol=3.2e-7):
         h = info.cpu()
         tr, f2, kept_w, dev, tr_a, idem = (float(h[k]) for k in (0, 1, 2, 4, 5, 6))
         if (abs(tr - 2 * target) < 2e-9 * target and abs(f2 - 2 * target) < 2e-9 * target and abs(idem) < 2e-11 * target and dev < 1e-12
-                and bool(torch.isfinite(h).all())):
+                and bool(torch.isfinite(h).all())
+                and (int(h[7]) // 1000000 <= (PURIFY_MAX_LIFT_RANK_GAP if target >= min(m, c) else PURIFY_MAX_LIFT) or 2 * m > JACOBI_MAX_N)):
             U = polish_columns(unembed_columns(V, m, target))
             return U, target, None, torch.tensor(max(0.5 * (tr_a - kept_w), 0.0), dtype=F64)
     if 2 * m > JACOBI_MAX_N:

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(1024) purify_dev_kernel(const double* __restri
     }
 }
 
-__global__ void purify_finish_kernel(const double* __restrict__ ctrl, int iters, const double* __restrict__ scal, double* __restrict__ info) {
+__global__ void purify_finish_kernel(const double* __restrict__ ctrl, int iters, double ne, const double* __restrict__ scal, double* __restrict__ info) {
     // scal: [0] = |A|_F^2, [1] = sum A o P ; ctrl[2 it .. 2 it + 1] = (tr X, |X|_F^2) of iterate `it` ; info[4] is written by purify_dev_kernel
     info[0] = ctrl[2 * iters];
     info[1] = ctrl[2 * iters + 1];
@@ -162,6 +162,13 @@ __global__ void purify_finish_kernel(const double* __restrict__ ctrl, int iters,
     info[3] = sqrt(scal[0]);
     info[5] = ctrl[0] * sqrt(scal[0]);          // tr A
     info[6] = ctrl[2 * (iters - 1)] - ctrl[2 * (iters - 1) + 1];   // idempotency defect tr(X - X^2) one step before the end
+    int lift = 0;                                                   // leading 2X - X^2 steps ~ log2(|A|_F / lambda_cut)
+    for (int it = 0; it < iters; ++it) {
+        const double tr0 = ctrl[2 * it], f0 = ctrl[2 * it + 1];
+        if (fabs(f0 - ne) < fabs(2.0 * tr0 - f0 - ne)) break;
+        ++lift;
+    }
+    info[7] = (double)iters + 1e6 * lift;
 }
 
 static inline int split_k(int rows_out, int cols_out, int K) {
@@ -217,7 +224,7 @@ int dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_
     }
     purify_dot_kernel<<<eb, 256, 0, st>>>(A, X, nn, scal + 1);
     if (int rc = launch_status("purify_dot_kernel")) return rc;
-    purify_finish_kernel<<<1, 1, 0, st>>>(ctrl, sp2_iters, scal, info);
+    purify_finish_kernel<<<1, 1, 0, st>>>(ctrl, sp2_iters, (double)ne, scal, info);
     if (int rc = launch_status("purify_finish_kernel")) return rc;
     // U0 = P[:, :ne]
     SYN_CUDA(cudaMemcpy2DAsync(Ua, sizeof(double) * ne, X, sizeof(double) * n, sizeof(double) * ne, n, cudaMemcpyDeviceToDevice, st));
@@ -421,18 +428,23 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     const int T = n / PF_T, lower = T * (T + 1) / 2;
     int it = 0;
     int extra = 0;
+    int lift = 0;            // leading 2X - X^2 steps: each doubles the small eigenvalues, so lift ~ log2(|A|_F / lambda_cut)
+    bool lifting = true;
     double tr0 = 0.0, f0 = 0.0;
     for (; it < a.sp2_max; ++it) {
         tr0 = __ldcg(trf + 2 * it);
         f0 = __ldcg(trf + 2 * it + 1);
         // a step squares the distance to {0, 1} of the eigenvalues on one side and doubles it on the other, so the defect tr(X - X^2) is
-        // dominated by the side that was just doubled: two more steps (one of each kind follows from the trace rule) finish both
+        // dominated by the side that was just doubled: two more steps, one of each kind, finish both sides
         const bool conv = fabs(tr0 - ne) < 1e-11 * ne && fabs(tr0 - f0) < 1e-11 * ne;
         if (conv || extra) {
             if (extra == 2) break;
             ++extra;
         }
-        const bool square = fabs(f0 - ne) < fabs(2.0 * tr0 - f0 - ne);
+        // once converged the trace rule only sees rounding noise: the two finishing steps are forced to be one of each kind
+        // (x^2 squares the distance of the eigenvalues near 0, 2x - x^2 of those near 1; the pair leaves 2 d^2 and 4 d^2)
+        const bool square = extra == 1 ? true : (extra == 2 ? false : fabs(f0 - ne) < fabs(2.0 * tr0 - f0 - ne));
+        if (lifting && !square) ++lift; else lifting = false;
         double tr = 0.0, f2 = 0.0;
         for (int tile = blockIdx.x; tile < lower; tile += gridDim.x) {
             int ti, tj;
@@ -550,7 +562,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
         a.info[4] = dev;
         a.info[5] = __ldcg(trf) * sqrt(f);
         a.info[6] = tr0 - f0;
-        a.info[7] = (double)(sp2_used + 1000 * ns);
+        a.info[7] = (double)(sp2_used + 1000 * ns) + 1e6 * lift;
     }
 }
 

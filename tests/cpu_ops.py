@@ -158,7 +158,12 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     for _ in range(int(ns_iters)):
         u = u @ (1.5 * np.eye(ne) - 0.5 * (u.T @ u))
     dev = float(np.max(np.abs(u.T @ u - np.eye(ne))))
-    info = np.array([hist[-1][0], hist[-1][1], float((a * x).sum()), fro, dev, tr0 * fro, hist[-2][0] - hist[-2][1], 0.0])
+    lift = 0
+    for tr, f2 in hist[:-1]:
+        if abs(f2 - ne) < abs(2 * tr - f2 - ne):
+            break
+        lift += 1
+    info = np.array([hist[-1][0], hist[-1][1], float((a * x).sum()), fro, dev, tr0 * fro, hist[-2][0] - hist[-2][1], sp2_iters + 1e6 * lift])
     return torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(info)
 
 

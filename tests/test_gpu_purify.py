@@ -45,7 +45,7 @@ def test_no_gap_is_reported_not_hidden():
         assert not (abs(h[0] - 64) < 1e-9 * 64 and abs(h[1] - 64) < 1e-9 * 64 and h[4] < 1e-12)
 
 
-@pytest.mark.parametrize("n,chi,chiw", [(14, 16, 4), (16, 32, 8)])
+@pytest.mark.parametrize("n,chi,chiw", [(14, 16, 4), (16, 32, 8), (16, 64, 8), (16, 64, 2)])
 def test_sweep_with_projection_solver_matches_oracle(n, chi, chiw):
     import bench
     from syngular.tensor import _sweeps as sw
@@ -63,12 +63,14 @@ def test_sweep_with_projection_solver_matches_oracle(n, chi, chiw):
         out_j, _ = sw.apply_round_dm(Xd, Wd, chi)
     finally:
         sw.PURIFY_MIN_N = saved
-    assert taken >= 4
+    # chi_W = 2 makes a steeply decaying spectrum (lambda_cut ~ 1e-7 .. 1e-11 lambda_0): the accuracy guard must send those bonds to
+    # Cholesky + Jacobi; the other chains have C2-like spectra and take the projection solver
+    assert taken >= 4 or chiw == 2
     got, got_j = [c.cpu().numpy() for c in out], [c.cpu().numpy() for c in out_j]
     dense_ref = R.to_dense(ref)
     scale = np.max(np.abs(dense_ref))
-    assert np.max(np.abs(R.to_dense(got) - dense_ref)) < 1e-10 * scale
-    assert np.max(np.abs(R.to_dense(got) - R.to_dense(got_j))) < 1e-10 * scale
+    assert np.max(np.abs(R.to_dense(got) - dense_ref)) < 2e-11 * scale           # north_star bound is 1e-10: keep a margin
+    assert np.max(np.abs(R.to_dense(got) - R.to_dense(got_j))) < 2e-11 * scale
     sig, keep, disc = trunc.host()
     for k in range(n - 1):
         kk = ref[k].shape[-1]
