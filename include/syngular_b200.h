@@ -156,6 +156,16 @@ int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
                                     double* info, void* stream);
 
+/* Q (m x q, contiguous) = orthonormal basis of the column space of A (m x q, row stride lda, full column rank) by the Newton-Schulz
+ * phase of the same persistent kernel: Q = A (A^T A)^(-1/2).  For the truncation step `Q, R = np.linalg.qr(L, "complete"); Q[:, :q]`
+ * (MPS:443-446, MPO:555-558) any orthonormal basis of span(L[:, :q]) is the same projection, and this one is GEMM-bound (0.2 ms against
+ * 1.2 ms for the cluster Householder kernel at 512 x 256).  info[4] = max |Q^T Q - I| at exit, info[7] = 1000 * steps; the caller falls
+ * back to syn_qrt_f64 when it did not converge (rank-deficient columns).  m, q multiples of 64, q <= m. */
+size_t syn_orthonormalize_columns_workspace_f64(int m, int q, int ns_max);
+int syn_orthonormalize_columns_fits(int m, int q);
+int syn_orthonormalize_columns_f64(const double* A, int64_t lda, int m, int q, int ns_max, double* Q, void* ws, size_t ws_bytes,
+                                   double* info, void* stream);
+
 /* ---- fused W-sandwich of the right-environment update (density-matrix rounding) -------------------------------------------------
  * Z[a, l, (l',i'), b'] = sum_{(o,r')} W[l',i',o,r'] ( sum_{(i,r)} W[l,i,o,r] P1[a, (i,r), (r',b')] ):  the two small-K contractions
  * with the MPO core W (l,i,o,r) on either side of the large intermediate in ONE kernel, the intermediate staying in shared memory

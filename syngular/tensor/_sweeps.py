@@ -153,6 +153,27 @@ def site_mpo_mpo(A, B):
 # ---------------------------------------------------------------------------------------------------------
 # reference-semantic sweeps
 # ---------------------------------------------------------------------------------------------------------
+ORTHO_MIN_ROWS = 256           # truncation steps with at least this many rows try the fused Newton-Schulz kernel first (0 = Householder only)
+
+
+def qrt_step(L, q, want_S=True):
+    """The reference truncation step `Q, R = np.linalg.qr(L, "complete"); Q[:, :q]; R[:q, :]` (MPS:443-446, MPO:555-558) = projection
+    of L on the span of its first q columns.  Any orthonormal basis of that span gives the same projection, so large blocks take the
+    GEMM-bound polar orthonormalisation Q = Lq (Lq^T Lq)^(-1/2) (fused Newton-Schulz kernel, csrc/purify.cu) and fall back to the
+    Householder kernel when it does not converge (rank-deficient leading columns) or the shape is not covered."""
+    if isinstance(L, Cx):
+        return cplx.qrt(L, q, want_S=want_S)
+    m, n = L.shape
+    q = int(q)
+    if (ORTHO_MIN_ROWS and m >= ORTHO_MIN_ROWS and q <= n and L.dim() == 2 and L.stride(1) == 1 and L.data_ptr() % 16 == 0
+            and ops.orthonormalize_columns_fits(m, q)):
+        Q, info = ops.orthonormalize_columns(L[:, :q])
+        h = info.cpu()
+        if bool(torch.isfinite(h).all()) and float(h[4]) < 1e-12:
+            return Q, (ops.matmul(Q.t(), L) if want_S else None)
+    return ops.qrt(L, q, want_S=want_S)
+
+
 @complex_aware
 def round_qr(sites, dim):
     """Strict `>>` sweep (MPS:432-468, MPO:544-580): QR-truncation left to right, no canonicalisation.
@@ -161,7 +182,7 @@ def round_qr(sites, dim):
     for k in range(len(out) - 1):
         cur, nxt = out[k], out[k + 1]
         L = cur.reshape(-1, cur.shape[-1])
-        Q, S = _O(L).qrt(L, dim)
+        Q, S = qrt_step(L, dim)
         kept = Q.shape[1]
         Wn = _O(S).matmul(S, nxt.reshape(nxt.shape[0], -1))
         out[k] = Q.reshape(tuple(cur.shape[:-1]) + (kept,))
@@ -421,7 +442,7 @@ def apply_round_qr(X, W, dim):
         s, o, _ = M.shape
         b, r = X[k].shape[2], W[k].shape[3]
         L = M.reshape(s * o, b * r)
-        Q, _ = ops.qrt(L, dim, want_S=False)
+        Q, _ = qrt_step(L, dim, want_S=False)
         kept = Q.shape[1]
         out.append(Q.reshape(s, o, kept))
         T = _carry_from(Q, L, kept, b, r, transposed_basis=False)

@@ -272,6 +272,8 @@ struct PurifyArgs {
     double *X0, *X1, *Ua, *Ub, *Va, *Vb, *G, *Uout, *ctrl, *info;
     unsigned* bar;
     int n, ne, sp2_max, ns_max;
+    int ns_only;             // 1: A is an (n x ne) matrix with row stride ld0 whose columns are to be orthonormalised (no projection phase)
+    int64_t ld0;
 };
 
 __device__ __forceinline__ unsigned pf_ld_acquire(const unsigned* p) {
@@ -403,12 +405,16 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     // ---- |A|_F^2 -------------------------------------------------------------------------------------------------------------------
     {
         double s = 0.0;
-        for (int64_t i = gid; i < nn; i += gstride) { const double x = a.A[i]; s = fma(x, x, s); }
+        if (!a.ns_only) {
+            for (int64_t i = gid; i < nn; i += gstride) { const double x = a.A[i]; s = fma(x, x, s); }
+        } else {
+            for (int64_t i = gid; i < (int64_t)n * ne; i += gstride) { const double x = a.A[(i / ne) * a.ld0 + (i % ne)]; s = fma(x, x, s); }
+        }
         block_accumulate(s, 0.0, ctrl, nullptr);
     }
     pf_grid_barrier(a.bar, target);
-    // ---- X0 = A / |A|_F ------------------------------------------------------------------------------------------------------------
-    {
+    if (!a.ns_only) {
+        // ---- X0 = A / |A|_F --------------------------------------------------------------------------------------------------------
         const double f = __ldcg(ctrl);
         const double inv = f > 0.0 ? rsqrt(f) : 0.0;
         double tr = 0.0, f2 = 0.0;
@@ -419,6 +425,16 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
             if (i / n == i % n) tr += x;
         }
         block_accumulate(tr, f2, trf, trf + 1);
+    } else {
+        // ---- U = A / |A|_F (all singular values <= 1) and its transpose -------------------------------------------------------------
+        const double f = __ldcg(ctrl);
+        const double inv = f > 0.0 ? rsqrt(f) : 0.0;
+        for (int64_t i = gid; i < (int64_t)n * ne; i += gstride) {
+            const int64_t r = i / ne, c = i - r * ne;
+            const double x = a.A[r * a.ld0 + c] * inv;
+            a.Ub[i] = x;
+            a.Vb[c * n + r] = x;
+        }
     }
     pf_grid_barrier(a.bar, target);
 
@@ -431,7 +447,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     int lift = 0;            // leading 2X - X^2 steps: each doubles the small eigenvalues, so lift ~ log2(|A|_F / lambda_cut)
     bool lifting = true;
     double tr0 = 0.0, f0 = 0.0;
-    for (; it < a.sp2_max; ++it) {
+    const int sp2_limit = a.ns_only ? 0 : a.sp2_max;
+    for (; it < sp2_limit; ++it) {
         tr0 = __ldcg(trf + 2 * it);
         f0 = __ldcg(trf + 2 * it + 1);
         // a step squares the distance to {0, 1} of the eigenvalues on one side and doubles it on the other, so the defect tr(X - X^2) is
@@ -477,15 +494,16 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     tr0 = __ldcg(trf + 2 * it);
     f0 = __ldcg(trf + 2 * it + 1);
     // Xc = P.  kept weight sum A o P (no barrier needed before the Gram phase: different outputs)
-    {
+    if (!a.ns_only) {
         double s = 0.0;
         for (int64_t i = gid; i < nn; i += gstride) s = fma(a.A[i], __ldcg(Xc + i), s);
         block_accumulate(s, 0.0, ctrl + 1, nullptr);
     }
 
     // ---- Newton-Schulz on U = P[:, :ne]  (V = U^T = P[:ne, :]) -----------------------------------------------------------------------
-    const double* U = Xc;  int64_t ldu = n;
-    const double* V = Xc;                                     // (ne x n), ld n
+    const double* U = a.ns_only ? a.Ub : Xc;
+    int64_t ldu = a.ns_only ? ne : n;
+    const double* V = a.ns_only ? a.Vb : Xc;                  // (ne x n), ld n
     double* Un = a.Ua;  double* Vn = a.Va;
     const int TG = ne / PF_T, lower_g = TG * (TG + 1) / 2, tiles_u = (n / PF_T) * TG;
     int ns = 0;
@@ -570,12 +588,15 @@ static size_t purify_fused_ws_doubles(int n, int ne, int sp2_max, int ns_max) {
     return (size_t)2 * n * n + (size_t)4 * n * ne + (size_t)ne * ne + 4 + 2 * (sp2_max + 2) + (ns_max + 2) + 64;
 }
 
+static bool ortho_fused_fits(int m, int q) { return m % PF_BK == 0 && q % PF_BK == 0 && m >= 128 && q >= 64 && q <= m; }
+
 static bool purify_fused_fits(int n, int ne) { return n % PF_BK == 0 && ne % PF_BK == 0 && n >= 128 && ne >= 64 && ne < n; }
 
 int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, double* ws, size_t ws_bytes, double* info,
-                                cudaStream_t st) {
+                                cudaStream_t st, int ns_only = 0, int64_t ld0 = 0) {
     SYN_REQUIRE(A && U && ws && info, "syn_dominant_subspace_f64: null argument");
-    SYN_REQUIRE(purify_fused_fits(n, ne), "syn_dominant_subspace_f64 (fused): n and ne must be multiples of 64 (n=%d ne=%d)", n, ne);
+    SYN_REQUIRE(ns_only ? ortho_fused_fits(n, ne) : purify_fused_fits(n, ne),
+                "syn_dominant_subspace_f64 (fused): n and ne must be multiples of 64 (n=%d ne=%d)", n, ne);
     SYN_REQUIRE(sp2_max >= 1 && sp2_max <= 400 && ns_max >= 0 && ns_max <= 400, "syn_dominant_subspace_f64: bad iteration limits");
     SYN_REQUIRE(ws_bytes >= purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double), "syn_dominant_subspace_f64: workspace too small");
     SYN_REQUIRE(((((uintptr_t)ws) | ((uintptr_t)A)) & 15) == 0, "syn_dominant_subspace_f64: A and the workspace must be 16-byte aligned");
@@ -601,6 +622,7 @@ int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int
     a.bar = reinterpret_cast<unsigned*>(a.ctrl + ctrl_doubles);
     a.Uout = U; a.info = info;
     a.n = n; a.ne = ne; a.sp2_max = sp2_max; a.ns_max = ns_max;
+    a.ns_only = ns_only; a.ld0 = ld0;
     SYN_CUDA(cudaMemsetAsync(a.ctrl, 0, sizeof(double) * (ctrl_doubles + 2), st));
     const int T = n / PF_T, lower = T * (T + 1) / 2;
     int grid = lower < max_ctas ? lower : max_ctas;
@@ -620,6 +642,18 @@ extern "C" size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_ite
 extern "C" size_t syn_dominant_subspace_fused_workspace_f64(int n, int ne, int sp2_max, int ns_max) {
     if (n < 2 || ne < 1 || sp2_max < 1 || ns_max < 0) return 0;
     return syn::purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double);
+}
+
+extern "C" int syn_orthonormalize_columns_fits(int m, int q) { return syn::ortho_fused_fits(m, q) ? 1 : 0; }
+
+extern "C" size_t syn_orthonormalize_columns_workspace_f64(int m, int q, int ns_max) {
+    if (m < 2 || q < 1 || ns_max < 0) return 0;
+    return syn::purify_fused_ws_doubles(m, q, 1, ns_max) * sizeof(double);
+}
+
+extern "C" int syn_orthonormalize_columns_f64(const double* A, int64_t lda, int m, int q, int ns_max, double* Q, void* ws, size_t ws_bytes,
+                                              double* info, void* stream) {
+    return syn::dominant_subspace_fused_f64(A, m, q, 1, ns_max, Q, (double*)ws, ws_bytes, info, (cudaStream_t)stream, 1, lda);
 }
 
 extern "C" int syn_dominant_subspace_fused_fits(int n, int ne) { return syn::purify_fused_fits(n, ne) ? 1 : 0; }

@@ -238,6 +238,28 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return U, info
 
 
+lib.syn_orthonormalize_columns_workspace_f64.restype = ctypes.c_size_t
+lib.syn_orthonormalize_columns_workspace_f64.argtypes = [_i32, _i32, _i32]
+
+
+def orthonormalize_columns_fits(m, q):
+    return PURIFY_FUSED and bool(lib.syn_orthonormalize_columns_fits(_i32(int(m)), _i32(int(q))))
+
+
+def orthonormalize_columns(A, ns_max=60):
+    """Q (m x q) = A (A^T A)^(-1/2): orthonormal basis of the column space of the 2-D view A (unit column stride) by the fused
+    Newton-Schulz kernel (csrc/purify.cu).  Returns (Q, info) with info on the DEVICE ([4] = max |Q^T Q - I|)."""
+    require_cuda_f64(A)
+    m, q = A.shape
+    assert A.stride(1) == 1
+    Q = torch.empty((m, q), dtype=torch.float64, device=A.device)
+    info = torch.zeros((8,), dtype=torch.float64, device=A.device)
+    ws = workspace(lib.syn_orthonormalize_columns_workspace_f64(m, q, int(ns_max)), A.device, tag="purify_fused")
+    check(lib.syn_orthonormalize_columns_f64(ptr(A), _i64(A.stride(0)), _i32(m), _i32(q), _i32(int(ns_max)), ptr(Q), ptr(ws),
+                                             _sz(ws.numel() * 8), ptr(info), stream_ptr()), "syn_orthonormalize_columns_f64")
+    return Q, info
+
+
 ENV_FUSED = os.environ.get("SYN_ENV_FUSED", "1") != "0"              # experiment knob: 0 = two GEMM launches
 
 

@@ -171,6 +171,20 @@ def dominant_subspace_fused_fits(n, ne):
     return n % 64 == 0 and ne % 64 == 0 and n >= 128 and ne >= 64 and ne < n
 
 
+def orthonormalize_columns_fits(m, q):
+    return m % 64 == 0 and q % 64 == 0 and m >= 128 and q >= 64 and q <= m
+
+
+def orthonormalize_columns(A, ns_max=60):
+    a = A.numpy()
+    u, s, vt = np.linalg.svd(a, full_matrices=False)
+    ok = s[-1] > 1e-10 * s[0]
+    qm = u @ vt
+    info = np.zeros(8)
+    info[4] = float(np.max(np.abs(qm.T @ qm - np.eye(a.shape[1])))) if ok else 1.0
+    return torch.from_numpy(np.ascontiguousarray(qm)), torch.from_numpy(info)
+
+
 def env_sandwich_fits(l, i, o, r, b):
     return (l, i, o, r) == (16, 2, 2, 16) and b % 16 == 0
 
@@ -231,7 +245,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

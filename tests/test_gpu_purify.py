@@ -118,3 +118,33 @@ def test_symmetric_environment_build_matches_full_gemm():
     assert any(e.shape[0] >= 512 for e in E1[1:-1])
     for a, b in zip(E1[1:-1], E0[1:-1]):
         assert (a - b).abs().max().item() <= 1e-12 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("m,q,cols", [(512, 256, 4096), (256, 128, 300), (1024, 64, 64), (128, 64, 200)])
+def test_polar_truncation_step_is_the_same_projection_as_householder(m, q, cols):
+    """qrt_step through the fused Newton-Schulz kernel against numpy's QR of the leading columns (gauge-invariant: Q Q^T L)."""
+    from syngular.tensor import _sweeps as sw
+    from syngular_b200 import ops
+    rng = np.random.default_rng(m + q)
+    L = rng.normal(size=(m, cols))
+    Ld = torch.from_numpy(L).cuda()
+    assert ops.orthonormalize_columns_fits(m, q)
+    Q, info = ops.orthonormalize_columns(Ld[:, :q])
+    assert float(info[4].item()) < 1e-13
+    Qs, S = sw.qrt_step(Ld, q)
+    Qn, Sn = Qs.cpu().numpy(), S.cpu().numpy()
+    assert np.max(np.abs(Qn.T @ Qn - np.eye(q))) < 1e-12
+    qr, _ = np.linalg.qr(L[:, :q])
+    assert np.max(np.abs(Qn @ Sn - qr @ (qr.T @ L))) < 1e-11 * np.max(np.abs(L))
+
+
+def test_polar_truncation_step_falls_back_on_dependent_columns():
+    from syngular.tensor import _sweeps as sw
+    rng = np.random.default_rng(3)
+    L = rng.normal(size=(256, 200))
+    L[:, 5] = L[:, 2] * 0.5                                   # rank-deficient leading block: Newton-Schulz cannot converge
+    Ld = torch.from_numpy(L).cuda()
+    Q, S = sw.qrt_step(Ld, 128)
+    Qn, Sn = Q.cpu().numpy(), S.cpu().numpy()
+    assert np.max(np.abs(Qn.T @ Qn - np.eye(128))) < 1e-12
+    assert np.max(np.abs((Qn @ Sn)[:, :128] - L[:, :128])) < 1e-11 * np.max(np.abs(L))
