@@ -229,6 +229,30 @@ def mpo_apply(cores, op_cores, indices):
     return cores
 
 
+def dmrg_right_blocks(state, operator):
+    """DMRG.__right_blocks (variational/dmrg.py:65-87): R_k[a, w, a'] = sum S_k[a,o,b] W_k[w,i,o,v] S_k[a',i,b'] R_{k+1}[b,v,b'] for
+    k = n-1 .. 2 (no conjugation; the FIRST state copy meets the operator's OUT leg); entries 0 and 1 stay None."""
+    n = len(state)
+    blocks = [None] * n
+    R = np.ones((1, 1, 1))
+    for k in range(n - 1, 1, -1):
+        R = np.einsum("aob,wiov,cid,bvd->awc", state[k], operator[k], state[k], R)
+        blocks[k] = R
+    return blocks
+
+
+def dmrg_left_blocks(state, operator):
+    """DMRG.__left_blocks (variational/dmrg.py:90-112): L_k[b, v, b'] = sum L_{k-1}[a,w,a'] S_k[a,o,b] W_k[w,i,o,v] S_k[a',i,b'] for
+    k = 0 .. n-3; the last two entries stay None."""
+    n = len(state)
+    blocks = [None] * n
+    L = np.ones((1, 1, 1))
+    for k in range(n - 2):
+        L = np.einsum("awc,aob,wiov,cid->bvd", L, state[k], operator[k], state[k])
+        blocks[k] = L
+    return blocks
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step, left to right (matrix_product_state.py:298-319,
     matrix_product_operator.py:430-450).  `T` is the (interleaved, for an MPO) dense tensor and `shapes` the

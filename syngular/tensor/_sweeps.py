@@ -362,6 +362,61 @@ def mpo_apply_range(sites, op_sites, indices):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------
+# three-layer transfer contractions: the DMRG environment blocks (variational/dmrg.py:65-112)
+# ---------------------------------------------------------------------------------------------------------
+@complex_aware
+def dmrg_right_blocks(state, operator):
+    """R_k[a, w, a'] = sum S_k[a,o,b] W_k[w,i,o,v] S_k[a',i,b'] R_{k+1}[b,v,b'] for k = n-1 .. 2 (dmrg.py:65-87; no conjugation, the
+    first state copy meets the operator's OUT leg): three GEMMs per site -- the `|` transfer contraction with an MPO in the middle."""
+    n = len(state)
+    blocks = [None] * n
+    R = ones_for(state[0], 1, 1, 1)
+    for k in range(n - 1, 1, -1):
+        S, W = state[k], operator[k]
+        O = _O(S)
+        a, d, b = S.shape
+        w, i, o, v = W.shape
+        # T1[(a,o), (v,b')] = sum_b S[(a,o), b] R[b, (v,b')]
+        T1 = O.matmul(S.reshape(a * d, b), R.reshape(b, -1))
+        bp = R.shape[2]
+        # T2[a, (w,i), b'] = sum_{(o,v)} W[(w,i), (o,v)] T1[a, (o,v), b']            batched over a
+        T2 = empty_for(S, a, w * i, bp)
+        O.gemm(W, T1, T2, M=w * i, N=bp, K=o * v, a_m=o * v, a_k=1, b_k=bp, b_n=1, c_m=bp, c_n=1,
+               batch=a, a_b=0, b_b=o * v * bp, c_b=w * i * bp)
+        # R_k[(a,w), a'] = sum_{(i,b')} T2[(a,w), (i,b')] S[a', (i,b')]
+        Sm = S.reshape(a, d * b)
+        R = O.matmul(T2.reshape(a * w, i * bp), Sm.t()).reshape(a, w, a)
+        blocks[k] = R
+    return blocks
+
+
+@complex_aware
+def dmrg_left_blocks(state, operator):
+    """L_k[b, v, b'] = sum L_{k-1}[a,w,a'] S_k[a,o,b] W_k[w,i,o,v] S_k[a',i,b'] for k = 0 .. n-3 (dmrg.py:90-112)."""
+    n = len(state)
+    blocks = [None] * n
+    L = ones_for(state[0], 1, 1, 1)
+    for k in range(n - 2):
+        S, W = state[k], operator[k]
+        O = _O(S)
+        a, d, b = S.shape
+        w, i, o, v = W.shape
+        ap = L.shape[2]
+        # T1[(w,a'), (o,b)] = sum_a L[a, (w,a')]^T S[a, (o,b)]
+        T1 = O.matmul(L.reshape(a, w * ap).t(), S.reshape(a, d * b))
+        # T2[a', (i,v), b] = sum_{(w,o)} W[w,i,o,v] T1[w, a', o, b]                       batched over a'
+        T2 = empty_for(S, ap, i * v, b)
+        O.gemm(W, T1, T2, M=i * v, N=b, K=w * o, a_m=(o * v, 1, v), a_k=(i * o * v, v, o), b_k=(ap * o * b, b, o), b_n=1, c_m=b, c_n=1,
+               batch=ap, a_b=0, b_b=o * b, c_b=i * v * b)
+        # G[(v,b), b'] = sum_{(a',i)} T2[a', i, v, b] S[a', i, b'] ;  L_k[b, v, b'] = G[v, b, b']
+        G = empty_for(S, v * b, b)
+        O.gemm(T2, S, G, M=v * b, N=b, K=ap * i, a_m=1, a_k=(i * v * b, v * b, i), b_k=b, b_n=1, c_m=b, c_n=1)
+        L = G.reshape(v, b, b).permute(1, 0, 2).contiguous()
+        blocks[k] = L
+    return blocks
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step (MPS:298-319, MPO:430-450)."""
     cores, l, n = [], 1, len(shapes)
