@@ -283,14 +283,14 @@ __device__ __forceinline__ unsigned pf_ld_acquire(const unsigned* p) {
 }
 
 __device__ __forceinline__ void pf_grid_barrier(unsigned* ctr, unsigned& target) {
+    // arrive with a release reduction, wait with acquire loads: the CTA barrier orders the other threads' stores before the release and
+    // their later loads after the acquire (all cross-CTA data is read through L2: ld.cg / cp.async.cg), so no separate fences are needed
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         for (unsigned spin = 0; pf_ld_acquire(ctr) < target; ++spin)
             if (spin > (1u << 23)) __trap();        // a lost CTA would otherwise hang the GPU
-        __threadfence();
     }
     __syncthreads();
 }
