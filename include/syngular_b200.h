@@ -156,6 +156,9 @@ int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
                                     double* info, void* stream);
 
+/* out[i] = sum_p parts[p * part_stride + i], i < count: the reduction after a split-K syn_gemm_f64 (partials as the batch index). */
+int syn_sum_parts_f64(const double* parts, int64_t part_stride, int nparts, double* out, int64_t count, void* stream);
+
 /* Q (m x q, contiguous) = orthonormal basis of the column space of A (m x q, row stride lda, full column rank) by the Newton-Schulz
  * phase of the same persistent kernel: Q = A (A^T A)^(-1/2).  For the truncation step `Q, R = np.linalg.qr(L, "complete"); Q[:, :q]`
  * (MPS:443-446, MPO:555-558) any orthonormal basis of span(L[:, :q]) is the same projection, and this one is GEMM-bound (0.2 ms against

@@ -648,14 +648,13 @@ def _w_sandwich_gemms(P1, Wk, a, i, b, l, o, r, D):
     return Z
 
 
-_ONES = {}
 
 
 def gram_with_environment(M2, E, b, r):
     """A = M2 E M2^T for an unfolding M2 (rows x (b,r), MPS-bond major) and an environment stored as in right_environments
     (rows (b,r), columns (r',b')).  M2 E is written with its columns permuted back to (b',r') on the fly (two-level C index),
     and the final rows x rows product, whose K = D is long and whose output is small, is split 8 ways along K so that it
-    fills the machine; the partial sums are added by one more (tiny) GEMM."""
+    fills the machine; the partial sums are added by a small reduction kernel."""
     rows, D = M2.shape
     ME = empty(rows, D)
     ops.gemm(M2, E, ME, M=rows, N=D, K=D, a_m=M2.stride(0), a_k=1, b_k=E.stride(0), b_n=1, c_m=D, c_n=(1, r, b))
@@ -666,12 +665,7 @@ def gram_with_environment(M2, E, b, r):
     part = empty(split, rows, rows)
     ops.gemm(ME, M2, part, M=rows, N=rows, K=kc, a_m=D, a_k=1, b_k=1, b_n=M2.stride(0), c_m=rows, c_n=1,
              batch=split, a_b=kc, b_b=kc, c_b=rows * rows)
-    ones = _ONES.get((split, M2.device))
-    if ones is None:
-        ones = _ONES[(split, M2.device)] = torch.ones((1, split), dtype=F64, device=M2.device)
-    A = empty(rows, rows)
-    ops.gemm(ones, part, A, M=1, N=rows * rows, K=split, a_m=split, a_k=1, b_k=rows * rows, b_n=1, c_m=rows * rows, c_n=1)
-    return A
+    return ops.sum_parts(part)
 
 
 CHOLESKY_MIN_N = 129          # multi-CTA Jacobi problems run on the shifted Cholesky factor of the Gram matrix (see eigh_gram); 0 = off

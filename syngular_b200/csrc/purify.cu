@@ -134,6 +134,15 @@ __global__ void __launch_bounds__(256) ns_poly_kernel(const double* __restrict__
     }
 }
 
+__global__ void __launch_bounds__(256) sum_parts_kernel(const double* __restrict__ parts, int64_t part_stride, int nparts, double* __restrict__ out,
+                                                        int64_t count) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += parts[p * part_stride + i];
+        out[i] = s;
+    }
+}
+
 // out[0] = max |H - I|   (single block)
 __global__ void __launch_bounds__(1024) purify_dev_kernel(const double* __restrict__ H, int k, double* __restrict__ out) {
     __shared__ double red[32];
@@ -642,6 +651,15 @@ extern "C" size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_ite
 extern "C" size_t syn_dominant_subspace_fused_workspace_f64(int n, int ne, int sp2_max, int ns_max) {
     if (n < 2 || ne < 1 || sp2_max < 1 || ns_max < 0) return 0;
     return syn::purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double);
+}
+
+// out[i] = sum_p parts[p * part_stride + i]: the reduction that follows a split-K GEMM (the rows x rows Gram product of the sweep)
+extern "C" int syn_sum_parts_f64(const double* parts, int64_t part_stride, int nparts, double* out, int64_t count, void* stream) {
+    using namespace syn;
+    SYN_REQUIRE(parts && out && nparts >= 1 && count >= 1 && count <= (int64_t)46340 * 46340, "syn_sum_parts_f64: bad arguments");
+    const int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
+    sum_parts_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(parts, part_stride, nparts, out, count);
+    return launch_status("sum_parts_kernel");
 }
 
 extern "C" int syn_orthonormalize_columns_fits(int m, int q) { return syn::ortho_fused_fits(m, q) ? 1 : 0; }

@@ -277,6 +277,16 @@ def env_sandwich(P1, W, Z, na, b):
     return Z
 
 
+def sum_parts(parts):
+    """out = parts.sum(0) for a contiguous (nparts, ...) stack of split-K partial products (csrc/purify.cu: sum_parts_kernel)."""
+    require_cuda_f64(parts)
+    assert parts.is_contiguous() and parts.dim() >= 2
+    out = torch.empty(tuple(parts.shape[1:]), dtype=torch.float64, device=parts.device)
+    count = out.numel()
+    check(lib.syn_sum_parts_f64(ptr(parts), _i64(count), _i32(parts.shape[0]), ptr(out), _i64(count), stream_ptr()), "syn_sum_parts_f64")
+    return out
+
+
 def env_mirror(E, na, L, ab):
     """Fill the strictly upper a-blocks of the symmetric environment E[(a,l),(l',a')] from the lower ones (csrc/env.cu), in place."""
     require_cuda_f64(E)

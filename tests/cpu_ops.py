@@ -199,6 +199,10 @@ def env_sandwich(P1, W, Z, na, b):
     return Z
 
 
+def sum_parts(parts):
+    return parts.sum(0)
+
+
 def env_mirror(E, na, L, ab):
     e = E.numpy().reshape(na, L, L, na)                            # [a][l][l'][a']
     blk = np.arange(na) // ab
@@ -245,7 +249,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "sum_parts", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 
