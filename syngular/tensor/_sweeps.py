@@ -333,7 +333,6 @@ def apply_gate(sites, gate, index, mode="compress", chi_max=None, cutoff=0.0):
     return out
 
 
-@complex_aware
 def mpo_apply_range(sites, op_sites, indices):
     """`MatrixProductOperator.apply(operator, indices)` with an MPO operator (MPO:582-626): one strided GEMM per site forms the
     product cores, a chain of GEMMs contracts the range, and the block is re-split by the qrt step keeping the target's right
@@ -417,6 +416,7 @@ def dmrg_left_blocks(state, operator):
     return blocks
 
 
+@complex_aware
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step (MPS:298-319, MPO:430-450)."""
     cores, l, n = [], 1, len(shapes)

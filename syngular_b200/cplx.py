@@ -220,19 +220,29 @@ def qrt(A, q, want_S=True):
     interleaved the real factorisation is the embedding of the complex one, so its even columns are the complex basis.
     When the leading columns are numerically dependent the reflectors built from rounding noise break that pairing (detected
     by the orthonormality check): dependent columns are then removed one at a time (the first flagged column is always
-    reliable), the basis is completed with fixed pseudo-random columns and factored again.  The completion directions are as
-    arbitrary as LAPACK's in the reference; span(A[:, :q]) is reproduced exactly."""
+    reliable), the basis is completed with fixed pseudo-random columns and factored again.  q > n (the reference's bond inflation by
+    the complete QR) is completed the same way.  The completion directions are as arbitrary as LAPACK's in the reference;
+    span(A[:, :q]) is reproduced exactly."""
     m, n = A.shape
     q = int(q)
-    if q > n:
-        raise NotImplementedError("complex qrt cannot inflate a bond (q = %d > %d columns)" % (q, n))
-    qk = min(q, m)
-    Aq = A[:, :q]
+    qk, qc = min(q, m), min(q, n)
+    Aq = A[:, :qc]
     if not Aq.is_contiguous():
         Aq = copy_strided(Aq)
-    Q, _ = _embedded_basis(Aq, qk, want_R=False)
+
+    def completed(cols):
+        """[A[:, cols] | fixed pseudo-random columns] with qk columns in all: q > n inflates the bond like the reference's complete QR
+        (the extra directions are arbitrary there too), and dropped dependent columns are replaced the same way."""
+        extra = qk - len(cols)
+        if extra <= 0 and len(cols) == qc:
+            return Aq
+        g = torch.Generator(device="cpu").manual_seed(1000 * m + q)
+        fill = torch.randn((2, m, max(extra, 0)), dtype=F64, generator=g).to(A.device)
+        return Cx(torch.cat([Aq.re[:, cols], fill[0]], dim=1).contiguous(), torch.cat([Aq.im[:, cols], fill[1]], dim=1).contiguous())
+
+    Q, _ = _embedded_basis(completed(list(range(min(qc, qk)))), qk, want_R=False)
     if float(gram_deviation(Q).item()) > ORTHO_TOL:
-        cols = list(range(q))
+        cols = list(range(qc))
         while cols:
             sub = Cx(Aq.re[:, cols].contiguous(), Aq.im[:, cols].contiguous())
             _, diag = _embedded_basis(sub, min(len(cols), m), want_R=True)
@@ -241,11 +251,7 @@ def qrt(A, q, want_S=True):
             if bad.numel() == 0 and len(cols) <= m:
                 break
             cols.pop(int(bad[0]) if bad.numel() else len(cols) - 1)
-        extra = qk - len(cols)
-        g = torch.Generator(device="cpu").manual_seed(1000 * m + q)
-        fill = torch.randn((2, m, max(extra, 0)), dtype=F64, generator=g).to(A.device)
-        full = Cx(torch.cat([Aq.re[:, cols], fill[0]], dim=1).contiguous(), torch.cat([Aq.im[:, cols], fill[1]], dim=1).contiguous())
-        Q, _ = _embedded_basis(full, qk, want_R=False)
+        Q, _ = _embedded_basis(completed(cols), qk, want_R=False)
         Q = polish_columns(Q)
     S = matmul(Q.h(), A) if want_S else None
     return Q, S

@@ -274,7 +274,6 @@ def _round_svd_numpy(cores, chi):
     return cores
 
 
-CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 
 def case_large_complex_bond_takes_the_projection_solver():
@@ -293,6 +292,35 @@ def case_large_complex_bond_takes_the_projection_solver():
     assert np.max(np.abs(Un.conj().T @ Un - np.eye(chi))) < 1e-12
     assert _rel(Un @ Un.conj().T, u[:, :chi] @ u[:, :chi].conj().T) < 1e-9
     assert abs(float(disc) - float(np.sum(s[chi:] ** 2))) < 1e-10 * float(np.sum(s ** 2))
+
+
+
+
+def case_mpo_products_and_decompose_with_complex_cores():
+    from oracle import ref_numpy as R
+    from syngular.tensor import MatrixProductOperator as MPO, MatrixProductState as MPS
+    from syngular.variational import DMRG
+    rng = np.random.default_rng(14)
+    a, b = _rand_chain(rng, (2, 3, 2), mpo=True), _rand_chain(rng, (3, 2, 3), mpo=True)
+    A, B = MPO.from_sites(a), MPO.from_sites(b)
+    Ar, Br = R.MPO.from_sites(a), R.MPO.from_sites(b)
+    C, Cr = A @ B, Ar @ Br                                   # site contraction + `>> min_bond` (MPO:278-289)
+    assert [tuple(s.shape) for s in C.sites] == [tuple(s.shape) for s in Cr.sites]
+    assert _rel(C.to_tensor(), R.to_dense(Cr.sites)) < RTOL
+    assert abs(C[(1, 0, 1, 1), (0, 1, 1, 0)][0, 0] - Cr[(1, 0, 1, 1), (0, 1, 1, 0)][0, 0]) < RTOL * np.max(np.abs(R.to_dense(Cr.sites)))
+    # TT decomposition of a dense complex tensor by the qrt step (MPS:298-319) reproduces it when the bonds are large enough
+    t = _crandn(rng, 2, 3, 2, 2)
+    X = MPS(t, bond_shape=(2, 6, 2)).decompose()
+    assert _rel(X.to_tensor(), t) < RTOL
+    assert _rel(X.to_tensor(), R.to_dense(R.MPS.dense(t, (2, 6, 2)).sites)) < RTOL
+    # three-layer transfer blocks with complex cores (no conjugation, like the reference)
+    xs = _rand_chain(rng, (2, 4, 2))
+    got = DMRG.right_blocks(A, MPS.from_sites(xs))
+    ref = R.dmrg_right_blocks(xs, a)
+    for g, r in zip(got, ref):
+        assert (g is None) == (r is None)
+        if r is not None:
+            assert _rel(g.cpu().numpy(), r) < RTOL
 
 
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
