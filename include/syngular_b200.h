@@ -150,7 +150,7 @@ int syn_dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int
 /* The same solver as ONE persistent cooperative kernel (one CTA per SM, iterates resident in L2, 32 x 32 DMMA tiles from a cp.async
  * ring, symmetric products computed on their lower tiles only, grid barrier per step).  The iteration counts adapt on the device:
  * SP2 stops two steps after tr(X - X^2) < 1e-11 ne (at most sp2_max steps), Newton-Schulz when max |U^T U - I| < 1e-13 (at most
- * ns_max).  Needs n and ne multiples of 64 (syn_dominant_subspace_fused_fits).  info as above, [7] = sp2 steps + 1000 * NS steps + 1e6 * leading lift steps. */
+ * ns_max).  Needs n and ne multiples of 32, n >= 128 (syn_dominant_subspace_fused_fits).  info as above, [7] = sp2 steps + 1000 * NS steps + 1e6 * leading lift steps. */
 size_t syn_dominant_subspace_fused_workspace_f64(int n, int ne, int sp2_max, int ns_max);
 int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
@@ -163,7 +163,7 @@ int syn_sum_parts_f64(const double* parts, int64_t part_stride, int nparts, doub
  * phase of the same persistent kernel: Q = A (A^T A)^(-1/2).  For the truncation step `Q, R = np.linalg.qr(L, "complete"); Q[:, :q]`
  * (MPS:443-446, MPO:555-558) any orthonormal basis of span(L[:, :q]) is the same projection, and this one is GEMM-bound (0.2 ms against
  * 1.2 ms for the cluster Householder kernel at 512 x 256).  info[4] = max |Q^T Q - I| at exit, info[7] = 1000 * steps; the caller falls
- * back to syn_qrt_f64 when it did not converge (rank-deficient columns).  m, q multiples of 64, q <= m. */
+ * back to syn_qrt_f64 when it did not converge (rank-deficient columns).  m, q multiples of 32, m >= 128, q <= m. */
 size_t syn_orthonormalize_columns_workspace_f64(int m, int q, int ns_max);
 int syn_orthonormalize_columns_fits(int m, int q);
 int syn_orthonormalize_columns_f64(const double* A, int64_t lda, int m, int q, int ns_max, double* Q, void* ws, size_t ws_bytes,

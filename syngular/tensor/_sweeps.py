@@ -714,7 +714,7 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
 # Bonds whose Gram matrix is at least this large take the spectral-projection solver (csrc/purify.cu) instead of Cholesky + Jacobi:
 # GEMM-bound (~1 ms at n = 512 against 6.3 ms), same kept subspace.  0 = off.  Needs a spectral gap at the cut, no cutoff, and
 # chi_max < n; otherwise (or when its own checks fail) the Jacobi path runs.
-PURIFY_MIN_N = 256
+PURIFY_MIN_N = 128
 PURIFY_SP2_ITERS = 52          # multi-launch variant: fixed counts
 PURIFY_NS_ITERS = 26
 PURIFY_SP2_MAX = 90            # fused kernel: upper limits (it stops by itself); 90 steps resolve gaps down to ~1e-12 |A|

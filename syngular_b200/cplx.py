@@ -25,7 +25,7 @@ from ._lib import SynError
 F64 = torch.float64
 C128 = torch.complex128
 JACOBI_MAX_N = 1024
-PURIFY_MIN_N = 256             # embedded bond problems at least this large try the spectral-projection solver first (0 = off)
+PURIFY_MIN_N = 128             # embedded bond problems at least this large try the spectral-projection solver first (0 = off)
 PURIFY_SP2_MAX = 90
 PURIFY_NS_MAX = 60
 PURIFY_MAX_LIFT = 14           # see syngular/tensor/_sweeps.py: cuts deeper in the spectrum go to the Jacobi route (when it fits)

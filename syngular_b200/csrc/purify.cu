@@ -306,7 +306,7 @@ __device__ __forceinline__ void pf_grid_barrier(unsigned* ctr, unsigned& target)
 
 // acc[i][j][0..1] of this warp's 16 x 16 sub-tile of  C(32 x 32) = R1[i0.., :K] R2[j0.., :K]^T ; warps 4..7 take the odd 32-wide
 // k-halves of every stage and are folded into warps 0..3 through shared memory at the end.  Returns true for the warps that own
-// the result.  K % PF_BK == 0, rows 16-byte aligned.
+// the result.  K % 32 == 0 (a last half stage is zero-filled), rows 16-byte aligned.
 __device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_t ld1, const double* __restrict__ R2, int64_t ld2, int i0, int j0, int K,
                                            double* smem, double (&acc)[2][2][2]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -322,11 +322,12 @@ __device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_
         for (int p = 0; p < 8; p++) {
             const int c = tid + PF_THREADS * p;              // 2048 16-byte chunks: operand | row | chunk
             const int op = c >> 10, row = (c >> 5) & 31, ch = c & 31;
-            const double* src = op ? (R2 + (int64_t)(j0 + row) * ld2 + k0 + ch * 2) : (R1 + (int64_t)(i0 + row) * ld1 + k0 + ch * 2);
-            cp_async<16>(sa + op * TILE + row * PF_LD + ch * 2, src, true);
+            const bool ok = k0 + ch * 2 < K;                 // K may end inside a stage (K % 32 == 0): the tail is zero-filled
+            const double* base = op ? (R2 + (int64_t)(j0 + row) * ld2) : (R1 + (int64_t)(i0 + row) * ld1);
+            cp_async<16>(sa + op * TILE + row * PF_LD + ch * 2, base + (ok ? k0 + ch * 2 : 0), ok);
         }
     };
-    const int KT = K / PF_BK;
+    const int KT = (K + PF_BK - 1) / PF_BK;
     __syncthreads();                                          // the previous user of the ring is done
 #pragma unroll
     for (int s = 0; s < PF_STAGES - 1; s++) {
@@ -597,15 +598,15 @@ static size_t purify_fused_ws_doubles(int n, int ne, int sp2_max, int ns_max) {
     return (size_t)2 * n * n + (size_t)4 * n * ne + (size_t)ne * ne + 4 + 2 * (sp2_max + 2) + (ns_max + 2) + 64;
 }
 
-static bool ortho_fused_fits(int m, int q) { return m % PF_BK == 0 && q % PF_BK == 0 && m >= 128 && q >= 64 && q <= m; }
+static bool ortho_fused_fits(int m, int q) { return m % PF_T == 0 && q % PF_T == 0 && m >= 128 && q >= 32 && q <= m; }
 
-static bool purify_fused_fits(int n, int ne) { return n % PF_BK == 0 && ne % PF_BK == 0 && n >= 128 && ne >= 64 && ne < n; }
+static bool purify_fused_fits(int n, int ne) { return n % PF_T == 0 && ne % PF_T == 0 && n >= 128 && ne >= 32 && ne < n; }
 
 int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, double* ws, size_t ws_bytes, double* info,
                                 cudaStream_t st, int ns_only = 0, int64_t ld0 = 0) {
     SYN_REQUIRE(A && U && ws && info, "syn_dominant_subspace_f64: null argument");
     SYN_REQUIRE(ns_only ? ortho_fused_fits(n, ne) : purify_fused_fits(n, ne),
-                "syn_dominant_subspace_f64 (fused): n and ne must be multiples of 64 (n=%d ne=%d)", n, ne);
+                "syn_dominant_subspace_f64 (fused): n and ne must be multiples of 32, n >= 128 (n=%d ne=%d)", n, ne);
     SYN_REQUIRE(sp2_max >= 1 && sp2_max <= 400 && ns_max >= 0 && ns_max <= 400, "syn_dominant_subspace_f64: bad iteration limits");
     SYN_REQUIRE(ws_bytes >= purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double), "syn_dominant_subspace_f64: workspace too small");
     SYN_REQUIRE(((((uintptr_t)ws) | ((uintptr_t)A)) & 15) == 0, "syn_dominant_subspace_f64: A and the workspace must be 16-byte aligned");

@@ -168,11 +168,11 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
 
 
 def dominant_subspace_fused_fits(n, ne):
-    return n % 64 == 0 and ne % 64 == 0 and n >= 128 and ne >= 64 and ne < n
+    return n % 32 == 0 and ne % 32 == 0 and n >= 128 and ne >= 32 and ne < n
 
 
 def orthonormalize_columns_fits(m, q):
-    return m % 64 == 0 and q % 64 == 0 and m >= 128 and q >= 64 and q <= m
+    return m % 32 == 0 and q % 32 == 0 and m >= 128 and q >= 32 and q <= m
 
 
 def orthonormalize_columns(A, ns_max=60):

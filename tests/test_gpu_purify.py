@@ -17,7 +17,7 @@ def _psd(rng, n, decay):
 
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("n,ne,decay", [(64, 32, 6.0), (256, 128, 10.0), (512, 256, 12.0), (512, 100, 8.0), (384, 256, 9.0), (512, 192, 20.0),
-                                        (1024, 512, 14.0), (128, 64, 3.0)])
+                                        (1024, 512, 14.0), (128, 64, 3.0), (128, 32, 4.0), (160, 96, 5.0), (288, 32, 8.0)])
 def test_dominant_subspace_matches_eigh(n, ne, decay, fused):
     from syngular_b200 import ops
     rng = np.random.default_rng(n + ne)
@@ -120,7 +120,7 @@ def test_symmetric_environment_build_matches_full_gemm():
         assert (a - b).abs().max().item() <= 1e-12 * b.abs().max().item()
 
 
-@pytest.mark.parametrize("m,q,cols", [(512, 256, 4096), (256, 128, 300), (1024, 64, 64), (128, 64, 200)])
+@pytest.mark.parametrize("m,q,cols", [(512, 256, 4096), (256, 128, 300), (1024, 64, 64), (128, 64, 200), (160, 96, 128), (256, 32, 40)])
 def test_polar_truncation_step_is_the_same_projection_as_householder(m, q, cols):
     """qrt_step through the fused Newton-Schulz kernel against numpy's QR of the leading columns (gauge-invariant: Q Q^T L)."""
     from syngular.tensor import _sweeps as sw
