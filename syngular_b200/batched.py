@@ -158,6 +158,20 @@ class BatchedMatrixProductState:
                 out.append(M.reshape(B, s, o, D))
                 break
             rows = s * o
+            right_dim = 1                                               # dimension of the space to the right of this bond
+            for wj in W[k + 1:]:
+                right_dim = min(right_dim * int(wj.shape[2]), 1 << 30)
+            keep = min(int(chi), rows, D, right_dim)
+            if keep == rows:
+                # nothing is truncated at this bond: every orthonormal basis of the whole space is a valid gauge -- identity cores,
+                # the unfolding itself is carried, no eigen-solve (ramp-up bonds; same rule as _sweeps.apply_round_dm)
+                eye = torch.eye(rows, dtype=F64, device=dev)
+                out.append(eye.expand(B, rows, rows).contiguous().reshape(B, s, o, rows))
+                Tn = empty(B, rows, r, b)
+                ops.gemm(eye, M, Tn, M=rows, N=D, K=rows, a_m=rows, a_k=1, b_k=D, b_n=1, c_m=r * b, c_n=(1, b, r),
+                         batch=B, a_b=0, b_b=rows * D, c_b=rows * r * b)
+                T = Tn
+                continue
             ME = empty(B, rows, D)                                     # columns permuted back to (b', r') on the fly
             ops.gemm(M, E[k + 1], ME, M=rows, N=D, K=D, a_m=D, a_k=1, b_k=D, b_n=1, c_m=D, c_n=(1, r, b),
                      batch=B, a_b=rows * D, b_b=D * D, c_b=rows * D)
@@ -166,10 +180,6 @@ class BatchedMatrixProductState:
             Bf, shift = ops.chol_upper(A)
             ops.jacobi_rows(Bf, null_rel=0.0)
             Ut, sigma, info, winfo = ops.jacobi_finalize(Bf, chi, rank_tol=0.0, sqrt_mode=2, shift=shift)
-            right_dim = 1                                               # dimension of the space to the right of this bond
-            for wj in W[k + 1:]:
-                right_dim = min(right_dim * int(wj.shape[2]), 1 << 30)
-            keep = min(int(chi), rows, D, right_dim)
             core = ops.copy_strided(Ut[:, :keep, :].transpose(1, 2))   # (B, rows, keep)
             out.append(core.reshape(B, s, o, keep))
             Tn = empty(B, keep, r, b)

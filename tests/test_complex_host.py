@@ -39,3 +39,37 @@ def test_real_golden_cases_through_the_emulated_kernels():
     be = backends.ProductBackend()
     for case in golden_cases.ALL_CASES:
         case(be)
+
+
+def test_truncation_step_host_logic_polar_and_fallback():
+    """qrt_step: large full-rank blocks take the polar orthonormalisation, dependent leading columns fall back to Householder (emulated
+    kernels: only the branch logic and the projection identity are checked here; the kernels run in tests/test_gpu_purify.py)."""
+    from syngular.tensor import _sweeps as sw
+    from syngular_b200 import ops
+    rng = np.random.default_rng(0)
+    L = rng.normal(size=(256, 300))
+    calls = {"polar": 0, "house": 0}
+    polar, house = ops.orthonormalize_columns, ops.qrt
+
+    def spy_polar(*a, **k):
+        calls["polar"] += 1
+        return polar(*a, **k)
+
+    def spy_house(*a, **k):
+        calls["house"] += 1
+        return house(*a, **k)
+    ops.orthonormalize_columns, ops.qrt = spy_polar, spy_house
+    try:
+        Q, S = sw.qrt_step(torch.from_numpy(L), 64)
+        assert calls == {"polar": 1, "house": 0}
+        qr, _ = np.linalg.qr(L[:, :64])
+        assert np.max(np.abs(Q.numpy() @ S.numpy() - qr @ (qr.T @ L))) < 1e-11
+        L2 = L.copy()
+        L2[:, 3] = 2.0 * L2[:, 1]
+        Q, S = sw.qrt_step(torch.from_numpy(L2), 64)
+        assert calls == {"polar": 2, "house": 1}
+        assert np.max(np.abs((Q.numpy() @ S.numpy())[:, :64] - L2[:, :64])) < 1e-11
+        Q, S = sw.qrt_step(torch.from_numpy(L[:100]), 40)          # too few rows: Householder directly
+        assert calls == {"polar": 2, "house": 2}
+    finally:
+        ops.orthonormalize_columns, ops.qrt = polar, house
