@@ -730,26 +730,32 @@ PURIFY_STATS = {"taken": 0, "fallback": 0}
 IDENTITY_WHEN_FULL = True      # bonds that keep their whole space skip the eigen-solve (gauge: identity core)
 
 
+def _projection_verdict(h, ne, rank_gap):
+    """Accept / reject the result of ops.dominant_subspace from its 8 info doubles (host copy): (ok, discarded weight)."""
+    tr, f2, kept_w, dev, tr_a, idem = h[0], h[1], h[2], h[4], h[5], h[6]
+    ok = (abs(tr - ne) < 1e-9 * ne and abs(f2 - ne) < 1e-9 * ne and abs(idem) < 1e-11 * ne and dev < 1e-12
+          and np.isfinite(h).all() and int(h[7]) // 1000000 <= (PURIFY_MAX_LIFT_RANK_GAP if rank_gap else PURIFY_MAX_LIFT))
+    return bool(ok), max(float(tr_a - kept_w), 0.0)
+
+
 def dominant_subspace(A, chi_max, rank_gap=False):
     """(U (n x chi_max) orthonormal, discarded weight) by spectral projection, or None when the iteration did not reach a projector
     of trace chi_max that is orthonormalised to 1e-12 (no gap at the cut: rank-deficient bonds) or the cut lies too deep in the
     spectrum for its normwise accuracy (see PURIFY_MAX_LIFT) -- one host read of 8 doubles."""
     U, info = ops.dominant_subspace(A, chi_max, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
-    h = info.cpu().numpy()
-    tr, f2, kept_w, dev, tr_a, idem = h[0], h[1], h[2], h[4], h[5], h[6]
-    ok = (abs(tr - chi_max) < 1e-9 * chi_max and abs(f2 - chi_max) < 1e-9 * chi_max and abs(idem) < 1e-11 * chi_max and dev < 1e-12
-          and np.isfinite(h).all() and int(h[7]) // 1000000 <= (PURIFY_MAX_LIFT_RANK_GAP if rank_gap else PURIFY_MAX_LIFT))
-    if not ok:
-        PURIFY_STATS["fallback"] += 1
-        return None
-    PURIFY_STATS["taken"] += 1
-    return U, max(float(tr_a - kept_w), 0.0)
+    ok, disc = _projection_verdict(info.cpu().numpy(), chi_max, rank_gap)
+    PURIFY_STATS["taken" if ok else "fallback"] += 1
+    return (U, disc) if ok else None
 
 
 def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
-    """`W @ X` + optimal (SVD) rounding by the density-matrix algorithm: right environments, then a left-to-right sweep that
-    diagonalises M E M^T (one-sided Jacobi) -- mathematically the truncation of round_svd(site_mpo_mps(...)) but every matrix
-    stays <= (chi d) x D.  Eigenvalues are squared singular values, so values below ~1e-8 sigma_0 are noise: rank_tol."""
+    """`W @ X` + optimal (SVD) rounding by the density-matrix algorithm: right environments, then a left-to-right sweep that finds the
+    dominant eigenspace of M E M^T at every bond -- mathematically the truncation of round_svd(site_mpo_mps(...)) but every matrix
+    stays <= (chi d) x D.  Eigenvalues are squared singular values, so values below ~1e-8 sigma_0 are noise: rank_tol.
+
+    The projection solver's verdict (8 doubles) is read ONE SITE LATE: its basis is used at once, the next site's kernels are queued, and
+    only then does the host look at the verdict -- the GPU never waits for the host.  A rejected bond (no gap at the cut, or the
+    accuracy guard) rolls the sweep back to that site, which is then solved by Cholesky + Jacobi."""
     n = len(X)
     E = right_environments(X, W)
     trunc = Truncation()
@@ -758,38 +764,63 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
     right_dim = [1] * (n + 1)                 # dimension of the physical space to the right of bond k: bounds the rank of that bond
     for k in range(n - 1, -1, -1):
         right_dim[k] = min(right_dim[k + 1] * int(W[k].shape[2]), 1 << 40)
-    for k in range(n - 1):
-        M = contract_carry(T, X[k], W[k])
-        s, o, D = M.shape
-        b, r = X[k].shape[2], W[k].shape[3]
-        M2 = M.reshape(s * o, D)
-        A = gram_with_environment(M2, E[k + 1], b, r)
+
+    def jacobi_site(A, M2, s, o, b, r):
         nA = s * o
-        # structural rank of the bond: when it is below chi_max nothing is truncated and the kept space is the range of A -- the
-        # projection solver then finds it at the (huge) gap between the last non-zero eigenvalue and the null space
-        ne = min(chi_max, D, right_dim[k + 1])
-        if IDENTITY_WHEN_FULL and cutoff == 0.0 and ne >= nA:
-            # nothing to truncate and (structurally) nothing rank-deficient: every orthonormal basis of the whole space is a valid gauge,
-            # so the core is the identity and the unfolding itself is carried -- no eigen-solve (ramp-up sites of a chain)
-            eye = torch.eye(nA, dtype=F64, device=A.device)
-            trunc.sigma.append(LazySpectrum(A, eye)); trunc.keep.append(nA); trunc.discarded.append(0.0)
-            out.append(eye.reshape(s, o, nA))
-            T = _carry_from(eye, M2, nA, b, r, transposed_basis=False)        # = M2 with its columns re-ordered to (r, b)
-            continue
-        if PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
-            got = dominant_subspace(A, ne, rank_gap=ne >= min(D, right_dim[k + 1]))
-            if got is not None:
-                U, disc = got
-                trunc.sigma.append(LazySpectrum(A, U)); trunc.keep.append(ne); trunc.discarded.append(disc)
-                out.append(U.reshape(s, o, ne))
-                T = _carry_from(U, M2, ne, b, r, transposed_basis=False)
-                continue
         if nA > 1024:
             raise NotImplementedError("density-matrix rounding needs chi*d <= 1024 (got %d)" % nA)
         Ut, sigma, info, winfo = eigh_gram(A, chi_max, cutoff, rank_tol)
         keep = int(info[0].item())
         trunc.sigma.append(sigma); trunc.keep.append(keep); trunc.discarded.append(winfo[0].item())
         out.append(ops.copy_strided(Ut[:keep].t()).reshape(s, o, keep))
-        T = _carry_from(Ut[:keep], M2, keep, b, r, transposed_basis=True)
+        return _carry_from(Ut[:keep], M2, keep, b, r, transposed_basis=True)
+
+    k = 0
+    pending = None                # (site, info on the device, target rank, rank_gap, carry before the site, slot in out / trunc)
+    while k < n - 1 or pending is not None:
+        queued = None
+        if k < n - 1:
+            M = contract_carry(T, X[k], W[k])
+            s, o, D = M.shape
+            b, r = X[k].shape[2], W[k].shape[3]
+            M2 = M.reshape(s * o, D)
+            A = gram_with_environment(M2, E[k + 1], b, r)
+            nA = s * o
+            # structural rank of the bond: when it is below chi_max nothing is truncated and the kept space is the range of A -- the
+            # projection solver then finds it at the (huge) gap between the last non-zero eigenvalue and the null space
+            ne = min(chi_max, D, right_dim[k + 1])
+            if IDENTITY_WHEN_FULL and cutoff == 0.0 and ne >= nA:
+                # nothing to truncate and (structurally) nothing rank-deficient: every orthonormal basis of the whole space is a valid
+                # gauge, so the core is the identity and the unfolding itself is carried -- no eigen-solve (ramp-up sites of a chain)
+                eye = torch.eye(nA, dtype=F64, device=A.device)
+                trunc.sigma.append(LazySpectrum(A, eye)); trunc.keep.append(nA); trunc.discarded.append(0.0)
+                out.append(eye.reshape(s, o, nA))
+                T = _carry_from(eye, M2, nA, b, r, transposed_basis=False)    # = M2 with its columns re-ordered to (r, b)
+            elif PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
+                U, info = ops.dominant_subspace(A, ne, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
+                queued = (k, info, ne, ne >= min(D, right_dim[k + 1]), T, len(out))
+                trunc.sigma.append(LazySpectrum(A, U)); trunc.keep.append(ne); trunc.discarded.append(None)
+                out.append(U.reshape(s, o, ne))
+                T = _carry_from(U, M2, ne, b, r, transposed_basis=False)
+            else:
+                T = jacobi_site(A, M2, s, o, b, r)
+            k += 1
+        if pending is not None:
+            pk, pinfo, pne, pgap, pT, slot = pending
+            ok, disc = _projection_verdict(pinfo.cpu().numpy(), pne, pgap)
+            PURIFY_STATS["taken" if ok else "fallback"] += 1
+            if ok:
+                trunc.discarded[slot] = disc
+            else:
+                # roll back to site pk: drop its speculative result and whatever was queued after it, solve it with Jacobi
+                del out[slot:], trunc.sigma[slot:], trunc.keep[slot:], trunc.discarded[slot:]
+                M = contract_carry(pT, X[pk], W[pk])
+                s, o, D = M.shape
+                b, r = X[pk].shape[2], W[pk].shape[3]
+                M2 = M.reshape(s * o, D)
+                T = jacobi_site(gram_with_environment(M2, E[pk + 1], b, r), M2, s, o, b, r)
+                k = pk + 1
+                queued = None
+        pending = queued
     out.append(contract_carry(T, X[-1], W[-1]))
     return out, trunc

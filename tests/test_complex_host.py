@@ -73,3 +73,44 @@ def test_truncation_step_host_logic_polar_and_fallback():
         assert calls == {"polar": 2, "house": 2}
     finally:
         ops.orthonormalize_columns, ops.qrt = polar, house
+
+
+@pytest.mark.parametrize("fail_calls", [(1,), (0, 1), (3,), (2, 5), tuple(range(20))])
+def test_density_matrix_sweep_rolls_back_a_rejected_projection(fail_calls):
+    """apply_round_dm reads the projection solver's verdict one site late; a rejected bond must roll the sweep back to that site and
+    redo it (and everything queued after it) with the Jacobi path -- same state as the oracle whichever calls are rejected."""
+    import bench
+    from oracle import ref_numpy as R, svd_numpy as S
+    from syngular.tensor import _sweeps as sw
+    from syngular_b200 import ops
+    X, W = bench.make_chain(5, n=14, chi=16, chiw=4)
+    ref, spectra, discarded = S.apply_round_svd(X, W, 16)
+    dense_ref = R.to_dense(ref)
+    real = ops.dominant_subspace
+    calls = [0]
+
+    def flaky(*a, **k):
+        U, info = real(*a, **k)
+        if calls[0] in fail_calls:
+            info = info.clone()
+            info[0] += 0.5                                     # trace off: the verdict rejects this bond
+        calls[0] += 1
+        return U, info
+    saved = sw.PURIFY_MIN_N
+    ops.dominant_subspace = flaky
+    try:
+        sw.PURIFY_MIN_N = 16
+        sw.PURIFY_STATS.update(taken=0, fallback=0)
+        out, trunc = sw.apply_round_dm([sw.as_core(c) for c in X], [sw.as_core(c) for c in W], 16)
+        stats = dict(sw.PURIFY_STATS)
+    finally:
+        ops.dominant_subspace = real
+        sw.PURIFY_MIN_N = saved
+    assert stats["fallback"] >= 1 and [tuple(c.shape) for c in out] == [c.shape for c in ref]
+    got = R.to_dense([c.numpy() for c in out])
+    assert np.max(np.abs(got - dense_ref)) < 1e-10 * np.max(np.abs(dense_ref))
+    sig, keep, disc = trunc.host()
+    assert len(keep) == len(ref) - 1 and all(d is not None for d in disc)
+    for k in range(len(ref) - 1):
+        assert keep[k] == ref[k].shape[-1]
+        assert abs(disc[k] - discarded[k]) < 1e-10 * spectra[k][0] ** 2 * len(spectra[k])
