@@ -13,9 +13,15 @@ optimal (SVD) truncation.  Prints ONE JSON line (rank 0).  See DESIGN.md section
   roofline  the strided DMMA GEMM (dominant kernel): algorithmic FLOPs of all its launches in one sweep / their summed
             CUDA-event durations, against the cuBLAS DGEMM rate measured in the same process (MEASURED_PEAKS.json
             has no FP64 entry)
-  cpu_baseline / --impl reference
-            the oracle's textbook apply + right-QR + left-SVD rounding (numpy/LAPACK, all host threads) on a bounded
-            sample of plateau sites, scaled to a sweep by the textbook flop model
+  cpu_baseline
+            ONE full C2 sweep of the like-for-like CPU algorithm (oracle/svd_numpy.StructuredDensityMatrixSweep: the same
+            density-matrix contraction sequence the GPU runs, numpy/BLAS/LAPACK on all host threads), measured, no scaling;
+            the GPU result is compared with it in the same run (config.parity_vs_cpu_sweep)
+  --impl reference
+            the same CPU sweep, cut into K consecutive chunks of its 127 unit operations: every step is a bounded sample
+            (one chunk), the K steps together are ONE complete sweep on real data, value = 1 / (sum of the step times)
+  --workload c4 | c5
+            the batched configs of BASELINE.json as the headline line (states/s, samples/s), batch-sharded over the ranks
 """
 import argparse
 import json
@@ -51,70 +57,43 @@ def make_chain(seed, n=N_SITES, d=D_PHYS, chi=CHI, chiw=CHI_W):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# flop models: only what the executed algorithm needs
+# CPU arm: the like-for-like density-matrix sweep of the oracle, MEASURED at full size (no flop-model scaling anywhere)
 # ---------------------------------------------------------------------------------------------------------------------
-def textbook_site_flops(a, l, i, o, b, r, s_left):
-    """Flops of the textbook algorithm at one site: materialise, absorb the right carry, QR of the right unfolding (factor +
-    form Q), absorb the left carry, SVD of the left unfolding (dominant terms; LAPACK conventions)."""
-    Dl, Dr = a * l, b * r
-    mat = 2.0 * a * l * i * o * b * r
-    absorb_r = 2.0 * (Dl * o) * Dr * Dr
-    m, n = o * Dr, Dl
-    k = min(m, n)
-    qr = 2.0 * (2.0 * m * n * k - (2.0 / 3.0) * k ** 3) if m >= n else 2.0 * (2.0 * n * m * k - (2.0 / 3.0) * k ** 3)
-    absorb_l = 2.0 * s_left * k * (o * Dr)
-    rows = s_left * o
-    p, q = max(rows, Dr), min(rows, Dr)
-    svd = 4.0 * p * q * q + 22.0 * q ** 3               # thin SVD with both factors (Golub & Van Loan)
-    return mat + absorb_r + qr + absorb_l + svd
-
-
-def chain_dims(X, W, chi):
-    dims, s = [], 1
-    for x, w in zip(X, W):
-        a, i, b = x.shape
-        l, _, o, r = w.shape
-        dims.append((a, l, i, o, b, r, s))
-        s = min(chi, s * o, b * r)
-    return dims
-
-
-# ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: oracle textbook algorithm on a bounded sample
-# ---------------------------------------------------------------------------------------------------------------------
-def cpu_textbook_sample(X, W, chi, sites):
-    """Run the textbook steps at FULL size on `sites` and return (seconds, flops of the sample by the model above).
-    The carries entering a site are replaced by identity-like matrices of the right shape: every step is a dense
-    BLAS/LAPACK call whose cost does not depend on the data."""
-    from oracle import ref_numpy as R
-    dims = chain_dims(X, W, chi)
+def cpu_full_sweep(X, W, chi):
+    """One complete C2 sweep on the host cores: (seconds, cores, spectra, discarded)."""
+    from oracle import svd_numpy as S
     t0 = time.perf_counter()
-    flops = 0.0
-    for k in sites:
-        a, l, i, o, b, r, s = dims[k]
-        C = R.site_mpo_mps(X[k], W[k])                                  # K1: (Dl, o, Dr)
-        Dl, Dr = C.shape[0], C.shape[2]
-        U = np.eye(Dr)
-        C2 = (C.reshape(Dl * o, Dr) @ U.T).reshape(Dl, o * Dr)          # absorb the carry coming from the right
-        V, Un = np.linalg.qr(C2.T)                                      # right-QR step (ref_numpy.right_orthonormalize)
-        carry = np.eye(s, V.shape[1])
-        M = (carry @ V.T).reshape(s * o, Dr)                            # absorb the carry coming from the left
-        Uu, S, Vt = np.linalg.svd(M, full_matrices=False)               # left-SVD step (svd_numpy.round_svd)
-        keep = min(chi, len(S))
-        _ = S[:keep, None] * Vt[:keep]
-        flops += textbook_site_flops(a, l, i, o, b, r, s)
-    return time.perf_counter() - t0, flops
+    sweep = S.StructuredDensityMatrixSweep(X, W, chi)
+    for op in sweep.operations():
+        sweep.run(op)
+    return time.perf_counter() - t0, sweep.out, sweep.spectra, sweep.discarded
 
 
-def cpu_sweeps_per_s(X, W, chi, sites, repeats=1):
-    dims = chain_dims(X, W, chi)
-    total = sum(textbook_site_flops(*d) for d in dims)
-    best, fl = None, None
-    for _ in range(repeats):
-        sec, fl = cpu_textbook_sample(X, W, chi, sites)
-        best = sec if best is None else min(best, sec)
-    est = best * total / fl
-    return 1.0 / est, best, total, fl
+def balanced_chunks(costs, k):
+    """Cut a list of costs into k consecutive chunks of roughly equal total cost (boundaries only; never scales a timing)."""
+    k = max(1, min(k, len(costs)))
+    total, bounds, acc, nxt = float(sum(costs)), [0], 0.0, 1
+    for idx, c in enumerate(costs):
+        acc += c
+        while nxt < k and acc >= total * nxt / k and len(costs) - (idx + 1) >= k - nxt:
+            bounds.append(idx + 1)
+            nxt += 1
+    bounds += [len(costs)] * (k + 1 - len(bounds))
+    return [(bounds[j], bounds[j + 1]) for j in range(k)]
+
+
+def ncu_traffic():
+    """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, parsed from an
+    `ncu --set full` capture by tools/ncu_traffic.py into profiles/gemm_traffic.json (committed beside the .txt summary).  It cannot
+    be measured inside a timed run (a number taken under a profiler is never a bench value), so it is read from that file with its
+    provenance -- or null when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return {"traffic": float(t["dram_bytes"]), "traffic_note": "%s; algorithmic bytes of that launch: %.4g" % (t["source"], t["algorithmic_bytes"])}
+    except Exception:
+        return {"traffic": None, "traffic_note": "no ncu capture parsed (profiles/gemm_traffic.json absent)"}
 
 
 def host_threads():
@@ -173,30 +152,41 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """CPU arm: ONE complete sweep of the like-for-like algorithm on all host threads, cut into `steps` consecutive chunks."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     use_all_host_threads()
+    from oracle import svd_numpy as S
     X, W = make_chain(2)
-    sites = [31]                                         # one plateau site per step (a few seconds of LAPACK)
-    for _ in range(args.warmup):
-        cpu_textbook_sample(X, W, CHI, sites)
-    dims = chain_dims(X, W, CHI)
-    total = sum(textbook_site_flops(*d) for d in dims)
-    secs, fl = [], None
-    for _ in range(args.steps):
-        s, fl = cpu_textbook_sample(X, W, CHI, sites)
-        secs.append(s)
-    per_sweep = float(np.mean(secs)) * total / fl
-    value = 1.0 / per_sweep
-    sample = ("oracle textbook steps (materialise product core, QR of its right unfolding + carry GEMM, SVD of the left unfolding "
-              "+ carry GEMM; numpy/LAPACK) at full size on plateau site 31 per step, scaled to the 64-site sweep by the "
-              "textbook flop model (x%.1f)" % (total / fl))
+    # warm-up: the BLAS/LAPACK thread pools on the cheap tail of the chain (environments of the last sites), then start over
+    for _ in range(max(args.warmup, 1)):
+        warm = S.StructuredDensityMatrixSweep(X, W, CHI)
+        for op in warm.operations()[:8]:
+            warm.run(op)
+    sweep = S.StructuredDensityMatrixSweep(X, W, CHI)
+    ops_list = sweep.operations()
+    chunks = balanced_chunks([sweep.op_flops(op) for op in ops_list], args.steps)
+    secs = []
+    for lo, hi in chunks:
+        t0 = time.perf_counter()
+        for op in ops_list[lo:hi]:
+            sweep.run(op)
+        secs.append(time.perf_counter() - t0)
+    secs += [0.0] * (args.steps - len(secs))             # more steps than unit operations: the surplus steps are empty
+    total = float(sum(secs))
+    value = 1.0 / total
+    sample = ("ONE complete C2 sweep (all 64 sites: 63 environment updates + 64 truncation steps on real data) of "
+              "oracle/svd_numpy.StructuredDensityMatrixSweep, cut into %d consecutive chunks = the %d timed steps (%.1f s in all, "
+              "longest step %.1f s); value = 1 sweep / total measured time, nothing is extrapolated" % (len(chunks), args.steps, total, max(secs)))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_sweep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "algorithm": "textbook right-QR + left-SVD rounding of the materialised product (oracle/svd_numpy.py)",
-                   "note": "the reference has no SVD rounding and cannot run d=2 chains with dim>2 (SURVEY fact 4): this is the oracle port"},
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "algorithm": "density-matrix SVD rounding through the (X, W) structure -- the same contraction sequence the GPU arm "
+                                                     "executes (oracle/svd_numpy.py), numpy + BLAS/LAPACK eigh",
+                   "step": "1/%d of one sweep (consecutive unit operations); steps x ms_per_step = one whole measured sweep" % args.steps,
+                   "note": "the reference has no SVD rounding and cannot run d=2 chains with dim>2 (SURVEY fact 4): this is the oracle port",
+                   "discarded_weight_total": float(sum(sweep.discarded))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -427,21 +417,29 @@ def run_ours(args):
         peak = 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
         achieved = g_fl / (g_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": 356.5e6,
-                    "traffic_note": "dram__bytes_read+write of ONE launch of the largest GEMM of the sweep (512 x 65536 x 256: 402.7 MB algorithmic), "
-                                    "ncu --set full capture profiles/r01_gemm_p1_ncu_summary.txt; `achieved` aggregates all GEMM launches of a sweep",
+                    "frac": achieved / peak, **ncu_traffic(),
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this process (MEASURED_PEAKS.json has no FP64 entry); DMMA pipe microbench: 37.1",
                     "launches_per_sweep": len(prof), "flops_per_sweep": g_fl, "algorithmic_bytes_per_sweep": g_by,
                     "kernel_ms_per_sweep": g_ms, "share_of_step": g_ms / (ms / args.steps),
                     "profiled_sweep_ms": sweep_ms,
                     "share_note": "kernel time of one extra sweep with CUDA events around every GEMM launch, over the timed ms_per_step"}
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu:
+            # ONE full sweep of the like-for-like CPU algorithm on the host cores (measured, not scaled), and the GPU result
+            # checked against it: per-bond discarded weights, the norm, and the overlap of the two rounded states
             use_all_host_threads()
-            v, sec, total, fl = cpu_sweeps_per_s(Xh, Wh, CHI, [31, 32])
-            cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                   "sample": "oracle textbook apply + right-QR + left-SVD steps at full size on plateau sites 31-32 (%.1f s), scaled to the "
-                             "64-site sweep by the textbook flop model (x%.1f)" % (sec, total / fl)}
+            sec, cpu_out, cpu_spec, cpu_disc = cpu_full_sweep(Xh, Wh, CHI)
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                   "sample": "ONE complete C2 sweep (all 64 sites) of oracle/svd_numpy.StructuredDensityMatrixSweep -- the same density-matrix "
+                             "contraction sequence the GPU runs, numpy + BLAS/LAPACK on all host threads: %.1f s measured, nothing scaled" % sec}
+            out_g, trunc_g = step_device()
+            _, keep_g, disc_g = trunc_g.host()
+            ref = [torch.from_numpy(np.ascontiguousarray(c)).to(dev) for c in cpu_out]
+            n_gg = float(sw.overlap(out_g, out_g).item()); n_cc = float(sw.overlap(ref, ref).item()); n_gc = float(sw.overlap(out_g, ref).item())
+            parity = {"norm2_rel_diff": abs(n_gg - n_cc) / n_cc, "state_rel_dist2": abs(n_gg + n_cc - 2.0 * n_gc) / n_cc,
+                      "discarded_weight_max_abs_diff_over_norm2": float(max(abs(a - b) for a, b in zip(disc_g, cpu_disc)) / n_cc),
+                      "kept_ranks_equal": [int(k) for k in keep_g] == [min(CHI, len(sp)) for sp in cpu_spec]}
+            del ref, cpu_out
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -449,7 +447,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "rounding": "SVD truncation by the density-matrix algorithm (Gram environments; dominant eigenspace of every bond by the fused SP2 spectral-projection kernel, one-sided Jacobi below 256 or without a gap)",
                        "l2": "inputs larger than L2: 63 right environments of up to 134 MB (8.5 GB) are streamed every sweep",
                        "multi_gpu": "replicas only: one independent chain per rank, no collective on the data path",
-                       "left_gram_err_site20": gram_err},
+                       "left_gram_err_site20": gram_err, "parity_vs_cpu_sweep": parity},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "syn.mul(W, X, mode='optimized', bond=256) on pinned host cores, result cores copied back"},

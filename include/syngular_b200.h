@@ -99,10 +99,13 @@ int syn_identity_deviation_f64(const double* X, int n, double* out, void* stream
  * info[2*b] = kept rank, winfo[2*b] = discarded weight sum_{k>=kept} sigma_k^2, winfo[2*b+1] = sigma_0.
  * sqrt_mode = 1 when G was a Gram matrix M E M^T (rows are lambda_i u_i^T, sigma_i = sqrt(lambda_i));
  * sqrt_mode = 2 when G was the factor of syn_chol_upper_f64 (rows are sqrt(lambda_i + shift) q_i^T, sigma_i = sqrt(lambda_i));
- * shift: device array (one per problem) written by syn_chol_upper_f64 (read only when sqrt_mode = 2; may be NULL otherwise). */
+ * shift: device array (one per problem) written by syn_chol_upper_f64 (read only when sqrt_mode = 2; may be NULL otherwise).
+ * ctrl / max_sweeps: the control buffer and sweep limit of the syn_jacobi_rows_f64 call that produced G (or NULL / 0).  With it,
+ * info[2*b+1] = n when that problem's convergence vote passed and -n when the rows kernel ran out of sweeps first (the rows are
+ * then not orthogonal to working precision: call syn_jacobi_rows_f64 on the same G again -- it resumes -- and finalize again). */
 int syn_jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs,
                             double* sigma, int64_t sbs, int* info, double* winfo, int chi_max, double cutoff,
-                            double rank_tol, int sqrt_mode, const double* shift, void* stream);
+                            double rank_tol, int sqrt_mode, const double* shift, const void* ctrl, int max_sweeps, void* stream);
 /* Shifted Cholesky factor of a symmetric PSD Gram matrix (the M E M^T of the density-matrix rounding; finished form of the
  * reference's MATMUL_MODE "opti" branch, matrix_product_operator.py:193-260, whose np.linalg.eigh at :228 this pipeline replaces):
  *   G (batch x n x n, row-major ld, batch stride bs, overwritten when n > 128)  ->  B (row-major ldb, batch stride bbs) upper

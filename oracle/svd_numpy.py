@@ -92,46 +92,84 @@ def apply_round_density_matrix(X, W, chi_max, cutoff=0.0):
     return out, spectra, discarded
 
 
-def apply_round_density_matrix_structured(X, W, chi_max, cutoff=0.0):
-    """Same algorithm as apply_round_density_matrix, with every contraction done through the (X, W) structure so that no
-    product core (D x d x D) is formed -- the exact sequence of contractions the CUDA fast path executes, in numpy/BLAS.
-    Used by bench.py as the like-for-like CPU timing of the algorithm the GPU runs."""
-    n = len(X)
-    E = [None] * (n + 1)
-    E[n] = np.ones((1, 1))
-    for k in range(n - 1, 0, -1):
-        Xk, Wk = X[k], W[k]
+class StructuredDensityMatrixSweep:
+    """apply_round_density_matrix, with every contraction done through the (X, W) structure so that no product core
+    (D x d x D) is formed -- the exact sequence of contractions the CUDA fast path executes, in numpy/BLAS -- and cut into its
+    2n - 1 unit operations so that a caller can time any contiguous part of ONE real sweep:
+
+        env_step(k)   k = n-1 .. 1   right environment E[k] from E[k+1]            (phase 1, right to left)
+        site_step(k)  k = 0 .. n-1   carry . C_k, Gram matrix, eigh, truncation    (phase 2, left to right)
+
+    `operations()` lists them in execution order; running all of them IS the sweep (apply_round_density_matrix_structured
+    below does exactly that).  bench.py times this on the host cores, whole (cpu_baseline) or in K consecutive chunks
+    (--impl reference), and tests/test_gpu_fullsize.py compares the CUDA sweep with it at BASELINE configs[1]'s full size."""
+
+    def __init__(self, X, W, chi_max, cutoff=0.0):
+        self.X, self.W, self.chi_max, self.cutoff = X, W, chi_max, cutoff
+        self.n = len(X)
+        self.E = [None] * (self.n + 1)
+        self.E[self.n] = np.ones((1, 1))
+        self.carry = np.ones((1, 1, 1))                                 # (s, a, l)
+        self.out, self.spectra, self.discarded = [], [], []
+
+    def operations(self):
+        return [("env", k) for k in range(self.n - 1, 0, -1)] + [("site", k) for k in range(self.n)]
+
+    def run(self, op):
+        kind, k = op
+        (self.env_step if kind == "env" else self.site_step)(k)
+
+    def op_flops(self, op):
+        """Dominant-term flop count of one unit operation (used only to balance chunks of a sweep, never to scale a timing)."""
+        kind, k = op
+        a, i, b = self.X[k].shape
+        l, _, o, r = self.W[k].shape
+        D, Dl = b * r, a * l
+        if kind == "env":
+            return 2.0 * a * i * b * r * D + 2.0 * l * o * a * D * i * r + 2.0 * l * a * b * l * i * o * r + 2.0 * Dl * Dl * i * b
+        s = min(self.chi_max, 2 ** min(k, 40))
+        return 2.0 * s * a * l * i * b + 2.0 * s * o * D * D + 2.0 * (s * o) ** 2 * D + 10.0 * (s * o) ** 3
+
+    def env_step(self, k):
+        Xk, Wk = self.X[k], self.W[k]
         a, i, b = Xk.shape
         l, _, o, r = Wk.shape
-        En = E[k + 1].reshape(b, r, b * r)
+        En = self.E[k + 1].reshape(b, r, b * r)
         P1 = np.tensordot(Xk, En, axes=(2, 0))                         # (a, i, r, y)
         P2 = np.tensordot(Wk, P1, axes=([1, 3], [1, 2]))               # (l, o, a, y)
         P2 = P2.reshape(l, o, a, b, r)
         Z = np.tensordot(P2, Wk, axes=([1, 4], [2, 3]))                # (l, a, b', l', i')
         Ek = np.tensordot(Z, Xk, axes=([4, 2], [1, 2]))                # (l, a, l', a')
-        E[k] = Ek.transpose(1, 0, 3, 2).reshape(a * l, a * l)
-    carry = np.ones((1, 1, 1))                                          # (s, a, l)
-    out, spectra, discarded = [], [], []
-    for k in range(n):
-        Xk, Wk = X[k], W[k]
+        self.E[k] = Ek.transpose(1, 0, 3, 2).reshape(a * l, a * l)
+
+    def site_step(self, k):
+        Xk, Wk = self.X[k], self.W[k]
         a, i, b = Xk.shape
         l, _, o, r = Wk.shape
-        T1 = np.tensordot(carry, Xk, axes=(1, 0))                      # (s, l, i, b)
+        T1 = np.tensordot(self.carry, Xk, axes=(1, 0))                 # (s, l, i, b)
         M = np.tensordot(T1, Wk, axes=([1, 2], [0, 1]))                # (s, b, o, r)
         M = M.transpose(0, 2, 1, 3)                                    # (s, o, b, r)
         s = M.shape[0]
-        if k == n - 1:
-            out.append(M.reshape(s, o, b * r))
-            break
+        if k == self.n - 1:
+            self.out.append(M.reshape(s, o, b * r))
+            return
         M2 = M.reshape(s * o, b * r)
-        A = M2 @ E[k + 1] @ M2.T
+        A = M2 @ self.E[k + 1] @ M2.T
         A = 0.5 * (A + A.T)
         lam, U = np.linalg.eigh(A)
         lam, U = lam[::-1], U[:, ::-1]
         S = np.sqrt(np.clip(lam, 0.0, None))
-        keep = keep_count(S, chi_max, cutoff)
-        spectra.append(S.copy())
-        discarded.append(float(np.sum(S[keep:] ** 2)))
-        out.append(U[:, :keep].reshape(s, o, keep))
-        carry = (U[:, :keep].T @ M2).reshape(keep, b, r)
-    return out, spectra, discarded
+        keep = keep_count(S, self.chi_max, self.cutoff)
+        self.spectra.append(S.copy())
+        self.discarded.append(float(np.sum(S[keep:] ** 2)))
+        self.out.append(U[:, :keep].reshape(s, o, keep))
+        self.carry = (U[:, :keep].T @ M2).reshape(keep, b, r)
+        self.E[k + 1] = None                                           # consumed: release the host memory
+
+
+def apply_round_density_matrix_structured(X, W, chi_max, cutoff=0.0):
+    """The whole structured sweep (see StructuredDensityMatrixSweep): returns (cores, spectra, discarded) like the others."""
+    sweep = StructuredDensityMatrixSweep(X, W, chi_max, cutoff)
+    for op in sweep.operations():
+        sweep.run(op)
+    return sweep.out, sweep.spectra, sweep.discarded

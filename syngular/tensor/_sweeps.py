@@ -520,8 +520,7 @@ class LazySpectrum:
         if self._sigma is None:
             T = ops.matmul(self.U.t(), ops.matmul(self.A, self.U))
             T = ops.copy_strided(T)
-            ops.jacobi_rows(T, null_rel=0.0)
-            _, sigma, _, _ = ops.jacobi_finalize(T, T.shape[0], 0.0, rank_tol=0.0, sqrt_mode=1)
+            _, sigma, _, _ = ops.jacobi_solve(T, T.shape[0], 0.0, rank_tol=0.0, sqrt_mode=1, null_rel=0.0)
             self._sigma, self.A, self.U = sigma, None, None
         return self._sigma
 
@@ -556,15 +555,13 @@ def _svd_basis(M, chi_max, cutoff, trunc):
         return core2d, keep
     if m <= c:
         G = ops.qr_r(M.t())                                 # R factor of M^T (m x m); rows rotate to sigma_i u_i^T
-        ops.jacobi_rows(G)
-        Ut, sigma, info, winfo = ops.jacobi_finalize(G, chi_max, cutoff, rank_tol=1e-14)
+        Ut, sigma, info, winfo = ops.jacobi_solve(G, chi_max, cutoff, rank_tol=1e-14)
         keep = int(info[0].item())
         core2d = ops.copy_strided(Ut[:keep].t())
     else:
         Gt = empty(c, c)
         Q1, _ = ops.qrt(M, c, S=Gt.t())                     # Gt = R1^T ; rows rotate to sigma_i u1_i^T
-        ops.jacobi_rows(Gt)
-        Ut, sigma, info, winfo = ops.jacobi_finalize(Gt, chi_max, cutoff, rank_tol=1e-14)
+        Ut, sigma, info, winfo = ops.jacobi_solve(Gt, chi_max, cutoff, rank_tol=1e-14)
         keep = int(info[0].item())
         core2d = ops.matmul(Q1, Ut[:keep].t())
     trunc.sigma.append(sigma)
@@ -617,7 +614,7 @@ def right_environments(X, W):
         # E[(a,l),(l',a')] = sum_{(i',b')} Z[(a,l), l', (i',b')] X[a',(i',b')]        batch over l'
         Ek = empty(a * l, l * a)
         ab = ENV_SYMMETRIC_BLOCK
-        if ab and a % ab == 0 and a >= 2 * ab:
+        if ab and a % ab == 0 and a >= 2 * ab and l * l <= 65535:      # env_mirror launches gridDim.z = l * l
             # E is symmetric under (a,l) <-> (a',l'): form only the a-blocks on and below the diagonal (one GEMM per block row,
             # N grows with the block index), then mirror the rest -- 62.5 % of the flops at four blocks
             for p in range(a // ab):
@@ -674,7 +671,8 @@ PRECONDITION_MIN_N = 0        # FP32-preconditioned eigen-solver for Gram matric
 
 def eigh_gram(A, chi_max, cutoff, rank_tol):
     """Eigen-decomposition of a symmetric PSD matrix A (n x n, overwritten) for the density-matrix rounding:
-    returns (Ut, sigma, info, winfo) like jacobi_finalize(sqrt_mode=True) -- rows of Ut are the eigenvectors, sorted.
+    returns (Ut, sigma, info, winfo) like ops.jacobi_solve(sqrt_mode=True) -- rows of Ut are the eigenvectors, sorted; `info` is on
+    the host and the solve has been checked for convergence (a non-converged Jacobi is resumed, never truncated on).
 
     Large problems are preconditioned in FP32: an FP32 Jacobi pass (cheap rounds) gives an approximate eigenbasis U0; two
     Newton-Schulz steps U <- U (1.5 I - 0.5 U^T U) (FP64 GEMMs) make it orthonormal to 1e-15; A' = U A U^T is then diagonal to
@@ -691,8 +689,7 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
         # Jacobi on the rows of B = L^T, G + delta I = L L^T: works on a matrix similar to G instead of G^2 -- 10 sweeps instead of
         # 13 on the C2 plateau, 15 instead of 27 on its rank-deficient sites (tools/chol_experiment.py); sigma comes out directly.
         B, shift = ops.chol_upper(A)
-        ops.jacobi_rows(B, null_rel=0.0)
-        return ops.jacobi_finalize(B, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=2, shift=shift)
+        return ops.jacobi_solve(B, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=2, shift=shift, null_rel=0.0)
     if PRECONDITION_MIN_N and n >= PRECONDITION_MIN_N:
         G32 = ops.cast_f32(A)
         ops.jacobi_rows_f32(G32)
@@ -704,11 +701,9 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
             U = Un
         if float(ops.identity_deviation(ops.matmul(U, U.t())).item()) < 1e-12:
             Ap = ops.matmul(ops.matmul(U, A), U.t())
-            ops.jacobi_rows(Ap, null_rel=null_rel)
-            Ut2, sigma, info, winfo = ops.jacobi_finalize(Ap, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True)
+            Ut2, sigma, info, winfo = ops.jacobi_solve(Ap, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True, null_rel=null_rel)
             return ops.matmul(Ut2, U), sigma, info, winfo
-    ops.jacobi_rows(A, null_rel=null_rel)
-    return ops.jacobi_finalize(A, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True)
+    return ops.jacobi_solve(A, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True, null_rel=null_rel)
 
 
 # Bonds whose Gram matrix is at least this large take the spectral-projection solver (csrc/purify.cu) instead of Cholesky + Jacobi:
@@ -748,14 +743,46 @@ def dominant_subspace(A, chi_max, rank_gap=False):
     return (U, disc) if ok else None
 
 
-def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
+class _AsyncVerdict:
+    """The 8 info doubles of a projection solve, copied to pinned host memory on a SIDE stream that waits only for the solver:
+    reading it does not wait for whatever was queued on the main stream afterwards (a `.cpu()` on the main stream would)."""
+    _side, _ring, _next = {}, {}, {}
+
+    def __init__(self, info):
+        dev = info.device
+        key = dev.index
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=dev)
+            self._ring[key] = [torch.empty(8, dtype=F64).pin_memory() for _ in range(4)]
+            self._next[key] = 0
+        side = self._side[key]
+        self.host = self._ring[key][self._next[key] % 4]
+        self._next[key] += 1
+        ready = torch.cuda.Event()
+        ready.record()                                   # main stream: right after the solver
+        side.wait_event(ready)
+        info.record_stream(side)
+        with torch.cuda.stream(side):
+            self.host.copy_(info, non_blocking=True)
+            self.done = torch.cuda.Event()
+            self.done.record(side)
+
+    def get(self):
+        self.done.synchronize()
+        return self.host.numpy().copy()
+
+
+def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None):
     """`W @ X` + optimal (SVD) rounding by the density-matrix algorithm: right environments, then a left-to-right sweep that finds the
     dominant eigenspace of M E M^T at every bond -- mathematically the truncation of round_svd(site_mpo_mps(...)) but every matrix
     stays <= (chi d) x D.  Eigenvalues are squared singular values, so values below ~1e-8 sigma_0 are noise: rank_tol.
 
     The projection solver's verdict (8 doubles) is read ONE SITE LATE: its basis is used at once, the next site's kernels are queued, and
-    only then does the host look at the verdict -- the GPU never waits for the host.  A rejected bond (no gap at the cut, or the
-    accuracy guard) rolls the sweep back to that site, which is then solved by Cholesky + Jacobi."""
+    only then does the host look at the verdict, which travels to pinned host memory on a side stream (_AsyncVerdict) -- the host
+    waits for the solver of site k only, with site k+1 already queued, so the GPU never waits for the host.  A rejected bond (no gap at the cut, or the
+    accuracy guard) rolls the sweep back to that site, which is then solved by Cholesky + Jacobi.
+
+    `capture` (tests only): a dict {site: None}; the Gram matrix of that bond and the basis the solver kept are stored in it."""
     n = len(X)
     E = right_environments(X, W)
     trunc = Truncation()
@@ -798,7 +825,9 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
                 T = _carry_from(eye, M2, nA, b, r, transposed_basis=False)    # = M2 with its columns re-ordered to (r, b)
             elif PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
                 U, info = ops.dominant_subspace(A, ne, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
-                queued = (k, info, ne, ne >= min(D, right_dim[k + 1]), T, len(out))
+                queued = (k, _AsyncVerdict(info) if info.is_cuda else info, ne, ne >= min(D, right_dim[k + 1]), T, len(out))
+                if capture is not None and k in capture:
+                    capture[k] = (A.clone(), U.clone())
                 trunc.sigma.append(LazySpectrum(A, U)); trunc.keep.append(ne); trunc.discarded.append(None)
                 out.append(U.reshape(s, o, ne))
                 T = _carry_from(U, M2, ne, b, r, transposed_basis=False)
@@ -807,7 +836,7 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7):
             k += 1
         if pending is not None:
             pk, pinfo, pne, pgap, pT, slot = pending
-            ok, disc = _projection_verdict(pinfo.cpu().numpy(), pne, pgap)
+            ok, disc = _projection_verdict(pinfo.get() if isinstance(pinfo, _AsyncVerdict) else pinfo.cpu().numpy(), pne, pgap)
             PURIFY_STATS["taken" if ok else "fallback"] += 1
             if ok:
                 trunc.discarded[slot] = disc

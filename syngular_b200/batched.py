@@ -178,8 +178,7 @@ class BatchedMatrixProductState:
             A = ops.matmul(ME, M.transpose(1, 2))
             # Jacobi on the rows of the shifted Cholesky factor of A (fewer sweeps than on A itself, see csrc/chol.cu)
             Bf, shift = ops.chol_upper(A)
-            ops.jacobi_rows(Bf, null_rel=0.0)
-            Ut, sigma, info, winfo = ops.jacobi_finalize(Bf, chi, rank_tol=0.0, sqrt_mode=2, shift=shift)
+            Ut, sigma, info, winfo = ops.jacobi_solve(Bf, chi, rank_tol=0.0, sqrt_mode=2, shift=shift, null_rel=0.0)
             core = ops.copy_strided(Ut[:, :keep, :].transpose(1, 2))   # (B, rows, keep)
             out.append(core.reshape(B, s, o, keep))
             Tn = empty(B, keep, r, b)

@@ -237,11 +237,12 @@ chol_panel_kernel(double* __restrict__ G, int64_t ld, int n, int k0, int nb, dou
 }
 
 static int chol_upper_one(double* G, int64_t ld, int n, double* B, int64_t ldb, double* shift, cudaStream_t st) {
-    static bool configured = false;
+    static PerDevice configured;
+    const int dev_ = current_device();
     const size_t smem = (size_t)CH_SLAB * CH_LD * sizeof(double);
-    if (!configured) {
+    if (!configured.get(dev_)) {
         SYN_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set(dev_);
     }
     SYN_CUDA(cudaMemset2DAsync(B, (size_t)ldb * sizeof(double), 0, (size_t)n * sizeof(double), (size_t)n, st));
     chol_shift_kernel<<<1, 1024, 0, st>>>(G, ld, n, shift);

@@ -36,7 +36,24 @@ inline int launch_status(const char* what) {
     return 0;
 }
 
-int sm_count();
+int sm_count();          // of the CURRENT device (cached per device)
+int current_device();    // cudaGetDevice, clamped to [0, SYN_MAX_DEVICES)
+
+// Per-device cached configuration.  cudaFuncSetAttribute, occupancy numbers and the SM count are per DEVICE, and a process may
+// switch devices (torch.cuda.set_device) or call from several host threads: every launcher keeps one of these as a function-local
+// static instead of a plain bool.  value = 0 means "not configured on this device yet"; the configuration code is idempotent, so
+// two threads racing on the first call at worst both run it (release/acquire orders their writes before the flag).
+constexpr int SYN_MAX_DEVICES = 64;
+struct PerDevice {
+    int v[SYN_MAX_DEVICES];
+    bool get(int dev, int* out = nullptr) const {
+        int x = __atomic_load_n(&v[dev], __ATOMIC_ACQUIRE);
+        if (!x) return false;
+        if (out) *out = x - 1;
+        return true;
+    }
+    void set(int dev, int value = 0) { __atomic_store_n(&v[dev], value + 1, __ATOMIC_RELEASE); }
+};
 
 // ---- device helpers -------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t idx2(const syn_index_t& ix, int x) {

@@ -23,13 +23,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return 1;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < SYN_MAX_DEVICES ? dev : SYN_MAX_DEVICES - 1;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
+    static PerDevice cache;
+    const int dev = current_device();
+    int n = 0;
+    if (cache.get(dev, &n)) return n;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache.set(dev, n);
     return n;
 }
 

@@ -132,10 +132,11 @@ int env_sandwich_f64(const double* P1, const double* W, double* Z, int na, int l
     SYN_REQUIRE(l == EV_L && r == EV_R && i == 2 && o == 2 && b >= EV_TB && b % EV_TB == 0 && na >= 1,
                 "syn_env_sandwich_f64: shape (l,i,o,r)=(%d,%d,%d,%d), b=%d is not covered by the fused kernel", l, i, o, r, b);
     SYN_REQUIRE(((((uintptr_t)P1) | ((uintptr_t)Z)) & 15) == 0, "syn_env_sandwich_f64: operands must be 16-byte aligned");
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
         SYN_CUDA(cudaFuncSetAttribute(env_sandwich_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV_SMEM));
-        configured = true;
+        configured.set(dev_);
     }
     const int64_t items = (int64_t)na * (b / EV_TB);
     const int grid = (int)(items < sm_count() ? items : sm_count());

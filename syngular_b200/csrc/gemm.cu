@@ -301,10 +301,11 @@ static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* 
     using LB = OperandLoader<C, C::BN, BN, VEC>;
     constexpr size_t smem = (size_t)C::STAGES * (LA::TILE_ELEMS + LB::TILE_ELEMS) * sizeof(double);
     auto kern = gemm_f64_kernel<C, AM, BN, VEC, TMA>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
         SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set(dev_);
     }
     int tiles_m = (d.M + C::BM - 1) / C::BM, tiles_n = (d.N + C::BN - 1) / C::BN;
     long long tiles = (long long)tiles_m * tiles_n;

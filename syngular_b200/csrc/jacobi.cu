@@ -309,6 +309,7 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
 #pragma unroll
     for (int k = 0; k < NREG; k++) ra[k] = R(0);
     int sweep = 0;
+    bool converged = false;
     for (; sweep < max_sweeps; ++sweep) {
         int rotated = 0;
         for (int t = 0; t < (P == 1 ? 1 : Mr); ++t) {
@@ -458,9 +459,9 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
             bar_target += P;
             problem_barrier(bar, bar_target);
             unsigned f = ld_acquire_u32(flags + sweep);
-            if ((f & 2u) == 0u) { ++sweep; break; }      // no rotation, or only small ones: converged
+            if ((f & 2u) == 0u) { ++sweep; converged = true; break; }      // no rotation, or only small ones: converged
         } else {
-            if ((s_rot & 2) == 0) { ++sweep; break; }
+            if ((s_rot & 2) == 0) { ++sweep; converged = true; break; }
             __syncthreads();
         }
     }
@@ -468,7 +469,10 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
         store_block(0, 0);
         store_block(1, 1);
     }
-    if (p == 0 && tid == 0) flags[max_sweeps] = (unsigned)sweep;   // sweeps used (diagnostic)
+    if (p == 0 && tid == 0) {
+        flags[max_sweeps] = (unsigned)sweep;                  // sweeps used (diagnostic)
+        flags[max_sweeps + 1] = converged ? 1u : 0u;          // read by jacobi_finalize_kernel: an unconverged problem is reported in info[1]
+    }
 #ifdef SYN_JACOBI_TIMING
     if (p == 1 && tid == 0 && blockIdx.y == 0)
         printf("jacobi n=%d w=%d P=%d sweeps=%d cycles: poll %lld  load %lld  prologue %lld  steps %lld  epilogue %lld  store+publish %lld\n", n, w, P,
@@ -485,7 +489,8 @@ jacobi_rows_kernel(R* __restrict__ G, int64_t ld, int64_t bs, int n, int w, int 
 __global__ void __launch_bounds__(1024, 1)
 jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int n, double* __restrict__ Ut, int64_t ldu, int64_t ubs,
                        double* __restrict__ sigma, int64_t sbs, int* __restrict__ info, double* __restrict__ winfo, int chi_max, double cutoff,
-                       double rank_tol, int sqrt_mode, const double* __restrict__ shift) {
+                       double rank_tol, int sqrt_mode, const double* __restrict__ shift, const unsigned* __restrict__ ctrl, int ctrl_stride,
+                       int max_sweeps) {
     __shared__ double key[1024];
     __shared__ int perm[1024];
     __shared__ double red[32];
@@ -560,7 +565,9 @@ jacobi_finalize_kernel(const double* __restrict__ G, int64_t ld, int64_t bs, int
     if (warp == 0) {
         double v = red[lane];
         v = warp_sum(v);
-        if (lane == 0) { info[0] = keep; info[1] = n; winfo[0] = v; winfo[1] = s0; }
+        // info[1] = n, negated when the rows kernel ran out of sweeps before its convergence vote passed (ctrl word max_sweeps + 2)
+        const bool conv = ctrl == nullptr || ctrl[(int64_t)blockIdx.x * ctrl_stride + max_sweeps + 2] != 0u;
+        if (lane == 0) { info[0] = keep; info[1] = conv ? n : -n; winfo[0] = v; winfo[1] = s0; }
     }
 }
 
@@ -703,14 +710,15 @@ template <typename R, int NREG, int THREADS>
 static int launch_jacobi(R* G, int64_t ld, int64_t bs, int n, int batch, const JacPlan& pl, unsigned* ctrl, int ctrl_stride,
                          int max_sweeps, double tol, double null_rel, cudaStream_t st) {
     auto kern = jacobi_rows_kernel<R, NREG, THREADS>;
-    static bool configured = false;
-    static int max_ctas = 0;
-    if (!configured) {
+    static PerDevice configured;          // value = co-resident CTAs of this kernel on the device
+    const int dev_ = current_device();
+    int max_ctas = 0;
+    if (!configured.get(dev_, &max_ctas)) {
         SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JAC_SMEM_CAP));
         int per_sm = 0;
         SYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, JAC_SMEM_CAP));
         max_ctas = per_sm * sm_count();
-        configured = true;
+        configured.set(dev_, max_ctas);
     }
     SYN_REQUIRE(pl.P <= max_ctas, "syn_jacobi_rows_f64: problem needs %d co-resident CTAs, device fits %d", pl.P, max_ctas);
     int chunk = max_ctas / pl.P;
@@ -760,9 +768,11 @@ int jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, void* c
 
 int jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs, double* sigma,
                         int64_t sbs, int* info, double* winfo, int chi_max, double cutoff, double rank_tol, int sqrt_mode, const double* shift,
-                        cudaStream_t st) {
+                        const void* ctrl, int max_sweeps, cudaStream_t st) {
     SYN_REQUIRE(n >= 1 && n <= 1024 && batch >= 1, "syn_jacobi_finalize_f64: n=%d batch=%d out of range", n, batch);
-    jacobi_finalize_kernel<<<batch, 1024, 0, st>>>(G, ld, bs, n, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode, shift);
+    SYN_REQUIRE(ctrl == nullptr || max_sweeps >= 1, "syn_jacobi_finalize_f64: max_sweeps must be the value given to syn_jacobi_rows_f64");
+    jacobi_finalize_kernel<<<batch, 1024, 0, st>>>(G, ld, bs, n, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode, shift,
+                                                   (const unsigned*)ctrl, ctrl ? jacobi_ctrl_stride(max_sweeps) : 0, max_sweeps);
     return launch_status("jacobi_finalize_kernel");
 }
 
@@ -868,7 +878,7 @@ extern "C" int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int
 
 extern "C" int syn_jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batch, double* Ut, int64_t ldu, int64_t ubs,
                                        double* sigma, int64_t sbs, int* info, double* winfo, int chi_max, double cutoff, double rank_tol,
-                                       int sqrt_mode, const double* shift, void* stream) {
+                                       int sqrt_mode, const double* shift, const void* ctrl, int max_sweeps, void* stream) {
     return syn::jacobi_finalize_f64(G, ld, bs, n, batch, Ut, ldu, ubs, sigma, sbs, info, winfo, chi_max, cutoff, rank_tol, sqrt_mode, shift,
-                                    (cudaStream_t)stream);
+                                    ctrl, max_sweeps, (cudaStream_t)stream);
 }

@@ -314,10 +314,11 @@ extern "C" int syn_overlap_batched_f64(const syn_overlap_site_t* sites, int n_si
     q.n_sites = n_sites;
     q.batch = batch;
     const size_t smem = (size_t)OV_SMEM_DOUBLES * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
         SYN_CUDA(cudaFuncSetAttribute(overlap_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.set(dev_);
     }
     const int grid = batch < sm_count() ? batch : sm_count();
     overlap_chain_kernel<<<grid, OV_THREADS, smem, (cudaStream_t)stream>>>(q);

@@ -611,14 +611,15 @@ int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int
     SYN_REQUIRE(ws_bytes >= purify_fused_ws_doubles(n, ne, sp2_max, ns_max) * sizeof(double), "syn_dominant_subspace_f64: workspace too small");
     SYN_REQUIRE(((((uintptr_t)ws) | ((uintptr_t)A)) & 15) == 0, "syn_dominant_subspace_f64: A and the workspace must be 16-byte aligned");
     auto kern = purify_fused_kernel;
-    static bool configured = false;
-    static int max_ctas = 0;
-    if (!configured) {
+    static PerDevice configured;          // value = co-resident CTAs of this kernel on the device
+    const int dev_ = current_device();
+    int max_ctas = 0;
+    if (!configured.get(dev_, &max_ctas)) {
         SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
         int per_sm = 0;
         SYN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF_THREADS, PF_SMEM));
         max_ctas = per_sm * sm_count();
-        configured = true;
+        configured.set(dev_, max_ctas);
     }
     SYN_REQUIRE(max_ctas >= 1, "syn_dominant_subspace_f64: the fused kernel does not fit this device");
     const int64_t nn = (int64_t)n * n, nk = (int64_t)n * ne;

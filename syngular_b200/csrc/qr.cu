@@ -255,10 +255,11 @@ static int qr_plan(QrPlan& p, int m, int n, int q, int batch, double* ws, size_t
     if (p.use_global) nb = 16;
     p.nb = nb;
     p.smem = p.use_global ? 0 : (size_t)nb * p.LD * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
         SYN_CUDA(cudaFuncSetAttribute(house_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        configured = true;
+        configured.set(dev_);
     }
     return 0;
 }

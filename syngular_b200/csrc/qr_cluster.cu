@@ -453,11 +453,12 @@ int qr_cluster_form_q(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs,
     const int rows_per = (m + QRC_CLUSTER - 1) / QRC_CLUSTER;
     const bool blocked = qr_env_cluster_mode() != 1;
     const size_t smem = (blocked ? sizeof(QrbShared) : sizeof(QrcShared)) + (size_t)rows_per * qk * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
         SYN_CUDA(cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QRC_SMEM_CAP));
         SYN_CUDA(cudaFuncSetAttribute(qr_cluster_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QRC_SMEM_CAP));
-        configured = true;
+        configured.set(dev_);
     }
     // gridDim.x must be a multiple of the (compile-time) cluster size; chunk large batches
     const int max_probs = 8192;

@@ -149,7 +149,7 @@ def jacobi_rows(G, max_sweeps=40, tol=None, null_rel=1e-14):
                                  _i32(max_sweeps), _dbl(tol if tol is not None else jacobi_tol(n)), _dbl(null_rel), stream_ptr())
     check(rc, "syn_jacobi_rows_f64")
     global _last_jacobi
-    _last_jacobi = (ctrl, max_sweeps, nb)
+    _last_jacobi = (ctrl, max_sweeps, nb, G3.data_ptr())
     return G
 
 
@@ -158,7 +158,7 @@ _last_jacobi = None
 
 def jacobi_sweeps_used():
     """Sweeps the last jacobi_rows call needed, per batch member (diagnostic; synchronises)."""
-    ctrl, max_sweeps, nb = _last_jacobi
+    ctrl, max_sweeps, nb, _ = _last_jacobi
     stride = lib.syn_jacobi_ctrl_stride(int(max_sweeps))
     words = ctrl.view(torch.int32)[: nb * stride].reshape(nb, stride)
     return words[:, max_sweeps + 1].tolist()
@@ -182,8 +182,9 @@ def chol_upper(G):
 
 
 def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shift=None):
-    """Sort / normalise / cut the rows produced by jacobi_rows.  Returns (Ut, sigma, info[int32: keep, n], winfo[f64: discarded, s0])
-    -- all DEVICE tensors; the caller decides when to synchronise on `info`."""
+    """Sort / normalise / cut the rows produced by jacobi_rows.  Returns (Ut, sigma, info[int32: keep, +-n], winfo[f64: discarded, s0])
+    -- all DEVICE tensors; the caller decides when to synchronise on `info`.  When G is the matrix the last jacobi_rows call worked
+    on, info[1] is NEGATIVE if that call ran out of sweeps before its convergence vote passed (see jacobi_solve)."""
     require_cuda_f64(G)
     batched = G.dim() == 3
     G3 = G if batched else G.unsqueeze(0)
@@ -192,13 +193,31 @@ def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shi
     sigma = torch.empty((nb, n), dtype=torch.float64, device=G.device)
     info = torch.empty((nb, 2), dtype=torch.int32, device=G.device)
     winfo = torch.empty((nb, 2), dtype=torch.float64, device=G.device)
+    mine = _last_jacobi is not None and _last_jacobi[2] == nb and _last_jacobi[3] == G3.data_ptr()
     rc = lib.syn_jacobi_finalize_f64(ptr(G3), _i64(G3.stride(1)), _i64(G3.stride(0)), _i32(n), _i32(nb), ptr(Ut), _i64(n), _i64(n * n),
                                      ptr(sigma), _i64(n), ptr(info), ptr(winfo), _i32(int(chi_max)), _dbl(cutoff), _dbl(rank_tol),
-                                     _i32(int(sqrt_mode)), ptr(shift) if shift is not None else None, stream_ptr())
+                                     _i32(int(sqrt_mode)), ptr(shift) if shift is not None else None,
+                                     ptr(_last_jacobi[0]) if mine else None, _i32(_last_jacobi[1] if mine else 0), stream_ptr())
     check(rc, "syn_jacobi_finalize_f64")
     if not batched:
         return Ut[0], sigma[0], info[0], winfo[0]
     return Ut, sigma, info, winfo
+
+
+JACOBI_MAX_ROUNDS = 4
+
+
+def jacobi_solve(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shift=None, null_rel=1e-14, max_sweeps=40):
+    """jacobi_rows + jacobi_finalize + ONE host read of `info` (kept rank and the convergence verdict of the rows kernel).
+    A problem that ran out of sweeps is not truncated on: the rows kernel is called again on the same G (it resumes -- the rows are
+    J G for an orthogonal J at any point) up to JACOBI_MAX_ROUNDS times, then SynError.  Returns (Ut, sigma, info ON THE HOST, winfo)."""
+    for _ in range(JACOBI_MAX_ROUNDS):
+        jacobi_rows(G, max_sweeps=max_sweeps, null_rel=null_rel)
+        Ut, sigma, info, winfo = jacobi_finalize(G, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=sqrt_mode, shift=shift)
+        h = info.cpu()
+        if bool((h[..., 1] > 0).all()):
+            return Ut, sigma, h, winfo
+    raise SynError("one-sided Jacobi did not converge in %d x %d sweeps (n = %d)" % (JACOBI_MAX_ROUNDS, max_sweeps, G.shape[-1]))
 
 
 lib.syn_dominant_subspace_workspace_f64.restype = ctypes.c_size_t

@@ -73,7 +73,7 @@ int main() {
     CK(cudaMalloc(&dG, G.size() * 8)); CK(cudaMalloc(&dUt, Ut.size() * 8)); CK(cudaMalloc(&dsig, nj * 8)); CK(cudaMalloc(&dw, 16)); CK(cudaMalloc(&dinfo, 8)); CK(cudaMalloc(&ctrl, cb));
     CK(cudaMemcpy(dG, G.data(), G.size() * 8, cudaMemcpyHostToDevice));
     SYN(syn_jacobi_rows_f64(dG, nj, (int64_t)nj * nj, nj, 1, ctrl, cb, 40, 1e-14, 1e-14, nullptr));
-    SYN(syn_jacobi_finalize_f64(dG, nj, (int64_t)nj * nj, nj, 1, dUt, nj, (int64_t)nj * nj, dsig, nj, dinfo, dw, 10, 0.0, 1e-14, 0, nullptr, nullptr));
+    SYN(syn_jacobi_finalize_f64(dG, nj, (int64_t)nj * nj, nj, 1, dUt, nj, (int64_t)nj * nj, dsig, nj, dinfo, dw, 10, 0.0, 1e-14, 0, nullptr, nullptr, 0, nullptr));
     int info[2]; CK(cudaMemcpy(info, dinfo, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(sig.data(), dsig, nj * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(Ut.data(), dUt, Ut.size() * 8, cudaMemcpyDeviceToHost));
     double e5 = 0; bool sorted = true;

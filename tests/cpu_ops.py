@@ -140,6 +140,11 @@ def jacobi_finalize(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shi
             torch.tensor([disc, sv[0]], dtype=F64))
 
 
+def jacobi_solve(G, chi_max, cutoff=0.0, rank_tol=1e-14, sqrt_mode=False, shift=None, null_rel=1e-14, max_sweeps=40):
+    jacobi_rows(G, max_sweeps=max_sweeps, null_rel=null_rel)
+    return jacobi_finalize(G, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=sqrt_mode, shift=shift)
+
+
 def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160, ns_max=80):
     """csrc/purify.cu restated: SP2 from A / |A|_F with the trace-steered branch, then Newton-Schulz on P[:, :ne]."""
     a = A.numpy()
@@ -249,7 +254,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "sum_parts", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "jacobi_solve", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "sum_parts", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

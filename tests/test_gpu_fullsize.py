@@ -1,5 +1,6 @@
 """GPU: the hot path at BASELINE.json's FULL sizes (configs[1]: N=64, d=2, chi=256, chi_W=16; configs[3]: N=32, chi=64 batch),
-checked through size-independent properties -- the oracle cannot run these sizes in seconds:
+checked (i) against ONE full-size sweep of the like-for-like CPU oracle (about a minute of BLAS/LAPACK on the host cores: the last
+test of this file) and (ii) through size-independent properties:
   * every rounded core is left-orthonormal;
   * sequential orthogonal projections:  |W X|^2 - |result|^2 == sum of the per-bond discarded weights   (SVD mode);
   * optimality: the SVD-rounded state is at least as close to W X as the reference's QR-rounded state;
@@ -89,3 +90,56 @@ def test_c4_batched_overlap_properties():
     # single-chain path on one member agrees with the batched kernel
     got = A.state(7) | B.state(7)
     assert abs(got - ab[7].item()) < 1e-12 * abs(got)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the headline path against the oracle AT HEADLINE SIZE: one full C2 sweep of the like-for-like CPU algorithm
+# (oracle/svd_numpy.StructuredDensityMatrixSweep, ~1 minute of BLAS/LAPACK on the host cores) versus the CUDA sweep
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_oracle_sweep():
+    import bench
+    from oracle import svd_numpy as S
+    X, W = bench.make_chain(2)
+    bench.use_all_host_threads()
+    return S.apply_round_density_matrix_structured(X, W, 256)
+
+
+def test_c2_svd_round_matches_the_oracle_at_full_size(c2, c2_oracle_sweep):
+    """Per-bond kept ranks, kept singular spectra and discarded weights, the norm, the rounded STATE itself (overlap of the two
+    results) and overlaps with a fixed probe state: 1e-10 relative (FP64 bar of BASELINE.json's north_star)."""
+    import bench
+    from syngular.tensor import _sweeps as sw
+    X, W = c2
+    ref_cores, ref_spec, ref_disc = c2_oracle_sweep
+    sw.PURIFY_STATS.update(taken=0, fallback=0)
+    capture = {31: None}
+    out, trunc = sw.apply_round_dm(X, W, 256, capture=capture)
+    assert sw.PURIFY_STATS["taken"] >= 40                      # the plateau bonds really took the spectral-projection solver
+    sig, keep, disc = trunc.host()
+    assert [int(k) for k in keep] == [min(256, len(s)) for s in ref_spec]
+    ref = [sw.as_core(c) for c in ref_cores]
+    n_gg = float(sw.overlap(out, out).item()); n_cc = float(sw.overlap(ref, ref).item()); n_gc = float(sw.overlap(out, ref).item())
+    assert abs(n_gg - n_cc) < 1e-10 * n_cc
+    assert abs(n_gg + n_cc - 2.0 * n_gc) < 1e-10 * n_cc         # |out_gpu - out_cpu|^2 relative to |out|^2: the same STATE, any gauge
+    for k, (s_g, s_c, d_g, d_c) in enumerate(zip(sig, ref_spec, disc, ref_disc)):
+        kk = keep[k]
+        assert len(s_g) >= kk, k
+        assert np.max(np.abs(np.sort(s_g)[::-1][:kk] - s_c[:kk])) < 1e-10 * s_c[0], k
+        assert abs(d_g - d_c) < 1e-10 * float(np.sum(s_c ** 2)), k
+    # overlaps with a fixed probe state (bond 8): a gauge-invariant linear functional of the rounded state
+    Xp, _ = bench.make_chain(77, chi=8)
+    probe = [sw.as_core(x) for x in Xp]
+    n_pp = float(sw.overlap(probe, probe).item())
+    o_g = float(sw.overlap(out, probe).item()); o_c = float(sw.overlap(ref, probe).item())
+    assert abs(o_g - o_c) < 1e-10 * np.sqrt(n_cc * n_pp)
+    # one plateau bond: the kept projector of the spectral-projection solver against LAPACK's eigh of the SAME Gram matrix
+    A, U = capture[31]
+    lam, V = np.linalg.eigh(A.cpu().numpy())
+    Vk = V[:, -256:]
+    Ug = U.cpu().numpy()
+    gap = lam[-256] - lam[-257]
+    dist = np.linalg.norm(Ug @ Ug.T - Vk @ Vk.T)
+    assert gap > 0
+    # Davis-Kahan: a backward-stable eigen-solver tilts the kept space by ~ eps |A| / gap; 100x head-room, and never worse than 1e-8
+    assert dist < min(100 * 2.2e-16 * lam[-1] / gap * np.sqrt(256), 1e-8), (dist, gap / lam[-1])
