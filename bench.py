@@ -438,7 +438,7 @@ def run_ours(args):
             n_gg = float(sw.overlap(out_g, out_g).item()); n_cc = float(sw.overlap(ref, ref).item()); n_gc = float(sw.overlap(out_g, ref).item())
             parity = {"norm2_rel_diff": abs(n_gg - n_cc) / n_cc, "state_rel_dist2": abs(n_gg + n_cc - 2.0 * n_gc) / n_cc,
                       "discarded_weight_max_abs_diff_over_norm2": float(max(abs(a - b) for a, b in zip(disc_g, cpu_disc)) / n_cc),
-                      "kept_ranks_equal": [int(k) for k in keep_g] == [min(CHI, len(sp)) for sp in cpu_spec]}
+                      "kept_ranks_equal": [int(k) for k in keep_g] == [min(CHI, int(np.count_nonzero(sp > 3.2e-7 * sp[0]))) for sp in cpu_spec]}
             del ref, cpu_out
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -198,6 +198,20 @@ int syn_scale_rsqrt_f64(double* x, int64_t n, const double* sumsq, void* stream)
  * (layers/TensorDense.py:139-142).  The TT contraction itself is a chain of syn_gemm_f64 calls. */
 int syn_bias_act_f64(double* y, const double* bias, int64_t rows, int cols, int act, void* stream);
 
+/* ---- TensorDense forward on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, TMEM, TMA) ------------------------------- */
+/* Fused TT-matvec of the MPO-compressed dense layer, reference layers/TensorDense.py:74-142 (`call`: per-sample opt_einsum contract of
+ * the reshaped input with the three cores at :103-118, `+ bias` at :139, activation at :142), for three cores with every mode and bond
+ * equal to 16 (BASELINE configs[4]: a 4096 -> 4096 layer):
+ *   y[s,o1,o2,o3] = act( sum x[s,i1,i2,i3] G1[i1,o1,b1] G2[i2,o2,b1,b2] G3[i3,o3,b2] + bias[o1,o2,o3] ),  float32 in / out, TF32 products
+ *   with FP32 accumulation; both 65,536-float intermediates of a sample stay in TMEM / shared memory.
+ * syn_tt_dense3_pack_tf32 turns the cores (the reference's layouts, device float32) into the pre-swizzled operand images the kernel
+ * stages with bulk copies (`packed`: syn_tt_dense3_packed_floats() device floats, 16-byte aligned; redo it when the weights change).
+ * syn_tt_dense3_tf32: x (batch x 4096) and y (batch x 4096) device float32, 16-byte aligned, contiguous; bias 4096 floats or NULL;
+ * relu = 0 / 1.  Other layer shapes run on the FP64 strided GEMM (syn_gemm_f64 + syn_bias_act_f64). */
+size_t syn_tt_dense3_packed_floats(void);
+int syn_tt_dense3_pack_tf32(const float* G1, const float* G2, const float* G3, float* packed, void* stream);
+int syn_tt_dense3_tf32(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,13 @@ pass is a chain of N strided DMMA GEMMs (one per core, no transposition, the who
 by a fused bias + activation kernel.  The reference contracts sample by sample under tf.vectorized_map, and its einsum
 specification is only valid for exactly 3 cores (TensorDense.py:110-114); this works for any number of cores.
 
-Arithmetic is FP64 (>= the reference's float32); a TF32 tcgen05 variant is the planned fast path for BASELINE configs[4].
+Two arithmetic paths:
+  precision="f64"  (default, the checked path): FP64 on the strided DMMA GEMM, any number of cores and any shapes;
+  precision="tf32": float32 in / out, products on tcgen05.mma.kind::tf32 with FP32 accumulation -- the reference computes in float32
+                    (Keras default dtype; TensorDense.py:50-71 add_weight) -- by ONE fused kernel per call that keeps both per-sample
+                    intermediates in TMEM / shared memory (csrc/ttdense.cu).  Covered shape: three cores with every mode and bond 16
+                    (BASELINE configs[4]); anything else raises.  Stated tolerance against the float64 restatement: 4e-3 of the output's
+                    largest magnitude (TF32 keeps 10 mantissa bits of every operand, three chained contractions).
 """
 import numpy as np
 import torch
@@ -16,7 +22,7 @@ from syngular_b200 import ops
 
 
 class TensorDense:
-    def __init__(self, tt_input_shape, tt_output_shape, tt_bond_shape, activation="relu", use_bias=True, seed=None):
+    def __init__(self, tt_input_shape, tt_output_shape, tt_bond_shape, activation="relu", use_bias=True, seed=None, precision="f64"):
         self.tt_input_shape = tuple(int(x) for x in tt_input_shape)
         self.tt_output_shape = tuple(int(x) for x in tt_output_shape)
         self.tt_bond_shape = tuple(int(x) for x in tt_bond_shape)
@@ -31,6 +37,14 @@ class TensorDense:
         self.use_bias = use_bias
         self.cores, self.bias = [], None
         self._seed = seed
+        if precision not in ("f64", "tf32"):
+            raise ValueError("precision must be 'f64' or 'tf32'")
+        if precision == "tf32" and not ops.tt_dense3_fits(self.tt_input_shape, self.tt_output_shape, self.tt_bond_shape):
+            raise NotImplementedError("the fused TF32 kernel covers three cores with every mode and bond equal to 16; use precision='f64'")
+        if precision == "tf32" and activation not in ("relu", None, "linear", "identity"):
+            raise NotImplementedError("the fused TF32 kernel applies relu or no activation")
+        self.precision = precision
+        self._packed = self._bias32 = None
 
     def core_shapes(self):
         n, i, o, b = self.cores_number, self.tt_input_shape, self.tt_output_shape, self.tt_bond_shape
@@ -46,6 +60,11 @@ class TensorDense:
         assert [tuple(c.shape) for c in cores] == self.core_shapes(), "cores must be in the reference's layouts"
         self.cores = [sw.as_core(c) for c in cores]
         self.bias = sw.as_core(bias if bias is not None else np.zeros(self.tt_output_shape)) if self.use_bias else None
+        if self.precision == "tf32":
+            # the reference's weights are float32 (Keras default): round once, pack into the kernel's operand images
+            g32 = [c.to(torch.float32).contiguous() for c in self.cores]
+            self._packed = ops.tt_dense3_pack(*g32)
+            self._bias32 = self.bias.to(torch.float32).reshape(-1).contiguous() if self.bias is not None else None
         return self
 
     def _dims(self, k):
@@ -59,6 +78,10 @@ class TensorDense:
     def call(self, inputs, chunk=None):
         if not self.cores:
             self.build()
+        if self.precision == "tf32":
+            x32 = inputs if isinstance(inputs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inputs, dtype=np.float32))
+            x32 = x32.to(device=sw.device(), dtype=torch.float32).reshape(-1, self.tt_input_shape_unfold).contiguous()
+            return ops.tt_dense3_tf32(x32, self._packed, self._bias32, relu=self.activation == "relu")
         x = sw.as_core(inputs).reshape(-1, self.tt_input_shape_unfold)
         batch = x.shape[0]
         out = torch.empty((batch, self.tt_output_shape_unfold), dtype=torch.float64, device=x.device)

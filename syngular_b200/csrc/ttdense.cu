@@ -1,0 +1,465 @@
+// Fused TT-matvec of the MPO-compressed dense layer (TensorDense forward, reference layers/TensorDense.py:74-142) on the 5th-generation
+// tensor cores: tcgen05.mma.kind::tf32 with TMEM accumulators, TMA-staged input, all intermediates on chip, bias + ReLU in the epilogue.
+//
+//   y[s,o1,o2,o3] = act( sum_{i1,i2,i3,b1,b2} x[s,i1,i2,i3] G1[i1,o1,b1] G2[i2,o2,b1,b2] G3[i3,o3,b2] + bias[o1,o2,o3] )
+//
+// for BASELINE configs[4]: three cores, every mode and bond = 16 (a 4096 -> 4096 layer held in 3 * 4096... 73,728 parameters).  Per sample
+// the contraction is three GEMMs whose intermediates are 16x the sample (65,536 floats each): written to HBM they would cost 34 GB per
+// 65,536-sample batch against 2 GB of input + output, so the whole chain runs inside one CTA per (sample, half of o2):
+//
+//   step 1   T1[(o3,b2), i1 | i2]        = sum_i3      G3^T[(o3,b2), i3]   x[(i2,i1), i3]             M=2x128  N=16   K=16   per i2
+//   step 2   T2[(o3,i1), (b1,o2)]       += sum_(i2,b2) T1[(o3,i1), (i2,b2)] G2[(b1,o2), (i2,b2)]      M=2x128  N=128  K=256  (16 chunks of K=16)
+//   step 3   Y [(o2,o3), o1]             = sum_(b1,i1) T2[(o2,o3), (b1,i1)] G1[o1, (b1,i1)]           M=128    N=16   K=256  (8 chunks of K=32)
+//
+// (the chain is contracted from the i3 end so that every operand, the input included, is K-major in memory).  In each step the
+// contracted index pairs a bond produced on the weight side with a mode of the data side, so the accumulator of one step (TMEM:
+// lane = M index, column = N index) is not the operand layout of the next: T1 and T2 are re-laid out TMEM -> registers -> shared
+// memory by the four epilogue warps.  The index orders are chosen so that in BOTH re-layouts the contracted index of the next step is
+// the TMEM lane: a warp's 32 lanes then write 32 consecutive words of one or two operand rows (conflict-free, one wavefront), in the
+// UMMA canonical K-major swizzled layout the next tcgen05.mma reads through its shared-memory descriptor.
+//
+// Warp roles (192 threads, one CTA per SM, persistent over its samples):
+//   warp 0     TMA producer: weights once (pre-swizzled images, cp.async.bulk), then one 16 KB tensor-map load per sample
+//              (cp.async.bulk.tensor.4d, 64B swizzle, box = the whole sample re-ordered to rows (i2,i1))
+//   warp 1     TMEM allocation + the single MMA-issuing thread (software pipeline: step 1 runs two chunks ahead of step 2)
+//   warps 2-5  epilogue: tcgen05.ld -> st.shared re-layouts, final tcgen05.ld + bias + ReLU + coalesced global stores
+// Pipelines (mbarriers): x full/empty, D1 double buffer full/empty, a ring of three 16 KB operand slots full/empty shared by the
+// T1 and T2 re-layouts, D2 full/empty, D3 full/empty.
+//
+// Shared memory (one CTA per SM): G2 half image 128 KB + 3 operand slots 48 KB + G3 image 16 KB + G1 image 16 KB + x 16 KB = 224 KB.
+// TMEM: D1 2x2x16 columns, D2 2x128, D3 16 -> 336 of 512 columns.
+#include <cuda.h>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace syn {
+
+namespace tt {
+
+constexpr int THREADS = 192;
+constexpr int SLOTS = 3;
+constexpr uint32_t SLOT_BYTES = 16384;
+// shared-memory map (offsets from a 1024-byte aligned base)
+constexpr uint32_t OFF_B2 = 0;                                  // 8 atoms x [128 rows x 128 B]   (SW128, K-major)
+constexpr uint32_t OFF_SLOT = OFF_B2 + 131072;                  // 3 x 16 KB
+constexpr uint32_t OFF_A1 = OFF_SLOT + SLOTS * SLOT_BYTES;      // 2 tiles x [128 rows x 64 B]     (SW64)
+constexpr uint32_t OFF_B3 = OFF_A1 + 16384;                     // 8 atoms x [16 rows x 128 B]     (SW128)
+constexpr uint32_t OFF_X = OFF_B3 + 16384;                      // 256 rows x 64 B                 (SW64, written by TMA)
+constexpr uint32_t OFF_BAR = OFF_X + 16384;                     // mbarriers + TMEM base pointer
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;           // + slack for the 1024-byte alignment of the base
+// packed weight image in global memory (floats): [A1 16 KB][B3 16 KB][B2 half 0 128 KB][B2 half 1 128 KB]
+constexpr size_t IMG_A1 = 0, IMG_B3 = 4096, IMG_B2 = 8192, IMG_FLOATS = 8192 + 2 * 32768;
+// TMEM columns
+constexpr uint32_t TM_D1 = 0, TM_D2 = 64, TM_D3 = 320, TM_COLS = 512;
+
+enum Bar { W_FULL = 0, X_FULL, X_EMPTY, D1_FULL0, D1_FULL1, D1_EMPTY0, D1_EMPTY1, SLOT_FULL0, SLOT_EMPTY0 = SLOT_FULL0 + SLOTS,
+           D2_FULL = SLOT_EMPTY0 + SLOTS, D2_EMPTY, D3_FULL, D3_EMPTY, NUM_BARS };
+
+// byte offset of element (row, kbyte) in a K-major operand block with 128-byte rows / 128B swizzle, resp. 64-byte rows / 64B swizzle
+__host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t kbyte) {
+    return (row >> 3) * 1024u + (row & 7u) * 128u + ((((kbyte >> 4) ^ (row & 7u)) & 7u) << 4) + (kbyte & 15u);
+}
+__host__ __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t kbyte) {
+    return (row >> 3) * 512u + (row & 7u) * 64u + ((((kbyte >> 4) ^ ((row & 7u) >> 1)) & 3u) << 4) + (kbyte & 15u);
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all tcgen05 operations issued so far by this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+
+// bounded wait with a diagnosis: a pipeline bug prints which barrier starved instead of hanging the GPU
+__device__ __noinline__ void tt_wait_timeout(int id, uint32_t parity) {
+    printf("tt_dense3_tf32_kernel: block %d thread %d starved on barrier %d (parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, id, parity);
+    __trap();
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tt_wait(uint64_t* bars, int id, uint32_t parity) {
+    if (mbar_try_wait(&bars[id], parity)) return;
+    const uint64_t t0 = global_ns();
+    for (unsigned spin = 1; !mbar_try_wait(&bars[id], parity); ++spin)
+        if ((spin & 255u) == 0 && global_ns() - t0 > 2000000000ull) tt_wait_timeout(id, parity);      // 2 s: far beyond any legitimate wait
+}
+
+#ifdef SYN_TT_DEBUG
+__device__ uint32_t* g_tt_dbg = nullptr;      // host-mapped progress words: [block][warp][4]
+#define TT_MARK(slot_, val_)                                                                            \
+    do {                                                                                                \
+        if (g_tt_dbg && (threadIdx.x & 31) == 0) {                                                      \
+            volatile uint32_t* w_ = g_tt_dbg + ((size_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + (slot_); \
+            *w_ = (uint32_t)(val_);                                                                     \
+            __threadfence_system();                                                                     \
+        }                                                                                               \
+    } while (0)
+#else
+#define TT_MARK(slot_, val_) do { } while (0)
+#endif
+
+// K-major shared-memory matrix descriptor (sm_100 "version 1"): start address, stride between 8-row groups, swizzle mode
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)layout_type << 61);
+}
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
+// instruction descriptor of kind::tf32: FP32 accumulate, TF32 A and B, both K-major, shape M x N (K = 8 per instruction)
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ---- weight packing: the three cores -> the pre-swizzled operand images ------------------------------------------------------------
+// G1 (i1,o1,b1), G2 (i2,o2,b1,b2), G3 (i3,o3,b2): the reference's layouts (layers/TensorDense.py:50-71), every extent 16.
+__global__ void __launch_bounds__(256) tt_pack_kernel(const float* __restrict__ G1, const float* __restrict__ G2, const float* __restrict__ G3,
+                                                      float* __restrict__ img) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    // A1[t][row = o3l*16 + b2][k = i3] = G3[i3, 8t + o3l, b2]                                      (SW64; 2 tiles of 8 KB)
+    for (int e = tid; e < 4096; e += stride) {
+        const int i3 = e & 15, row = (e >> 4) & 127, t = e >> 11;
+        const int o3 = 8 * t + (row >> 4), b2 = row & 15;
+        img[IMG_A1 + (t * 8192 + sw64_off(row, i3 * 4)) / 4] = G3[(i3 * 16 + o3) * 16 + b2];
+    }
+    // B3[atom a][row = o1][kk = (b1 & 1)*16 + i1], b1 = 2a + (kk >> 4)  = G1[i1, o1, b1]              (SW128; 8 atoms of 2 KB)
+    for (int e = tid; e < 4096; e += stride) {
+        const int kk = e & 31, o1 = (e >> 5) & 15, a = e >> 9;
+        const int b1 = 2 * a + (kk >> 4), i1 = kk & 15;
+        img[IMG_B3 + (a * 2048 + sw128_off(o1, kk * 4)) / 4] = G1[(i1 * 16 + o1) * 16 + b1];
+    }
+    // B2[h][atom a][row n = b1*8 + o2l][kk = (i2 & 1)*16 + b2], i2 = 2a + (kk >> 4)  = G2[i2, 8h + o2l, b1, b2]   (SW128; 8 atoms of 16 KB)
+    for (int e = tid; e < 65536; e += stride) {
+        const int kk = e & 31, n = (e >> 5) & 127, a = (e >> 12) & 7, h = e >> 15;
+        const int i2 = 2 * a + (kk >> 4), b2 = kk & 15, b1 = n >> 3, o2 = 8 * h + (n & 7);
+        img[IMG_B2 + (size_t)h * 32768 + (a * 16384 + sw128_off(n, kk * 4)) / 4] = G2[((i2 * 16 + o2) * 16 + b1) * 16 + b2];
+    }
+}
+
+// ---- the fused forward kernel ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ img, const float* __restrict__ bias,
+                      float* __restrict__ y, int batch, int relu) {
+    extern __shared__ uint8_t tt_smem_raw[];
+    // 1024-byte aligned base: SW128 atoms and the descriptors' swizzle phases assume it
+    const uint32_t raw = smem_u32(tt_smem_raw);
+    uint8_t* smem = tt_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x & 1;                                   // which half of o2 this CTA computes
+    const int first = blockIdx.x >> 1, step = gridDim.x >> 1;       // its samples: first, first + step, ...
+    const int my_samples = first < batch ? (batch - first + step - 1) / step : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[W_FULL], 1);
+        mbar_init(&bars[X_FULL], 1);
+        mbar_init(&bars[X_EMPTY], 1);
+        mbar_init(&bars[D1_FULL0], 1);
+        mbar_init(&bars[D1_FULL1], 1);
+        mbar_init(&bars[D1_EMPTY0], 128);
+        mbar_init(&bars[D1_EMPTY1], 128);
+        for (int s = 0; s < SLOTS; s++) {
+            mbar_init(&bars[SLOT_FULL0 + s], 128);
+            mbar_init(&bars[SLOT_EMPTY0 + s], 1);
+        }
+        mbar_init(&bars[D2_FULL], 1);
+        mbar_init(&bars[D2_EMPTY], 128);
+        mbar_init(&bars[D3_FULL], 1);
+        mbar_init(&bars[D3_EMPTY], 128);
+        fence_async_smem();
+    }
+    TT_MARK(2, 1);
+    if (warp == 1) tmem_alloc(tmem_ptr, TM_COLS);
+    TT_MARK(2, 2);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer ==============================================================================================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+            // weights: A1 (16 KB), B3 (16 KB), this CTA's half of B2 (128 KB in 8 copies)
+            mbar_expect_tx(&bars[W_FULL], 16384u + 16384u + 131072u);
+            bulk_g2s(smem + OFF_A1, img + IMG_A1, 16384u, &bars[W_FULL]);
+            bulk_g2s(smem + OFF_B3, img + IMG_B3, 16384u, &bars[W_FULL]);
+            for (int a = 0; a < 8; a++)
+                bulk_g2s(smem + OFF_B2 + a * 16384, img + IMG_B2 + (size_t)h * 32768 + (size_t)a * 4096, 16384u, &bars[W_FULL]);
+            uint32_t ph_empty = 1;                                   // a fresh barrier passes a wait on the "previous" phase
+            for (int j = 0; j < my_samples; j++) {
+                TT_MARK(0, 0x100 + j);
+                tt_wait(bars, X_EMPTY, ph_empty);
+                ph_empty ^= 1;
+                TT_MARK(1, 0x100 + j);
+                mbar_expect_tx(&bars[X_FULL], 16384u);
+                tma_load_4d(smem + OFF_X, &xmap, 0, 0, 0, first + j * step, &bars[X_FULL]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====================================================================================================
+        if (lane == 0) {
+            constexpr uint32_t ID_S1 = idesc_tf32(128, 16), ID_S2 = idesc_tf32(128, 128), ID_S3 = idesc_tf32(128, 16);
+            constexpr int LAG = 2;
+            tt_wait(bars, W_FULL, 0);
+            uint32_t ph_x = 0, ph_d1e = 3, ph_d2e = 1, ph_d3e = 1;      // "empty" barriers: a fresh barrier passes a wait on parity 1
+            uint32_t slot = 0, ph_slot_full = 0;                        // one phase bit per slot / buffer
+            for (int j = 0; j < my_samples; j++) {
+                for (int c = 0; c < 16 + LAG; c++) {
+                    if (c < 16) {
+                        // step 1, chunk c (= i2): D1[c & 1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16)
+                        const int b = c & 1;
+                        TT_MARK(0, 0x10000 + j * 256 + c);
+                        if (c == 0) { tt_wait(bars, X_FULL, ph_x); ph_x ^= 1; }
+                        TT_MARK(1, 0x10000 + j * 256 + c);
+                        tt_wait(bars, D1_EMPTY0 + b, (ph_d1e >> b) & 1u);
+                        ph_d1e ^= 1u << b;
+                        tc_fence_after();
+#pragma unroll
+                        for (int t = 0; t < 2; t++)
+#pragma unroll
+                            for (int k = 0; k < 2; k++)
+                                umma_tf32(tmem + TM_D1 + b * 32 + t * 16,
+                                          smem_desc(sbase + OFF_A1 + t * 8192 + k * 32, 512, LAYOUT_SW64),
+                                          smem_desc(sbase + OFF_X + c * 1024 + k * 32, 512, LAYOUT_SW64), ID_S1, k);
+                        umma_commit(&bars[D1_FULL0 + b]);
+                        if (c == 15) umma_commit(&bars[X_EMPTY]);
+                    }
+                    if (c >= LAG) {
+                        // step 2, chunk cc: D2[t] += T1 chunk (slot: 2 tiles of 128 x 16) . G2 half [(b1,o2l), (i2 = cc, b2)]^T
+                        const int cc = c - LAG;
+                        TT_MARK(0, 0x20000 + j * 256 + cc);
+                        tt_wait(bars, SLOT_FULL0 + slot, (ph_slot_full >> slot) & 1u);
+                        ph_slot_full ^= 1u << slot;
+                        if (cc == 0) { tt_wait(bars, D2_EMPTY, ph_d2e); ph_d2e ^= 1; }
+                        tc_fence_after();
+                        const uint32_t a_base = sbase + OFF_SLOT + slot * SLOT_BYTES;
+                        const uint32_t b_base = sbase + OFF_B2 + (cc >> 1) * 16384 + (cc & 1) * 64;
+#pragma unroll
+                        for (int t = 0; t < 2; t++)
+#pragma unroll
+                            for (int k = 0; k < 2; k++)
+                                umma_tf32(tmem + TM_D2 + t * 128, smem_desc(a_base + t * 8192 + k * 32, 512, LAYOUT_SW64),
+                                          smem_desc(b_base + k * 32, 1024, LAYOUT_SW128), ID_S2, (cc > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&bars[SLOT_EMPTY0 + slot]);
+                        if (cc == 15) umma_commit(&bars[D2_FULL]);
+                        slot = slot + 1 == SLOTS ? 0 : slot + 1;
+                    }
+                }
+                // step 3, chunk p (= b1 pair): D3 += T2 chunk (slot: 128 x 32) . G1 [o1, (b1, i1)]^T
+                for (int p = 0; p < 8; p++) {
+                    TT_MARK(0, 0x30000 + j * 256 + p);
+                    tt_wait(bars, SLOT_FULL0 + slot, (ph_slot_full >> slot) & 1u);
+                    ph_slot_full ^= 1u << slot;
+                    if (p == 0) { tt_wait(bars, D3_EMPTY, ph_d3e); ph_d3e ^= 1; }
+                    tc_fence_after();
+                    const uint32_t a_base = sbase + OFF_SLOT + slot * SLOT_BYTES;
+                    const uint32_t b_base = sbase + OFF_B3 + p * 2048;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        umma_tf32(tmem + TM_D3, smem_desc(a_base + k * 32, 1024, LAYOUT_SW128), smem_desc(b_base + k * 32, 1024, LAYOUT_SW128),
+                                  ID_S3, (p > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&bars[SLOT_EMPTY0 + slot]);
+                    if (p == 7) umma_commit(&bars[D3_FULL]);
+                    slot = slot + 1 == SLOTS ? 0 : slot + 1;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: re-layouts and the output ===================================================================================
+        const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        const int hb = lane >> 4, lo = lane & 15;
+        uint32_t ph_d1f = 0, ph_d2f = 0, ph_d3f = 0;
+        uint32_t slot = 0, ph_slot_empty = (1u << SLOTS) - 1u;
+        // re-layout 1: D1 lane = (o3l = 2q + hb, b2 = lo), column i1  ->  A2 slot, tile t, row m = q*32 + i1*2 + hb, k = b2        (SW64)
+        //   row m: group (m >> 3) = q*4 + (i1 >> 2), in-group (m & 7) = (i1 & 3)*2 + hb, swizzle phase = i1 & 3
+        const uint32_t r1_base = (uint32_t)(q * 4) * 512u + (uint32_t)hb * 64u + (uint32_t)(lo & 3) * 4u;
+        // re-layout 2: D2 lane = (o3l = 2q + hb', i1), lane index L = i1*2 + hb' within the quadrant; column = b1l*8 + o2l of the chunk
+        //   ->  A3 slot row m' = o2l*16 + t*8 + hb'*4 + q, k = b1l*16 + i1                                                         (SW128)
+        const int hb2 = lane & 1, i1_2 = lane >> 1;
+        for (int j = 0; j < my_samples; j++) {
+            const int s = first + j * step;
+            for (int c = 0; c < 16; c++) {
+                const int b = c & 1;
+                TT_MARK(0, 0x40000 + j * 256 + c);
+                tt_wait(bars, D1_FULL0 + b, (ph_d1f >> b) & 1u);
+                ph_d1f ^= 1u << b;
+                tc_fence_after();
+                uint32_t r0[16], r1[16];
+                tmem_ld16(tq + TM_D1 + b * 32, r0);
+                tmem_ld16(tq + TM_D1 + b * 32 + 16, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[D1_EMPTY0 + b]);
+                TT_MARK(0, 0x50000 + j * 256 + c);
+                tt_wait(bars, SLOT_EMPTY0 + slot, (ph_slot_empty >> slot) & 1u);
+                ph_slot_empty ^= 1u << slot;
+                uint8_t* dst = smem + OFF_SLOT + slot * SLOT_BYTES + r1_base;
+#pragma unroll
+                for (int i1 = 0; i1 < 16; i1++) {
+                    const uint32_t off = (uint32_t)(i1 >> 2) * 512u + (uint32_t)(i1 & 3) * 128u + ((((uint32_t)(lo >> 2)) ^ (uint32_t)(i1 & 3)) << 4);
+                    *reinterpret_cast<uint32_t*>(dst + off) = r0[i1];
+                    *reinterpret_cast<uint32_t*>(dst + 8192 + off) = r1[i1];
+                }
+                fence_async_smem();
+                mbar_arrive(&bars[SLOT_FULL0 + slot]);
+                slot = slot + 1 == SLOTS ? 0 : slot + 1;
+            }
+            TT_MARK(0, 0x60000 + j * 256);
+            tt_wait(bars, D2_FULL, ph_d2f);
+            ph_d2f ^= 1;
+            tc_fence_after();
+            for (int p = 0; p < 8; p++) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(tq + TM_D2 + p * 16, r0);
+                tmem_ld16(tq + TM_D2 + 128 + p * 16, r1);
+                tmem_ld_wait();
+                if (p == 7) { tc_fence_before(); mbar_arrive(&bars[D2_EMPTY]); }
+                TT_MARK(0, 0x70000 + j * 256 + p);
+                tt_wait(bars, SLOT_EMPTY0 + slot, (ph_slot_empty >> slot) & 1u);
+                ph_slot_empty ^= 1u << slot;
+                uint8_t* dst = smem + OFF_SLOT + slot * SLOT_BYTES;
+#pragma unroll
+                for (int cidx = 0; cidx < 16; cidx++) {
+                    const int b1l = cidx >> 3, o2l = cidx & 7;
+                    const uint32_t kbyte = (uint32_t)(b1l * 16 + i1_2) * 4u;
+                    const uint32_t row0 = (uint32_t)(o2l * 16 + hb2 * 4 + q);
+                    *reinterpret_cast<uint32_t*>(dst + sw128_off(row0, kbyte)) = r0[cidx];
+                    *reinterpret_cast<uint32_t*>(dst + sw128_off(row0 + 8, kbyte)) = r1[cidx];
+                }
+                fence_async_smem();
+                mbar_arrive(&bars[SLOT_FULL0 + slot]);
+                slot = slot + 1 == SLOTS ? 0 : slot + 1;
+            }
+            // output: D3 lane m' = o2l*16 + t*8 + hb*4 + q', column o1
+            TT_MARK(0, 0x80000 + j * 256);
+            tt_wait(bars, D3_FULL, ph_d3f);
+            ph_d3f ^= 1;
+            tc_fence_after();
+            uint32_t acc[16];
+            tmem_ld16(tq + TM_D3, acc);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[D3_EMPTY]);
+            const int mrow = q * 32 + lane;
+            const int o2 = 8 * h + (mrow >> 4), o3 = 8 * ((mrow >> 3) & 1) + 2 * (mrow & 3) + ((mrow >> 2) & 1);
+            float* yo = y + (size_t)s * 4096 + o2 * 16 + o3;
+            const float* bo = bias ? bias + o2 * 16 + o3 : nullptr;
+#pragma unroll
+            for (int o1 = 0; o1 < 16; o1++) {
+                float v = __uint_as_float(acc[o1]) + (bo ? __ldg(bo + o1 * 256) : 0.0f);
+                if (relu) v = fmaxf(v, 0.0f);
+                yo[o1 * 256] = v;
+            }
+        }
+    }
+    TT_MARK(0, 0x90000);
+    tc_fence_before();
+    __syncthreads();
+    TT_MARK(0, 0xA0000);
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem, TM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;              // the driver entry point is process-wide, not per device
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int tt_dense3_tf32(const float* x, const float* img, const float* bias, float* y, int batch, int relu, cudaStream_t st) {
+    SYN_REQUIRE(x && img && y && batch >= 0, "syn_tt_dense3_tf32: null argument");
+    if (batch == 0) return 0;
+    SYN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)img) | ((uintptr_t)y)) & 15) == 0, "syn_tt_dense3_tf32: x, weights and y must be 16-byte aligned");
+    EncodeTiledFn enc = encode_tiled_fn();
+    SYN_REQUIRE(enc != nullptr, "syn_tt_dense3_tf32: cuTensorMapEncodeTiled is not available from this driver");
+    // x[s][i1][i2][i3] seen as a rank-4 tensor with dimensions (i3, i1, i2, s): one box = one sample, landing as rows (i2, i1) of 64 bytes
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {16, 16, 16, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {1024, 64, 16384};               // bytes, dimensions 1..3
+    const cuuint32_t box[4] = {16, 16, 16, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SYN_REQUIRE(cr == CUDA_SUCCESS, "syn_tt_dense3_tf32: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
+        SYN_CUDA(cudaFuncSetAttribute(tt_dense3_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        configured.set(dev_);
+    }
+    int grid = sm_count() & ~1;                                     // CTA pairs (o2 halves) share the samples
+    if (const char* e = getenv("SYN_TT_GRID")) { int g = atoi(e) & ~1; if (g >= 2 && g < grid) grid = g; }   // experiment knob
+    if (grid > 2 * batch) grid = 2 * batch;
+    tt_dense3_tf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(map, img, bias, y, batch, relu);
+    return launch_status("tt_dense3_tf32_kernel");
+}
+
+}  // namespace tt
+}  // namespace syn
+
+#ifdef SYN_TT_DEBUG
+extern "C" int syn_tt_debug_buffer(uint32_t* host_mapped_device_ptr) {
+    return cudaMemcpyToSymbol(syn::tt::g_tt_dbg, &host_mapped_device_ptr, sizeof(uint32_t*)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+extern "C" size_t syn_tt_dense3_packed_floats(void) { return syn::tt::IMG_FLOATS; }
+
+extern "C" int syn_tt_dense3_pack_tf32(const float* G1, const float* G2, const float* G3, float* packed, void* stream) {
+    using namespace syn;
+    SYN_REQUIRE(G1 && G2 && G3 && packed, "syn_tt_dense3_pack_tf32: null argument");
+    tt::tt_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(G1, G2, G3, packed);
+    return launch_status("tt_pack_kernel");
+}
+
+extern "C" int syn_tt_dense3_tf32(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream) {
+    return syn::tt::tt_dense3_tf32(x, packed, bias, y, batch, relu, (cudaStream_t)stream);
+}

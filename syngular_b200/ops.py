@@ -366,6 +366,38 @@ def bias_act_(y, bias, act="relu"):
     return y
 
 
+lib.syn_tt_dense3_packed_floats.restype = ctypes.c_size_t
+
+
+def tt_dense3_fits(tt_input_shape, tt_output_shape, tt_bond_shape):
+    """Shapes covered by the fused tcgen05 TF32 kernel (csrc/ttdense.cu): three cores, every mode and bond equal to 16."""
+    return tuple(tt_input_shape) == (16, 16, 16) and tuple(tt_output_shape) == (16, 16, 16) and tuple(tt_bond_shape) == (16, 16)
+
+
+def tt_dense3_pack(G1, G2, G3):
+    """Cores in the reference's layouts (float32 CUDA: (16,16,16), (16,16,16,16), (16,16,16)) -> the pre-swizzled operand images."""
+    for g, shape in ((G1, (16, 16, 16)), (G2, (16, 16, 16, 16)), (G3, (16, 16, 16))):
+        if not (g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == shape):
+            raise SynError("tt_dense3_pack: expected contiguous CUDA float32 cores of extent 16, got %r %r" % (tuple(g.shape), g.dtype))
+    packed = torch.empty(int(lib.syn_tt_dense3_packed_floats()), dtype=torch.float32, device=G1.device)
+    check(lib.syn_tt_dense3_pack_tf32(ptr(G1), ptr(G2), ptr(G3), ptr(packed), stream_ptr()), "syn_tt_dense3_pack_tf32")
+    return packed
+
+
+def tt_dense3_tf32(x, packed, bias=None, relu=True, out=None):
+    """y = act(TT-matvec(x) + bias) for a (batch, 4096) float32 CUDA input, on tcgen05.mma.kind::tf32 (one fused launch)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[1] == 4096):
+        raise SynError("tt_dense3_tf32: expected a contiguous CUDA float32 (batch, 4096) input")
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape
+    if bias is not None:
+        assert bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == 4096
+    check(lib.syn_tt_dense3_tf32(ptr(x), ptr(packed), ptr(bias) if bias is not None else None, ptr(out), _i32(x.shape[0]), _i32(1 if relu else 0),
+                                 stream_ptr()), "syn_tt_dense3_tf32")
+    return out
+
+
 def jacobi_rows_f32(G, max_sweeps=30, tol=None, null_rel=1e-6):
     """FP32 one-sided Jacobi on the rows of a contiguous float32 (n x n) matrix, in place (preconditioning sweeps)."""
     assert G.is_cuda and G.dtype == torch.float32 and G.dim() == 2 and G.is_contiguous()
