@@ -18,11 +18,12 @@
 // the TMEM lane: a warp's 32 lanes then write 32 consecutive words of one or two operand rows (conflict-free, one wavefront), in the
 // UMMA canonical K-major swizzled layout the next tcgen05.mma reads through its shared-memory descriptor.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over its samples):
+// Warp roles (64 + 128 GROUPS threads, one CTA per SM, persistent over its samples):
 //   warp 0     TMA producer: weights once (pre-swizzled images, cp.async.bulk), then one 16 KB tensor-map load per sample
 //              (cp.async.bulk.tensor.4d, 64B swizzle, box = the whole sample re-ordered to rows (i2,i1))
 //   warp 1     TMEM allocation + the single MMA-issuing thread (software pipeline: step 1 runs two chunks ahead of step 2)
-//   warps 2-5  epilogue: tcgen05.ld -> st.shared re-layouts, final tcgen05.ld + bias + ReLU + coalesced global stores
+//   warps 2..  epilogue, in GROUPS groups of four warps (one per TMEM lane quadrant) that take alternate chunks: tcgen05.ld -> st.shared
+//              re-layouts, final tcgen05.ld + bias + ReLU + coalesced global stores
 // Pipelines (mbarriers): x full/empty, D1 double buffer full/empty, a ring of three 16 KB operand slots full/empty shared by the
 // T1 and T2 re-layouts, D2 full/empty, D3 full/empty.
 //
@@ -37,7 +38,8 @@ namespace syn {
 
 namespace tt {
 
-constexpr int THREADS = 192;
+constexpr int GROUPS = 2;                                       // epilogue groups of four warps
+constexpr int THREADS = 64 + 128 * GROUPS;
 constexpr int SLOTS = 3;
 constexpr uint32_t SLOT_BYTES = 16384;
 // shared-memory map (offsets from a 1024-byte aligned base)
@@ -69,6 +71,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (the same one every time): the warp stays uniform around the single-thread tcgen05 instructions, so
+// the compiler keeps descriptors and addresses in uniform registers instead of moving them there lane by lane
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -93,6 +103,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 16 || N == 8, "tmem_ld: 8 or 16 columns");
+    if constexpr (N == 16) {
+        tmem_ld16(taddr, r);
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr) : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -199,9 +220,9 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             mbar_init(&bars[SLOT_EMPTY0 + s], 1);
         }
         mbar_init(&bars[D2_FULL], 1);
-        mbar_init(&bars[D2_EMPTY], 128);
+        mbar_init(&bars[D2_EMPTY], 128 * GROUPS);
         mbar_init(&bars[D3_FULL], 1);
-        mbar_init(&bars[D3_EMPTY], 128);
+        mbar_init(&bars[D3_EMPTY], 128 * GROUPS);
         fence_async_smem();
     }
     TT_MARK(2, 1);
@@ -222,92 +243,100 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             bulk_g2s(smem + OFF_B3, img + IMG_B3, 16384u, &bars[W_FULL]);
             for (int a = 0; a < 8; a++)
                 bulk_g2s(smem + OFF_B2 + a * 16384, img + IMG_B2 + (size_t)h * 32768 + (size_t)a * 4096, 16384u, &bars[W_FULL]);
-            uint32_t ph_empty = 1;                                   // a fresh barrier passes a wait on the "previous" phase
             for (int j = 0; j < my_samples; j++) {
                 TT_MARK(0, 0x100 + j);
-                tt_wait(bars, X_EMPTY, ph_empty);
-                ph_empty ^= 1;
+                tt_wait(bars, X_EMPTY, (uint32_t)(j & 1) ^ 1u);      // a fresh barrier passes a wait on the "previous" phase
                 TT_MARK(1, 0x100 + j);
                 mbar_expect_tx(&bars[X_FULL], 16384u);
                 tma_load_4d(smem + OFF_X, &xmap, 0, 0, 0, first + j * step, &bars[X_FULL]);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====================================================================================================
-        if (lane == 0) {
+        // ===== MMA issuer (the whole warp runs the loop; one elected lane issues) ==========================================================
+        // Every ring position has a running use count u (24 operand-slot uses per sample: 16 T1 chunks, 8 T2 chunks; 8 uses of each D1
+        // buffer): slot = u % SLOTS, and the parity to wait for is (u / SLOTS) & 1 on a "full" barrier, the opposite on an "empty" one.
+        {
             constexpr uint32_t ID_S1 = idesc_tf32(128, 16), ID_S2 = idesc_tf32(128, 128), ID_S3 = idesc_tf32(128, 16);
-            constexpr int LAG = 2;
+            constexpr int LAG = 2;                                   // step 1 runs LAG chunks ahead of step 2 (= number of D1 buffers)
+            // descriptor templates: everything but the start address; a k-step of 8 TF32 (32 bytes) adds 2 to the address field
+            const uint64_t d64 = smem_desc(0, 512, LAYOUT_SW64), d128 = smem_desc(0, 1024, LAYOUT_SW128);
+            const uint64_t a1_desc = d64 + ((sbase + OFF_A1) >> 4), x_desc = d64 + ((sbase + OFF_X) >> 4);
+            const uint64_t b2_desc = d128 + ((sbase + OFF_B2) >> 4), b3_desc = d128 + ((sbase + OFF_B3) >> 4);
+            const uint64_t slot64_desc = d64 + ((sbase + OFF_SLOT) >> 4), slot128_desc = d128 + ((sbase + OFF_SLOT) >> 4);
             tt_wait(bars, W_FULL, 0);
-            uint32_t ph_x = 0, ph_d1e = 3, ph_d2e = 1, ph_d3e = 1;      // "empty" barriers: a fresh barrier passes a wait on parity 1
-            uint32_t slot = 0, ph_slot_full = 0;                        // one phase bit per slot / buffer
             for (int j = 0; j < my_samples; j++) {
                 for (int c = 0; c < 16 + LAG; c++) {
                     if (c < 16) {
                         // step 1, chunk c (= i2): D1[c & 1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16)
                         const int b = c & 1;
+                        const uint32_t use = (uint32_t)(8 * j + (c >> 1));
                         TT_MARK(0, 0x10000 + j * 256 + c);
-                        if (c == 0) { tt_wait(bars, X_FULL, ph_x); ph_x ^= 1; }
-                        TT_MARK(1, 0x10000 + j * 256 + c);
-                        tt_wait(bars, D1_EMPTY0 + b, (ph_d1e >> b) & 1u);
-                        ph_d1e ^= 1u << b;
+                        if (c == 0) tt_wait(bars, X_FULL, (uint32_t)(j & 1));
+                        tt_wait(bars, D1_EMPTY0 + b, (use & 1u) ^ 1u);
                         tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t xd = x_desc + (uint64_t)(c * 64);
 #pragma unroll
-                        for (int t = 0; t < 2; t++)
+                            for (int t = 0; t < 2; t++)
 #pragma unroll
-                            for (int k = 0; k < 2; k++)
-                                umma_tf32(tmem + TM_D1 + b * 32 + t * 16,
-                                          smem_desc(sbase + OFF_A1 + t * 8192 + k * 32, 512, LAYOUT_SW64),
-                                          smem_desc(sbase + OFF_X + c * 1024 + k * 32, 512, LAYOUT_SW64), ID_S1, k);
-                        umma_commit(&bars[D1_FULL0 + b]);
-                        if (c == 15) umma_commit(&bars[X_EMPTY]);
+                                for (int k = 0; k < 2; k++)
+                                    umma_tf32(tmem + TM_D1 + b * 32 + t * 16, a1_desc + (uint64_t)(t * 512 + k * 2), xd + (uint64_t)(k * 2), ID_S1, k);
+                            umma_commit(&bars[D1_FULL0 + b]);
+                            if (c == 15) umma_commit(&bars[X_EMPTY]);
+                        }
+                        __syncwarp();
                     }
                     if (c >= LAG) {
                         // step 2, chunk cc: D2[t] += T1 chunk (slot: 2 tiles of 128 x 16) . G2 half [(b1,o2l), (i2 = cc, b2)]^T
                         const int cc = c - LAG;
+                        const uint32_t u = (uint32_t)(24 * j + cc), slot = u % SLOTS;
                         TT_MARK(0, 0x20000 + j * 256 + cc);
-                        tt_wait(bars, SLOT_FULL0 + slot, (ph_slot_full >> slot) & 1u);
-                        ph_slot_full ^= 1u << slot;
-                        if (cc == 0) { tt_wait(bars, D2_EMPTY, ph_d2e); ph_d2e ^= 1; }
+                        tt_wait(bars, SLOT_FULL0 + slot, (u / SLOTS) & 1u);
+                        if (cc == 0) tt_wait(bars, D2_EMPTY, (uint32_t)(j & 1) ^ 1u);
                         tc_fence_after();
-                        const uint32_t a_base = sbase + OFF_SLOT + slot * SLOT_BYTES;
-                        const uint32_t b_base = sbase + OFF_B2 + (cc >> 1) * 16384 + (cc & 1) * 64;
+                        if (elect_one()) {
+                            const uint64_t ad = slot64_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
+                            const uint64_t bd = b2_desc + (uint64_t)((cc >> 1) * 1024 + (cc & 1) * 4);
 #pragma unroll
-                        for (int t = 0; t < 2; t++)
+                            for (int t = 0; t < 2; t++)
 #pragma unroll
-                            for (int k = 0; k < 2; k++)
-                                umma_tf32(tmem + TM_D2 + t * 128, smem_desc(a_base + t * 8192 + k * 32, 512, LAYOUT_SW64),
-                                          smem_desc(b_base + k * 32, 1024, LAYOUT_SW128), ID_S2, (cc > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&bars[SLOT_EMPTY0 + slot]);
-                        if (cc == 15) umma_commit(&bars[D2_FULL]);
-                        slot = slot + 1 == SLOTS ? 0 : slot + 1;
+                                for (int k = 0; k < 2; k++)
+                                    umma_tf32(tmem + TM_D2 + t * 128, ad + (uint64_t)(t * 512 + k * 2), bd + (uint64_t)(k * 2), ID_S2,
+                                              (cc > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(&bars[SLOT_EMPTY0 + slot]);
+                            if (cc == 15) umma_commit(&bars[D2_FULL]);
+                        }
+                        __syncwarp();
                     }
                 }
                 // step 3, chunk p (= b1 pair): D3 += T2 chunk (slot: 128 x 32) . G1 [o1, (b1, i1)]^T
                 for (int p = 0; p < 8; p++) {
+                    const uint32_t u = (uint32_t)(24 * j + 16 + p), slot = u % SLOTS;
                     TT_MARK(0, 0x30000 + j * 256 + p);
-                    tt_wait(bars, SLOT_FULL0 + slot, (ph_slot_full >> slot) & 1u);
-                    ph_slot_full ^= 1u << slot;
-                    if (p == 0) { tt_wait(bars, D3_EMPTY, ph_d3e); ph_d3e ^= 1; }
+                    tt_wait(bars, SLOT_FULL0 + slot, (u / SLOTS) & 1u);
+                    if (p == 0) tt_wait(bars, D3_EMPTY, (uint32_t)(j & 1) ^ 1u);
                     tc_fence_after();
-                    const uint32_t a_base = sbase + OFF_SLOT + slot * SLOT_BYTES;
-                    const uint32_t b_base = sbase + OFF_B3 + p * 2048;
+                    if (elect_one()) {
+                        const uint64_t ad = slot128_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
+                        const uint64_t bd = b3_desc + (uint64_t)(p * 128);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_tf32(tmem + TM_D3, smem_desc(a_base + k * 32, 1024, LAYOUT_SW128), smem_desc(b_base + k * 32, 1024, LAYOUT_SW128),
-                                  ID_S3, (p > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&bars[SLOT_EMPTY0 + slot]);
-                    if (p == 7) umma_commit(&bars[D3_FULL]);
-                    slot = slot + 1 == SLOTS ? 0 : slot + 1;
+                        for (int k = 0; k < 4; k++)
+                            umma_tf32(tmem + TM_D3, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), ID_S3, (p > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&bars[SLOT_EMPTY0 + slot]);
+                        if (p == 7) umma_commit(&bars[D3_FULL]);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else {
         // ===== epilogue warps: re-layouts and the output ===================================================================================
+        // GROUPS groups of four warps (one warp per TMEM lane quadrant); group g takes the chunks c = g (mod GROUPS) of both re-layouts, so
+        // the tcgen05.ld -> st.shared -> fence latency chains of consecutive chunks overlap, and GROUPS-th of the output columns.
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         const int hb = lane >> 4, lo = lane & 15;
-        uint32_t ph_d1f = 0, ph_d2f = 0, ph_d3f = 0;
-        uint32_t slot = 0, ph_slot_empty = (1u << SLOTS) - 1u;
         // re-layout 1: D1 lane = (o3l = 2q + hb, b2 = lo), column i1  ->  A2 slot, tile t, row m = q*32 + i1*2 + hb, k = b2        (SW64)
         //   row m: group (m >> 3) = q*4 + (i1 >> 2), in-group (m & 7) = (i1 & 3)*2 + hb, swizzle phase = i1 & 3
         const uint32_t r1_base = (uint32_t)(q * 4) * 512u + (uint32_t)hb * 64u + (uint32_t)(lo & 3) * 4u;
@@ -316,11 +345,12 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         const int hb2 = lane & 1, i1_2 = lane >> 1;
         for (int j = 0; j < my_samples; j++) {
             const int s = first + j * step;
-            for (int c = 0; c < 16; c++) {
+            for (int c = grp; c < 16; c += GROUPS) {
                 const int b = c & 1;
+                const uint32_t use = (uint32_t)(8 * j + (c >> 1));
+                const uint32_t u = (uint32_t)(24 * j + c), slot = u % SLOTS;
                 TT_MARK(0, 0x40000 + j * 256 + c);
-                tt_wait(bars, D1_FULL0 + b, (ph_d1f >> b) & 1u);
-                ph_d1f ^= 1u << b;
+                tt_wait(bars, D1_FULL0 + b, use & 1u);
                 tc_fence_after();
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tq + TM_D1 + b * 32, r0);
@@ -329,8 +359,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 tc_fence_before();
                 mbar_arrive(&bars[D1_EMPTY0 + b]);
                 TT_MARK(0, 0x50000 + j * 256 + c);
-                tt_wait(bars, SLOT_EMPTY0 + slot, (ph_slot_empty >> slot) & 1u);
-                ph_slot_empty ^= 1u << slot;
+                tt_wait(bars, SLOT_EMPTY0 + slot, ((u / SLOTS) & 1u) ^ 1u);
                 uint8_t* dst = smem + OFF_SLOT + slot * SLOT_BYTES + r1_base;
 #pragma unroll
                 for (int i1 = 0; i1 < 16; i1++) {
@@ -340,21 +369,19 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 }
                 fence_async_smem();
                 mbar_arrive(&bars[SLOT_FULL0 + slot]);
-                slot = slot + 1 == SLOTS ? 0 : slot + 1;
             }
             TT_MARK(0, 0x60000 + j * 256);
-            tt_wait(bars, D2_FULL, ph_d2f);
-            ph_d2f ^= 1;
+            tt_wait(bars, D2_FULL, (uint32_t)(j & 1));
             tc_fence_after();
-            for (int p = 0; p < 8; p++) {
+            for (int p = grp; p < 8; p += GROUPS) {
+                const uint32_t u = (uint32_t)(24 * j + 16 + p), slot = u % SLOTS;
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tq + TM_D2 + p * 16, r0);
                 tmem_ld16(tq + TM_D2 + 128 + p * 16, r1);
                 tmem_ld_wait();
-                if (p == 7) { tc_fence_before(); mbar_arrive(&bars[D2_EMPTY]); }
+                if (p + GROUPS >= 8) { tc_fence_before(); mbar_arrive(&bars[D2_EMPTY]); }      // this thread's last read of D2
                 TT_MARK(0, 0x70000 + j * 256 + p);
-                tt_wait(bars, SLOT_EMPTY0 + slot, (ph_slot_empty >> slot) & 1u);
-                ph_slot_empty ^= 1u << slot;
+                tt_wait(bars, SLOT_EMPTY0 + slot, ((u / SLOTS) & 1u) ^ 1u);
                 uint8_t* dst = smem + OFF_SLOT + slot * SLOT_BYTES;
 #pragma unroll
                 for (int cidx = 0; cidx < 16; cidx++) {
@@ -366,24 +393,23 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 }
                 fence_async_smem();
                 mbar_arrive(&bars[SLOT_FULL0 + slot]);
-                slot = slot + 1 == SLOTS ? 0 : slot + 1;
             }
-            // output: D3 lane m' = o2l*16 + t*8 + hb*4 + q', column o1
+            // output: D3 lane m' = o2l*16 + t*8 + hb*4 + q', column o1; this group stores the o1 in [grp * OC, (grp + 1) * OC)
+            constexpr int OC = 16 / GROUPS;
             TT_MARK(0, 0x80000 + j * 256);
-            tt_wait(bars, D3_FULL, ph_d3f);
-            ph_d3f ^= 1;
+            tt_wait(bars, D3_FULL, (uint32_t)(j & 1));
             tc_fence_after();
-            uint32_t acc[16];
-            tmem_ld16(tq + TM_D3, acc);
+            uint32_t acc[OC];
+            tmem_ld<OC>(tq + TM_D3 + grp * OC, acc);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[D3_EMPTY]);
             const int mrow = q * 32 + lane;
             const int o2 = 8 * h + (mrow >> 4), o3 = 8 * ((mrow >> 3) & 1) + 2 * (mrow & 3) + ((mrow >> 2) & 1);
-            float* yo = y + (size_t)s * 4096 + o2 * 16 + o3;
-            const float* bo = bias ? bias + o2 * 16 + o3 : nullptr;
+            float* yo = y + (size_t)s * 4096 + (grp * OC) * 256 + o2 * 16 + o3;
+            const float* bo = bias ? bias + (grp * OC) * 256 + o2 * 16 + o3 : nullptr;
 #pragma unroll
-            for (int o1 = 0; o1 < 16; o1++) {
+            for (int o1 = 0; o1 < OC; o1++) {
                 float v = __uint_as_float(acc[o1]) + (bo ? __ldg(bo + o1 * 256) : 0.0f);
                 if (relu) v = fmaxf(v, 0.0f);
                 yo[o1 * 256] = v;

@@ -24,3 +24,55 @@ def test_tensordense_forward_matches_restatement(ins, outs, bonds, batch):
     lin = TensorDense(ins, outs, bonds, activation=None, use_bias=False).build(cores)
     ref2 = TD.forward(x, cores, None, None)
     assert np.max(np.abs(lin(x, chunk=3).cpu().numpy() - ref2)) < 1e-10 * max(1.0, np.max(np.abs(ref2)))     # chunked path
+
+
+# ---- TF32 path: the fused tcgen05 kernel (csrc/ttdense.cu) for BASELINE configs[4]'s layer -------------------------------------------
+TF32_TOL = 4e-3        # of the output's largest magnitude: TF32 keeps 10 mantissa bits of every operand, three chained contractions
+
+
+@pytest.mark.parametrize("batch", [1, 2, 75, 300, 1111])
+def test_tensordense_tf32_fused_kernel_matches_restatement(batch):
+    """float32 in / out on tcgen05.mma.kind::tf32 against the float64 restatement of the reference's einsum (TensorDense.py:103-142) on the
+    SAME float32 weights and inputs; batch sizes cover one sample per CTA, ragged sample counts and several samples per CTA."""
+    import torch
+    from syngular.layers import TensorDense
+    from oracle import tensordense_numpy as TD
+    rng = np.random.default_rng(batch)
+    shape = (16, 16, 16)
+    layer = TensorDense(shape, shape, (16, 16), precision="tf32")
+    cores = [rng.normal(scale=0.05, size=s).astype(np.float32) for s in layer.core_shapes()]
+    bias = (0.01 * rng.normal(size=shape)).astype(np.float32)
+    layer.build(cores, bias)
+    x = rng.normal(size=(batch, 4096)).astype(np.float32)
+    got = layer(x)
+    assert got.dtype == torch.float32 and tuple(got.shape) == (batch, 4096)
+    ref = TD.forward(x.astype(np.float64), [c.astype(np.float64) for c in cores], bias.astype(np.float64), "relu")
+    assert np.max(np.abs(got.cpu().numpy() - ref)) < TF32_TOL * np.max(np.abs(ref))
+    lin = TensorDense(shape, shape, (16, 16), activation=None, use_bias=False, precision="tf32").build(cores)
+    ref2 = TD.forward(x.astype(np.float64), [c.astype(np.float64) for c in cores], None, None)
+    assert np.max(np.abs(lin(x).cpu().numpy() - ref2)) < TF32_TOL * np.max(np.abs(ref2))
+
+
+def test_tensordense_tf32_is_exact_on_exactly_representable_data():
+    """Identity-like cores and small-integer inputs are exact in TF32: any index permutation inside the kernel's re-layouts would show."""
+    from syngular.layers import TensorDense
+    shape = (16, 16, 16)
+    I1 = np.zeros((16, 16, 16)); I2 = np.zeros((16, 16, 16, 16)); I3 = np.zeros((16, 16, 16))
+    for i in range(16):
+        I1[i, i, 0] = 1; I2[i, i, 0, 0] = 1; I3[i, i, 0] = 1
+    layer = TensorDense(shape, shape, (16, 16), activation=None, use_bias=False, precision="tf32").build([I1, I2, I3])
+    x = (np.arange(5 * 4096) % 1021).astype(np.float32).reshape(5, 4096)
+    assert np.array_equal(layer(x).cpu().numpy(), x)
+    # a permutation layer: out (o1,o2,o3) = in (i1,i2,i3) with every mode index reversed
+    P1 = np.zeros((16, 16, 16)); P2 = np.zeros((16, 16, 16, 16)); P3 = np.zeros((16, 16, 16))
+    for i in range(16):
+        P1[i, 15 - i, 3] = 1; P2[i, 15 - i, 3, 7] = 1; P3[i, 15 - i, 7] = 1
+    layer = TensorDense(shape, shape, (16, 16), activation=None, use_bias=False, precision="tf32").build([P1, P2, P3])
+    want = x.reshape(5, 16, 16, 16)[:, ::-1, ::-1, ::-1].reshape(5, 4096)
+    assert np.array_equal(layer(x).cpu().numpy(), want)
+
+
+def test_tensordense_tf32_rejects_uncovered_shapes():
+    from syngular.layers import TensorDense
+    with pytest.raises(NotImplementedError):
+        TensorDense((8, 8, 8), (8, 8, 8), (4, 4), precision="tf32")
