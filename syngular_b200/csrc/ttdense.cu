@@ -20,15 +20,17 @@
 //
 // Warp roles (64 + 128 GROUPS threads, one CTA per SM, persistent over its samples):
 //   warp 0     TMA producer: weights once (pre-swizzled images, cp.async.bulk), then one 16 KB tensor-map load per sample
-//              (cp.async.bulk.tensor.4d, 64B swizzle, box = the whole sample re-ordered to rows (i2,i1))
-//   warp 1     TMEM allocation + the single MMA-issuing thread (software pipeline: step 1 runs two chunks ahead of step 2)
+//              (cp.async.bulk.tensor.4d, 64B swizzle, box = the whole sample re-ordered to rows (i2,i1)); it also issues the step-1
+//              MMAs, which run ahead of step 2 through NB1 accumulator buffers
+//   warp 1     TMEM allocation + the step-2 / step-3 MMA issue (an independent instruction stream: a wait on an operand slot
+//              never holds step 1 back)
 //   warps 2..  epilogue, in GROUPS groups of four warps (one per TMEM lane quadrant) that take alternate chunks: tcgen05.ld -> st.shared
 //              re-layouts, final tcgen05.ld + bias + ReLU + coalesced global stores
-// Pipelines (mbarriers): x full/empty, D1 double buffer full/empty, a ring of three 16 KB operand slots full/empty shared by the
+// Pipelines (mbarriers): x full/empty, D1 buffers full/empty, a ring of three 16 KB operand slots full/empty shared by the
 // T1 and T2 re-layouts, D2 full/empty, D3 full/empty.
 //
 // Shared memory (one CTA per SM): G2 half image 128 KB + 3 operand slots 48 KB + G3 image 16 KB + G1 image 16 KB + x 16 KB = 224 KB.
-// TMEM: D1 2x2x16 columns, D2 2x128, D3 16 -> 336 of 512 columns.
+// TMEM: D1 NB1 x 2 x 16 columns, D2 2 x 128, D3 16 -> 400 of 512 columns.
 #include <cuda.h>
 #include <cstdlib>
 
@@ -41,6 +43,7 @@ namespace tt {
 constexpr int GROUPS = 2;                                       // epilogue groups of four warps
 constexpr int THREADS = 64 + 128 * GROUPS;
 constexpr int SLOTS = 3;
+constexpr int NB1 = 4;                                          // D1 (step-1 accumulator) buffers: step 1 runs up to NB1 chunks ahead
 constexpr uint32_t SLOT_BYTES = 16384;
 // shared-memory map (offsets from a 1024-byte aligned base)
 constexpr uint32_t OFF_B2 = 0;                                  // 8 atoms x [128 rows x 128 B]   (SW128, K-major)
@@ -53,10 +56,12 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;           // + slack for t
 // packed weight image in global memory (floats): [A1 16 KB][B3 16 KB][B2 half 0 128 KB][B2 half 1 128 KB]
 constexpr size_t IMG_A1 = 0, IMG_B3 = 4096, IMG_B2 = 8192, IMG_FLOATS = 8192 + 2 * 32768;
 // TMEM columns
-constexpr uint32_t TM_D1 = 0, TM_D2 = 64, TM_D3 = 320, TM_COLS = 512;
+constexpr uint32_t TM_D1 = 0, TM_D2 = 32 * NB1, TM_D3 = TM_D2 + 256, TM_COLS = 512;
+static_assert(TM_D3 + 16 <= TM_COLS, "TMEM columns");
 
-enum Bar { W_FULL = 0, X_FULL, X_EMPTY, D1_FULL0, D1_FULL1, D1_EMPTY0, D1_EMPTY1, SLOT_FULL0, SLOT_EMPTY0 = SLOT_FULL0 + SLOTS,
+enum Bar { W_FULL = 0, X_FULL, X_EMPTY, D1_FULL0, D1_EMPTY0 = D1_FULL0 + NB1, SLOT_FULL0 = D1_EMPTY0 + NB1, SLOT_EMPTY0 = SLOT_FULL0 + SLOTS,
            D2_FULL = SLOT_EMPTY0 + SLOTS, D2_EMPTY, D3_FULL, D3_EMPTY, NUM_BARS };
+static_assert(NB1 % GROUPS == 0 && 16 % NB1 == 0, "a D1 buffer must always be drained by the same epilogue group");
 
 // byte offset of element (row, kbyte) in a K-major operand block with 128-byte rows / 128B swizzle, resp. 64-byte rows / 64B swizzle
 __host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t kbyte) {
@@ -211,10 +216,10 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         mbar_init(&bars[W_FULL], 1);
         mbar_init(&bars[X_FULL], 1);
         mbar_init(&bars[X_EMPTY], 1);
-        mbar_init(&bars[D1_FULL0], 1);
-        mbar_init(&bars[D1_FULL1], 1);
-        mbar_init(&bars[D1_EMPTY0], 128);
-        mbar_init(&bars[D1_EMPTY1], 128);
+        for (int b = 0; b < NB1; b++) {
+            mbar_init(&bars[D1_FULL0 + b], 1);
+            mbar_init(&bars[D1_EMPTY0 + b], 128);
+        }
         for (int s = 0; s < SLOTS; s++) {
             mbar_init(&bars[SLOT_FULL0 + s], 128);
             mbar_init(&bars[SLOT_EMPTY0 + s], 1);
@@ -234,8 +239,11 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
     const uint32_t tmem = *tmem_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer ==============================================================================================================
-        if (lane == 0) {
+        // ===== TMA producer + step-1 issuer (the whole warp runs the loop; one elected lane issues) =========================================
+        constexpr uint32_t ID_S1 = idesc_tf32(128, 16);
+        const uint64_t d64 = smem_desc(0, 512, LAYOUT_SW64);
+        const uint64_t a1_desc = d64 + ((sbase + OFF_A1) >> 4), x_desc = d64 + ((sbase + OFF_X) >> 4);
+        if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
             // weights: A1 (16 KB), B3 (16 KB), this CTA's half of B2 (128 KB in 8 copies)
             mbar_expect_tx(&bars[W_FULL], 16384u + 16384u + 131072u);
@@ -243,71 +251,71 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             bulk_g2s(smem + OFF_B3, img + IMG_B3, 16384u, &bars[W_FULL]);
             for (int a = 0; a < 8; a++)
                 bulk_g2s(smem + OFF_B2 + a * 16384, img + IMG_B2 + (size_t)h * 32768 + (size_t)a * 4096, 16384u, &bars[W_FULL]);
-            for (int j = 0; j < my_samples; j++) {
-                TT_MARK(0, 0x100 + j);
-                tt_wait(bars, X_EMPTY, (uint32_t)(j & 1) ^ 1u);      // a fresh barrier passes a wait on the "previous" phase
-                TT_MARK(1, 0x100 + j);
+        }
+        __syncwarp();
+        tt_wait(bars, W_FULL, 0);
+        for (int j = 0; j < my_samples; j++) {
+            TT_MARK(0, 0x100 + j);
+            tt_wait(bars, X_EMPTY, (uint32_t)(j & 1) ^ 1u);          // a fresh barrier passes a wait on the "previous" phase
+            if (elect_one()) {
                 mbar_expect_tx(&bars[X_FULL], 16384u);
                 tma_load_4d(smem + OFF_X, &xmap, 0, 0, 0, first + j * step, &bars[X_FULL]);
             }
+            __syncwarp();
+            tt_wait(bars, X_FULL, (uint32_t)(j & 1));
+            // step 1, chunk c (= i2): D1[c % NB1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16); runs ahead of step 2 as far as
+            // the D1 buffers allow
+            for (int c = 0; c < 16; c++) {
+                const int b = c % NB1;
+                const uint32_t use = (uint32_t)((16 / NB1) * j + c / NB1);
+                TT_MARK(0, 0x10000 + j * 256 + c);
+                tt_wait(bars, D1_EMPTY0 + b, (use & 1u) ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t xd = x_desc + (uint64_t)(c * 64);
+#pragma unroll
+                    for (int t = 0; t < 2; t++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++)
+                            umma_tf32(tmem + TM_D1 + b * 32 + t * 16, a1_desc + (uint64_t)(t * 512 + k * 2), xd + (uint64_t)(k * 2), ID_S1, k);
+                    umma_commit(&bars[D1_FULL0 + b]);
+                    if (c == 15) umma_commit(&bars[X_EMPTY]);
+                }
+                __syncwarp();
+            }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (the whole warp runs the loop; one elected lane issues) ==========================================================
-        // Every ring position has a running use count u (24 operand-slot uses per sample: 16 T1 chunks, 8 T2 chunks; 8 uses of each D1
-        // buffer): slot = u % SLOTS, and the parity to wait for is (u / SLOTS) & 1 on a "full" barrier, the opposite on an "empty" one.
+        // ===== step-2 / step-3 issuer (the whole warp runs the loop; one elected lane issues) ===============================================
+        // Every ring position has a running use count u (24 operand-slot uses per sample: 16 T1 chunks, 8 T2 chunks):
+        // slot = u % SLOTS, and the parity to wait for is (u / SLOTS) & 1 on a "full" barrier, the opposite on an "empty" one.
         {
-            constexpr uint32_t ID_S1 = idesc_tf32(128, 16), ID_S2 = idesc_tf32(128, 128), ID_S3 = idesc_tf32(128, 16);
-            constexpr int LAG = 2;                                   // step 1 runs LAG chunks ahead of step 2 (= number of D1 buffers)
+            constexpr uint32_t ID_S2 = idesc_tf32(128, 128), ID_S3 = idesc_tf32(128, 16);
             // descriptor templates: everything but the start address; a k-step of 8 TF32 (32 bytes) adds 2 to the address field
             const uint64_t d64 = smem_desc(0, 512, LAYOUT_SW64), d128 = smem_desc(0, 1024, LAYOUT_SW128);
-            const uint64_t a1_desc = d64 + ((sbase + OFF_A1) >> 4), x_desc = d64 + ((sbase + OFF_X) >> 4);
             const uint64_t b2_desc = d128 + ((sbase + OFF_B2) >> 4), b3_desc = d128 + ((sbase + OFF_B3) >> 4);
             const uint64_t slot64_desc = d64 + ((sbase + OFF_SLOT) >> 4), slot128_desc = d128 + ((sbase + OFF_SLOT) >> 4);
             tt_wait(bars, W_FULL, 0);
             for (int j = 0; j < my_samples; j++) {
-                for (int c = 0; c < 16 + LAG; c++) {
-                    if (c < 16) {
-                        // step 1, chunk c (= i2): D1[c & 1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16)
-                        const int b = c & 1;
-                        const uint32_t use = (uint32_t)(8 * j + (c >> 1));
-                        TT_MARK(0, 0x10000 + j * 256 + c);
-                        if (c == 0) tt_wait(bars, X_FULL, (uint32_t)(j & 1));
-                        tt_wait(bars, D1_EMPTY0 + b, (use & 1u) ^ 1u);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t xd = x_desc + (uint64_t)(c * 64);
+                // step 2, chunk cc: D2[t] += T1 chunk (slot: 2 tiles of 128 x 16) . G2 half [(b1,o2l), (i2 = cc, b2)]^T
+                for (int cc = 0; cc < 16; cc++) {
+                    const uint32_t u = (uint32_t)(24 * j + cc), slot = u % SLOTS;
+                    TT_MARK(0, 0x20000 + j * 256 + cc);
+                    tt_wait(bars, SLOT_FULL0 + slot, (u / SLOTS) & 1u);
+                    if (cc == 0) tt_wait(bars, D2_EMPTY, (uint32_t)(j & 1) ^ 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = slot64_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
+                        const uint64_t bd = b2_desc + (uint64_t)((cc >> 1) * 1024 + (cc & 1) * 4);
 #pragma unroll
-                            for (int t = 0; t < 2; t++)
+                        for (int t = 0; t < 2; t++)
 #pragma unroll
-                                for (int k = 0; k < 2; k++)
-                                    umma_tf32(tmem + TM_D1 + b * 32 + t * 16, a1_desc + (uint64_t)(t * 512 + k * 2), xd + (uint64_t)(k * 2), ID_S1, k);
-                            umma_commit(&bars[D1_FULL0 + b]);
-                            if (c == 15) umma_commit(&bars[X_EMPTY]);
-                        }
-                        __syncwarp();
+                            for (int k = 0; k < 2; k++)
+                                umma_tf32(tmem + TM_D2 + t * 128, ad + (uint64_t)(t * 512 + k * 2), bd + (uint64_t)(k * 2), ID_S2,
+                                          (cc > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&bars[SLOT_EMPTY0 + slot]);
+                        if (cc == 15) umma_commit(&bars[D2_FULL]);
                     }
-                    if (c >= LAG) {
-                        // step 2, chunk cc: D2[t] += T1 chunk (slot: 2 tiles of 128 x 16) . G2 half [(b1,o2l), (i2 = cc, b2)]^T
-                        const int cc = c - LAG;
-                        const uint32_t u = (uint32_t)(24 * j + cc), slot = u % SLOTS;
-                        TT_MARK(0, 0x20000 + j * 256 + cc);
-                        tt_wait(bars, SLOT_FULL0 + slot, (u / SLOTS) & 1u);
-                        if (cc == 0) tt_wait(bars, D2_EMPTY, (uint32_t)(j & 1) ^ 1u);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t ad = slot64_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
-                            const uint64_t bd = b2_desc + (uint64_t)((cc >> 1) * 1024 + (cc & 1) * 4);
-#pragma unroll
-                            for (int t = 0; t < 2; t++)
-#pragma unroll
-                                for (int k = 0; k < 2; k++)
-                                    umma_tf32(tmem + TM_D2 + t * 128, ad + (uint64_t)(t * 512 + k * 2), bd + (uint64_t)(k * 2), ID_S2,
-                                              (cc > 0 || k > 0) ? 1u : 0u);
-                            umma_commit(&bars[SLOT_EMPTY0 + slot]);
-                            if (cc == 15) umma_commit(&bars[D2_FULL]);
-                        }
-                        __syncwarp();
-                    }
+                    __syncwarp();
                 }
                 // step 3, chunk p (= b1 pair): D3 += T2 chunk (slot: 128 x 32) . G1 [o1, (b1, i1)]^T
                 for (int p = 0; p < 8; p++) {
@@ -346,8 +354,8 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         for (int j = 0; j < my_samples; j++) {
             const int s = first + j * step;
             for (int c = grp; c < 16; c += GROUPS) {
-                const int b = c & 1;
-                const uint32_t use = (uint32_t)(8 * j + (c >> 1));
+                const int b = c % NB1;
+                const uint32_t use = (uint32_t)((16 / NB1) * j + c / NB1);
                 const uint32_t u = (uint32_t)(24 * j + c), slot = u % SLOTS;
                 TT_MARK(0, 0x40000 + j * 256 + c);
                 tt_wait(bars, D1_FULL0 + b, use & 1u);
