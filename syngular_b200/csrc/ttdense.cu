@@ -61,7 +61,10 @@ static_assert(TM_D3 + 16 <= TM_COLS, "TMEM columns");
 
 enum Bar { W_FULL = 0, X_FULL, X_EMPTY, D1_FULL0, D1_EMPTY0 = D1_FULL0 + NB1, SLOT_FULL0 = D1_EMPTY0 + NB1, SLOT_EMPTY0 = SLOT_FULL0 + SLOTS,
            D2_FULL = SLOT_EMPTY0 + SLOTS, D2_EMPTY, D3_FULL, D3_EMPTY, NUM_BARS };
-static_assert(NB1 % GROUPS == 0 && 16 % NB1 == 0, "a D1 buffer must always be drained by the same epilogue group");
+static_assert(NB1 % GROUPS == 0, "a D1 buffer must always be drained by the same epilogue group");
+// mbarrier waits are by parity: a waiter may run at most one phase ahead.  An epilogue group takes every GROUPS-th chunk and its wait on
+// a slot proves that the chunk SLOTS uses earlier was consumed, so it stays within one phase only if GROUPS <= SLOTS.
+static_assert(GROUPS <= SLOTS, "epilogue groups could run two phases ahead of an operand slot");
 
 // byte offset of element (row, kbyte) in a K-major operand block with 128-byte rows / 128B swizzle, resp. 64-byte rows / 64B swizzle
 __host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t kbyte) {
@@ -111,9 +114,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
-    static_assert(N == 16 || N == 8, "tmem_ld: 8 or 16 columns");
+    static_assert(N == 16 || N == 8 || N == 4, "tmem_ld: 4, 8 or 16 columns");
     if constexpr (N == 16) {
         tmem_ld16(taddr, r);
+    } else if constexpr (N == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
     } else {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -227,7 +233,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         mbar_init(&bars[D2_FULL], 1);
         mbar_init(&bars[D2_EMPTY], 128 * GROUPS);
         mbar_init(&bars[D3_FULL], 1);
-        mbar_init(&bars[D3_EMPTY], 128 * GROUPS);
+        mbar_init(&bars[D3_EMPTY], 128);
         fence_async_smem();
     }
     TT_MARK(2, 1);
@@ -266,8 +272,8 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             // step 1, chunk c (= i2): D1[c % NB1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16); runs ahead of step 2 as far as
             // the D1 buffers allow
             for (int c = 0; c < 16; c++) {
-                const int b = c % NB1;
-                const uint32_t use = (uint32_t)((16 / NB1) * j + c / NB1);
+                const uint32_t g1 = (uint32_t)(16 * j + c);          // running chunk count: D1 buffer g1 % NB1, its use g1 / NB1
+                const uint32_t b = g1 % NB1, use = g1 / NB1;
                 TT_MARK(0, 0x10000 + j * 256 + c);
                 tt_wait(bars, D1_EMPTY0 + b, (use & 1u) ^ 1u);
                 tc_fence_after();
@@ -353,9 +359,10 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         const int hb2 = lane & 1, i1_2 = lane >> 1;
         for (int j = 0; j < my_samples; j++) {
             const int s = first + j * step;
-            for (int c = grp; c < 16; c += GROUPS) {
-                const int b = c % NB1;
-                const uint32_t use = (uint32_t)((16 / NB1) * j + c / NB1);
+            for (int c = 0; c < 16; c++) {
+                const uint32_t g1 = (uint32_t)(16 * j + c);          // running chunk count: group g1 % GROUPS, D1 buffer g1 % NB1
+                if (g1 % GROUPS != (uint32_t)grp) continue;
+                const uint32_t b = g1 % NB1, use = g1 / NB1;
                 const uint32_t u = (uint32_t)(24 * j + c), slot = u % SLOTS;
                 TT_MARK(0, 0x40000 + j * 256 + c);
                 tt_wait(bars, D1_FULL0 + b, use & 1u);
@@ -381,13 +388,17 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             TT_MARK(0, 0x60000 + j * 256);
             tt_wait(bars, D2_FULL, (uint32_t)(j & 1));
             tc_fence_after();
-            for (int p = grp; p < 8; p += GROUPS) {
+            int last_p = -1;                                         // this group's last T2 chunk of the sample: its last read of D2
+            for (int p = 0; p < 8; p++)
+                if ((uint32_t)(8 * j + p) % GROUPS == (uint32_t)grp) last_p = p;
+            for (int p = 0; p < 8; p++) {
+                if ((uint32_t)(8 * j + p) % GROUPS != (uint32_t)grp) continue;
                 const uint32_t u = (uint32_t)(24 * j + 16 + p), slot = u % SLOTS;
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tq + TM_D2 + p * 16, r0);
                 tmem_ld16(tq + TM_D2 + 128 + p * 16, r1);
                 tmem_ld_wait();
-                if (p + GROUPS >= 8) { tc_fence_before(); mbar_arrive(&bars[D2_EMPTY]); }      // this thread's last read of D2
+                if (p == last_p) { tc_fence_before(); mbar_arrive(&bars[D2_EMPTY]); }
                 TT_MARK(0, 0x70000 + j * 256 + p);
                 tt_wait(bars, SLOT_EMPTY0 + slot, ((u / SLOTS) & 1u) ^ 1u);
                 uint8_t* dst = smem + OFF_SLOT + slot * SLOT_BYTES;
@@ -402,22 +413,22 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 fence_async_smem();
                 mbar_arrive(&bars[SLOT_FULL0 + slot]);
             }
-            // output: D3 lane m' = o2l*16 + t*8 + hb*4 + q', column o1; this group stores the o1 in [grp * OC, (grp + 1) * OC)
-            constexpr int OC = 16 / GROUPS;
+            // output: D3 lane m' = o2l*16 + t*8 + hb*4 + q', column o1; the groups take the samples' outputs in turn
+            if (j % GROUPS != grp) continue;
             TT_MARK(0, 0x80000 + j * 256);
             tt_wait(bars, D3_FULL, (uint32_t)(j & 1));
             tc_fence_after();
-            uint32_t acc[OC];
-            tmem_ld<OC>(tq + TM_D3 + grp * OC, acc);
+            uint32_t acc[16];
+            tmem_ld16(tq + TM_D3, acc);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[D3_EMPTY]);
             const int mrow = q * 32 + lane;
             const int o2 = 8 * h + (mrow >> 4), o3 = 8 * ((mrow >> 3) & 1) + 2 * (mrow & 3) + ((mrow >> 2) & 1);
-            float* yo = y + (size_t)s * 4096 + (grp * OC) * 256 + o2 * 16 + o3;
-            const float* bo = bias ? bias + (grp * OC) * 256 + o2 * 16 + o3 : nullptr;
+            float* yo = y + (size_t)s * 4096 + o2 * 16 + o3;
+            const float* bo = bias ? bias + o2 * 16 + o3 : nullptr;
 #pragma unroll
-            for (int o1 = 0; o1 < OC; o1++) {
+            for (int o1 = 0; o1 < 16; o1++) {
                 float v = __uint_as_float(acc[o1]) + (bo ? __ldg(bo + o1 * 256) : 0.0f);
                 if (relu) v = fmaxf(v, 0.0f);
                 yo[o1 * 256] = v;
