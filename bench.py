@@ -194,6 +194,257 @@ def run_reference(args):
     emit(line)
 
 
+class Runtime:
+    """torch.distributed / CUDA plumbing shared by the workloads: one process per GPU, barrier + synchronize around every timed
+    region, CUDA events on the launching stream, MAX over ranks."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.dev = torch.device("cuda", self.local)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def finish(self, line):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+        if self.rank == 0:
+            emit(line)
+
+
+def cublas_peak(torch, dev, dtype, allow_tf32=False):
+    """Tensor-pipe roofline denominator measured in this process with a library GEMM (8192^3, burst, best of 6): MEASURED_PEAKS.json
+    carries HBM and bf16 only."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    try:
+        a = torch.randn(8192, 8192, dtype=dtype, device=dev)
+        b = torch.randn(8192, 8192, dtype=dtype, device=dev)
+        best = 1e30
+        for _ in range(6):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(); torch.matmul(a, b); p1.record(); torch.cuda.synchronize()
+            best = min(best, p0.elapsed_time(p1))
+        return 2 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: TensorDense forward, MPO (16,16,16)x(16,16,16) bond 16, batch 65536 x 4096, batch-sharded
+# ---------------------------------------------------------------------------------------------------------------------
+C5_BATCH, C5_FLOP_PER_SAMPLE = 65536, 3.7748736e7          # 2 * (16 + 256 + 16) * 65536  (SURVEY 8(d) C5)
+
+
+def c5_cpu_forward(x, cores, bias):
+    """The reference's float32 arithmetic (layers/TensorDense.py:103-142) restated with numpy tensordot on the host cores."""
+    T = x.reshape(x.shape[0], 16, 16, 16)
+    T = np.tensordot(T, cores[0], axes=([1], [0]))                 # (s, i2, i3, o1, b1)
+    T = np.tensordot(T, cores[1], axes=([1, 4], [0, 2]))           # (s, i3, o1, o2, b2)
+    T = np.tensordot(T, cores[2], axes=([1, 4], [0, 2]))           # (s, o1, o2, o3)
+    return np.maximum(T.reshape(x.shape[0], -1) + bias.reshape(-1), 0)
+
+
+def run_c5(args):
+    rt = Runtime()
+    torch = rt.torch
+    from syngular.layers import TensorDense
+    from syngular_b200 import ops, parallel
+    lo, hi = parallel.shard_bounds(C5_BATCH, rt.rank, rt.world)
+    rng = np.random.default_rng(5)
+    cores = [rng.normal(scale=0.05, size=s).astype(np.float32) for s in ((16, 16, 16), (16, 16, 16, 16), (16, 16, 16))]
+    bias = np.zeros((16, 16, 16), np.float32)
+    layer = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), precision="tf32").build(cores, bias)
+    g = torch.Generator(device=rt.dev).manual_seed(500 + rt.rank)
+    x = torch.randn((hi - lo, 4096), dtype=torch.float32, device=rt.dev, generator=g)
+    xh = x.cpu().pin_memory()
+    yh = torch.empty_like(xh).pin_memory()
+    out = torch.empty_like(x)
+
+    def step_device():
+        return ops.tt_dense3_tf32(x, layer._packed, layer._bias32, relu=True, out=out)
+
+    def step_e2e():
+        xd = xh.to(rt.dev, non_blocking=True)                      # H2D of the step's inputs from pinned host memory
+        yh.copy_(layer(xd), non_blocking=True)                     # the public API call, result copied back
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_device()
+    sampler = ClockSampler(rt.local)
+    if rt.rank == 0:
+        sampler.start()
+    l0 = ops.lib.syn_launch_count()
+    ms = rt.timed(step_device, args.steps)
+    launches = (ops.lib.syn_launch_count() - l0) / float(args.steps)
+    clocks = sampler.stop() if rt.rank == 0 else None
+    value = C5_BATCH * args.steps / (ms * 1e-3)
+    step_e2e()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e = rt.timed(step_e2e, e2e_steps)
+    line = None
+    if rt.rank == 0:
+        # parity inside the bench: the first 512 samples against the float64 restatement (stated TF32 tolerance 4e-3 of the scale)
+        from oracle import tensordense_numpy as TD
+        ref = TD.forward(x[:512].cpu().numpy().astype(np.float64), [c.astype(np.float64) for c in cores], bias.astype(np.float64), "relu")
+        err = float(np.max(np.abs(out[:512].cpu().numpy() - ref)) / np.max(np.abs(ref)))
+        peak = cublas_peak(torch, rt.dev, torch.float32, allow_tf32=True)
+        per_launch_ms = ms / args.steps
+        achieved = C5_FLOP_PER_SAMPLE * (hi - lo) / (per_launch_ms * 1e-3) / 1e12
+        cpu = None
+        if rt.world == 1 and not args.no_cpu:
+            use_all_host_threads()
+            n_cpu = 4096
+            xs = x[:n_cpu].cpu().numpy()
+            c5_cpu_forward(xs[:256], cores, bias)
+            t0 = time.perf_counter()
+            c5_cpu_forward(xs, cores, bias)
+            sec = time.perf_counter() - t0
+            cpu = {"value": n_cpu / sec, "unit": "samples/s", "cores": host_threads(), "kind": "port",
+                   "sample": "float32 numpy tensordot restatement of layers/TensorDense.py:103-142 on the first %d samples of the batch (%.2f s)" % (n_cpu, sec)}
+        line = {
+            "metric": "tensordense_forward_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": rt.world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": "C5 TensorDense forward: MPO (16,16,16)x(16,16,16) bond 16, batch 65536 x 4096 float32, bias + ReLU, batch-sharded",
+                       "l2": "inputs larger than L2: 1.07 GB of x and 1.07 GB of y per step", "multi_gpu": "batch sharded in contiguous blocks, no collective (outputs stay sharded)",
+                       "parity_rel_err_first_512": err, "tolerance": 4e-3},
+            "clocks": clocks,
+            "e2e": {"value": C5_BATCH * e2e_steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": int(yh.numel() * 4),
+                    "steps": e2e_steps, "api": "TensorDense(..., precision='tf32')(x) on a pinned host batch, output copied back"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "tt_dense3_tf32_kernel (tcgen05.mma.kind::tf32)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this process",
+                         "flop_per_sample": C5_FLOP_PER_SAMPLE},
+            "cpu_baseline": cpu,
+        }
+    rt.finish(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: 8192 independent random MPS (N=32, d=2, chi=64): overlaps <A_b|B_b>, batch-sharded, ONE all-gather
+# ---------------------------------------------------------------------------------------------------------------------
+C4_BATCH, C4_SITES, C4_CHI = 8192, 32, 64
+
+
+def run_c4(args):
+    rt = Runtime()
+    torch = rt.torch
+    from syngular_b200 import ops, parallel
+    from syngular_b200.batched import BatchedMatrixProductState as BMPS
+    lo, hi = parallel.shard_bounds(C4_BATCH, rt.rank, rt.world)
+    bonds = capped_bonds(C4_SITES, 2, C4_CHI)[1:-1]
+    A = BMPS.random(hi - lo, (2,) * C4_SITES, bonds, seed=1000 + rt.rank, device=rt.dev)
+    B = BMPS.random(hi - lo, (2,) * C4_SITES, bonds, seed=2000 + rt.rank, device=rt.dev)
+    full = [1] + list(bonds) + [1]
+    flops = sum(4.0 * 2 * a * b * max(a, b) for a, b in zip(full[:-1], full[1:])) * C4_BATCH
+    bytes_ = 2 * 8.0 * sum(a * 2 * b for a, b in zip(full[:-1], full[1:])) * C4_BATCH
+
+    def step_device():
+        return parallel.gather_scalars(A.overlap(B), C4_BATCH)
+
+    # end to end: a sub-batch of E2E_N pairs per rank from pinned host memory (the full sets are 2 x 12 GB), overlaps copied back
+    e2e_n = min(1024, hi - lo)
+    Ah = [c[:e2e_n].cpu().pin_memory() for c in A.sites]
+    Bh = [c[:e2e_n].cpu().pin_memory() for c in B.sites]
+    res_h = torch.empty(e2e_n, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        a = BMPS([c.to(rt.dev, non_blocking=True) for c in Ah])
+        b = BMPS([c.to(rt.dev, non_blocking=True) for c in Bh])
+        res_h.copy_(a.overlap(b), non_blocking=True)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        ov = step_device()
+    sampler = ClockSampler(rt.local)
+    if rt.rank == 0:
+        sampler.start()
+    l0 = ops.lib.syn_launch_count()
+    ms = rt.timed(step_device, args.steps)
+    launches = (ops.lib.syn_launch_count() - l0) / float(args.steps)
+    clocks = sampler.stop() if rt.rank == 0 else None
+    value = C4_BATCH * args.steps / (ms * 1e-3)
+    step_e2e()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e = rt.timed(step_e2e, e2e_steps)
+    line = None
+    if rt.rank == 0:
+        # parity inside the bench: the first 4 pairs against the oracle's transfer-matrix contraction
+        from oracle import ref_numpy as R
+        errs = []
+        for b in range(4):
+            got = float(ov[b].item())
+            want = float(R.overlap([c[b].cpu().numpy() for c in A.sites], [c[b].cpu().numpy() for c in B.sites]))
+            errs.append(abs(got - want) / max(abs(want), 1e-300))
+        peak = cublas_peak(torch, rt.dev, torch.float64)
+        achieved = flops / rt.world / (ms / args.steps * 1e-3) / 1e12
+        cpu = None
+        if rt.world == 1 and not args.no_cpu:
+            use_all_host_threads()
+            n_cpu = 64
+            host = [([c[b].cpu().numpy() for c in A.sites], [c[b].cpu().numpy() for c in B.sites]) for b in range(n_cpu)]
+            t0 = time.perf_counter()
+            for a, b in host:
+                R.overlap(a, b)
+            sec = time.perf_counter() - t0
+            cpu = {"value": n_cpu / sec, "unit": "states/s", "cores": host_threads(), "kind": "port",
+                   "sample": "oracle transfer-matrix `|` (ref_numpy.overlap, MPS:116-129) looped over the first %d pairs (%.2f s)" % (n_cpu, sec)}
+        line = {
+            "metric": "batched_overlap_states_per_s", "value": value, "unit": "states/s", "n_gpus": rt.world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 batched inner products: 8192 independent random MPS pairs (N=32, d=2, chi=64), batch-sharded, one all-gather of 8192 float64",
+                       "l2": "inputs larger than L2: 24 GB of cores per step over all ranks", "multi_gpu": "contiguous batch blocks per rank; the only collective is the all-gather of the scalars",
+                       "parity_rel_err_first_4": max(errs), "hbm_gbs_algorithmic": bytes_ / rt.world / (ms / args.steps * 1e-3) / 1e9,
+                       "hbm_peak_gbs": measured_peaks().get("hbm_gbs")},
+            "clocks": clocks,
+            "e2e": {"value": rt.world * e2e_n * e2e_steps / (ms_e2e * 1e-3), "unit": "states/s",
+                    "h2d_bytes_per_step": int(sum(c.numel() for c in Ah + Bh) * 8), "d2h_bytes_per_step": int(e2e_n * 8), "steps": e2e_steps,
+                    "api": "BatchedMatrixProductState(host cores).overlap(...) on a %d-pair sub-batch per rank from pinned host memory" % e2e_n},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "overlap_chain_kernel (DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this process",
+                         "note": "FP64 compute governs this kernel in FP64 (SURVEY 8(d) K8): 4 d chi^3 flop against 16 d chi^2 bytes per plateau site"},
+            "cpu_baseline": cpu,
+        }
+    rt.finish(line)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -204,7 +455,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: ONE JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import syngular as syn
     from syngular.tensor import MatrixProductOperator as MPO, MatrixProductState as MPS, _sweeps as sw
@@ -313,14 +563,21 @@ def run_ours(args):
     del A4, B4, sub
     # BASELINE configs[4]: TensorDense forward, MPO (16,16,16)x(16,16,16) bond 16, batch 65536 x 4096, batch-sharded
     from syngular.layers import TensorDense
-    layer5 = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), seed=5).build()
+    layer5 = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), seed=5, precision="tf32").build()
     lo5, hi5 = parallel.shard_bounds(65536, rank, world)
     g5 = torch.Generator(device=dev).manual_seed(500 + rank)
-    x5 = torch.randn((hi5 - lo5, 4096), dtype=torch.float64, device=dev, generator=g5)
-    layer5(x5[:4096])
-    ms_c5 = timed(lambda: layer5(x5), 1)
+    x5 = torch.randn((hi5 - lo5, 4096), dtype=torch.float32, device=dev, generator=g5)
+    y5 = torch.empty_like(x5)
+    step_c5 = lambda: ops.tt_dense3_tf32(x5, layer5._packed, layer5._bias32, relu=True, out=y5)
+    step_c5(); step_c5()
+    ms_c5 = timed(step_c5, 3) / 3
     c5_value = 65536 / (ms_c5 * 1e-3)
-    del x5
+    layer5_f64 = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), seed=5).build()
+    x5d = x5[:8192].to(torch.float64)
+    layer5_f64(x5d)
+    ms_c5_f64 = timed(lambda: layer5_f64(x5d), 1)
+    c5_f64_value = world * 8192 / (ms_c5_f64 * 1e-3)
+    del x5, x5d, y5
 
     # BASELINE configs[0]: the README chain (readme.md:53-73) from the reference's decomposed cores (tests/golden), GPU vs the
     # numpy oracle on the host; tiny tensors (d = 16, bonds <= 24): launch-latency territory, reported for completeness
@@ -460,8 +717,8 @@ def run_ours(args):
                                      world, c4_flops / (ms_c4 / c4_reps * 1e-3) / 1e12, c4_bytes / (ms_c4 / c4_reps * 1e-3) / 1e9,
                                      "ok" if ov_ok else "BAD"),
                       "c5_tensordense_samples_per_s": c5_value,
-                      "c5_note": "configs[4] forward in FP64 on the DMMA GEMM (%.1f TFLOP/s); the reference computes in float32 -- a TF32 "
-                                 "tcgen05 kernel is the planned fast path" % (3.78e7 * 65536 / (ms_c5 * 1e-3) / 1e12),
+                      "c5_note": "configs[4] forward, float32 in/out on the fused tcgen05.mma.kind::tf32 kernel (%.0f TFLOP/s; `--workload c5` prints the "
+                                 "full line); the FP64 DMMA-GEMM path of the same layer: %.0f samples/s" % (3.7748736e7 * 65536 / (ms_c5 * 1e-3) / 1e12, c5_f64_value),
                       "c4_apply_qr_round_states_per_s": c4_apply_qr, "c4_apply_svd_round_states_per_s": c4_apply_svd,
                       "c4_apply_note": "configs[3](ii): shared MPO chi_W=4 applied + rounded to chi=64, batched over 256 states per rank",
                       "qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),
@@ -501,9 +758,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default, the headline): single-chain apply + SVD-round; c4: batched overlaps (states/s); c5: TensorDense forward (samples/s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -172,6 +172,7 @@ __device__ __forceinline__ int rotate_cached(R (&ra)[NREG], R& na, R* __restrict
     }
     na = fma(-t, ab, na);
     if (lane == 0) *nb = fma(t, ab, bb);
+    __syncwarp();          // the cached norm is read by every lane of this warp in its next rotation (racecheck: intra-warp RAW)
     return kind;
 }
 

@@ -14,6 +14,9 @@ for s in $steps; do
     svdlist) ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_svd.csv python tools/profile_sweep.py svd > gpurun_out/${tag}_svdlist.log 2>&1; tail -2 gpurun_out/${tag}_svdlist.log ;;
     ovncu) ncu --set full --clock-control none --import-source on -k regex:overlap -s 2 -c 1 -f -o gpurun_out/${tag}_overlap python tools/overlap_bench.py 2048 > gpurun_out/${tag}_ovncu.log 2>&1; tail -3 gpurun_out/${tag}_ovncu.log ;;
     gemmshapes) python tools/gemm_shapes.py svd > gpurun_out/${tag}_gemm_shapes_svd.txt 2>&1; python tools/gemm_shapes.py qr > gpurun_out/${tag}_gemm_shapes_qr.txt 2>&1; head -12 gpurun_out/${tag}_gemm_shapes_svd.txt ;;
+    benchc4) python bench.py --workload c4 > gpurun_out/${tag}_bench_c4.json 2> gpurun_out/${tag}_bench_c4.err; tail -c 400 gpurun_out/${tag}_bench_c4.json ;;
+    benchc5) python bench.py --workload c5 > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err; tail -c 400 gpurun_out/${tag}_bench_c5.json ;;
+    sanitize) tools/sanitize.sh ${tag} ;;
     *) echo "unknown step $s" ;;
   esac
 done

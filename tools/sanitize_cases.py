@@ -1,0 +1,64 @@
+"""Small invocations of every kernel that synchronises by hand (grid barriers, version words, DSMEM exchanges, mbarrier pipelines),
+for compute-sanitizer (tools/sanitize.sh): purify / orthonormalise, Jacobi (single- and multi-CTA), cluster QR, Householder QR,
+Cholesky, fused overlap, environment sandwich, strided GEMM (TMA and cp.async variants), the TF32 tcgen05 layer kernel."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from syngular_b200 import ops
+from syngular.tensor import _sweeps as sw
+import bench
+
+which = sys.argv[1:] or ["gemm", "purify", "ortho", "jacobi", "qr", "chol", "overlap", "sweep", "ttdense"]
+dev = torch.device("cuda")
+rng = np.random.default_rng(0)
+
+
+def spd(n, gap_at):
+    q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    lam = np.concatenate([np.linspace(1.0, 0.5, gap_at), np.linspace(0.05, 0.001, n - gap_at)])
+    return torch.from_numpy((q * lam) @ q.T).to(dev)
+
+
+if "gemm" in which:
+    a = torch.randn(256, 128, dtype=torch.float64, device=dev); b = torch.randn(128, 384, dtype=torch.float64, device=dev)
+    assert torch.allclose(ops.matmul(a, b), a @ b)
+    a = torch.randn(70, 33, dtype=torch.float64, device=dev); b = torch.randn(33, 45, dtype=torch.float64, device=dev)
+    assert torch.allclose(ops.matmul(a, b), a @ b)
+if "purify" in which:
+    A = spd(128, 64)
+    U, info = ops.dominant_subspace(A, 64, 52, 26, sp2_max=90, ns_max=60)
+    assert float((U.t() @ U - torch.eye(64, dtype=torch.float64, device=dev)).abs().max()) < 1e-10
+if "ortho" in which:
+    L = torch.randn(256, 64, dtype=torch.float64, device=dev)
+    Q, info = ops.orthonormalize_columns(L)
+    assert float((Q.t() @ Q - torch.eye(64, dtype=torch.float64, device=dev)).abs().max()) < 1e-10
+if "jacobi" in which:
+    for n in (48, 160):
+        G = spd(n, n // 2).contiguous()
+        Ut, sigma, info, winfo = ops.jacobi_solve(G.clone(), n, sqrt_mode=True)
+        assert int(info[1]) == n
+if "qr" in which:
+    for m, n, q in ((96, 40, 24), (512, 128, 64)):
+        L = torch.randn(m, n, dtype=torch.float64, device=dev)
+        Q, S = ops.qrt(L, q)
+        assert float((Q.t() @ Q - torch.eye(Q.shape[1], dtype=torch.float64, device=dev)).abs().max()) < 1e-10
+if "chol" in which:
+    G = spd(192, 96).contiguous()
+    B, shift = ops.chol_upper(G.clone())
+if "overlap" in which:
+    from syngular_b200.batched import BatchedMatrixProductState as BMPS
+    bonds = bench.capped_bonds(12, 2, 32)[1:-1]
+    A = BMPS.random(5, (2,) * 12, bonds, seed=1); B = BMPS.random(5, (2,) * 12, bonds, seed=2)
+    A.overlap(B)
+if "sweep" in which:
+    X, W = bench.make_chain(3, n=14, chi=64, chiw=16)
+    Xd = [sw.as_core(x) for x in X]; Wd = [sw.as_core(w) for w in W]
+    sw.apply_round_dm(Xd, Wd, 64)
+    sw.apply_round_qr(Xd, Wd, 64)
+if "ttdense" in which:
+    from syngular.layers import TensorDense
+    layer = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), seed=1, precision="tf32").build()
+    layer(np.random.default_rng(1).normal(size=(5, 4096)).astype(np.float32))
+torch.cuda.synchronize()
+print("sanitize cases ok:", " ".join(which))
