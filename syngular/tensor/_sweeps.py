@@ -629,7 +629,7 @@ def right_environments(X, W):
     return E
 
 
-ENV_SYMMETRIC_BLOCK = 64       # a-block of the block-lower environment build (0 = full GEMM)
+ENV_SYMMETRIC_BLOCK = 128      # a-block of the block-lower environment build (0 = full GEMM); 128: every launch is whole 128 x 128 tiles
 
 
 def _w_sandwich_gemms(P1, Wk, a, i, b, l, o, r, D):

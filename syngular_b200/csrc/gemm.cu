@@ -40,9 +40,8 @@ struct OperandLoader {
     static constexpr int CH = (ALONG_ROWS ? ROWS : C::BK) / VEC;       // chunks per line
     static constexpr int LINES = ALONG_ROWS ? C::BK : ROWS;            // number of lines
     static constexpr int LINES_PER_PASS = T / CH;
-    static constexpr int PASSES = LINES / LINES_PER_PASS;
-    static_assert(T % CH == 0, "thread count must be a multiple of chunks per line");
-    static_assert(LINES % LINES_PER_PASS == 0, "lines must divide evenly");
+    static constexpr int PASSES = LINES_PER_PASS > 0 ? LINES / (LINES_PER_PASS > 0 ? LINES_PER_PASS : 1) : 1;
+    static constexpr bool USABLE = (T % CH == 0) && LINES_PER_PASS > 0 && (LINES % (LINES_PER_PASS > 0 ? LINES_PER_PASS : 1) == 0);
 
     int pos;            // position along the contiguous dimension (element index within tile)
     int line0;          // first line handled by this thread
@@ -53,6 +52,7 @@ struct OperandLoader {
     unsigned row_ok;
 
     __device__ __forceinline__ void init(const syn_index_t& rows_ix, int row0, int nrows, int tid) {
+        static_assert(USABLE, "cp.async loader: thread count must be a multiple of the chunks per line, lines must divide evenly");
         pos = (tid % CH) * VEC;
         line0 = tid / CH;
         if constexpr (ALONG_ROWS) {
@@ -159,7 +159,14 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
         }
         __syncthreads();
     }
-    // TMA producer side: every tile line is owned by one thread, which arms the stage barrier with its bytes and issues the copy
+    // TMA producer side: every tile line is owned by one thread, which arms the stage barrier with its bytes and issues the copy.
+    // A B tile whose lines run along n may hang over the right edge of the matrix (the 128 x 112 configuration: N need not be a
+    // multiple of 112): its lines are copied short; the stale tail of the stage only feeds output columns the epilogue masks.
+    uint32_t b_line_bytes = TB::LINE_BYTES;
+    if constexpr (TMA && B_ALONG_N) {
+        const int left = d.N - n0;
+        if (left < C::BN) b_line_bytes = (uint32_t)left * (uint32_t)sizeof(double);
+    }
     auto tma_fill = [&](int stage, int k0) {
         for (int line = tid; line < TA::LINES + TB::LINES; line += C::THREADS) {
             if (line < TA::LINES) {
@@ -167,8 +174,8 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
                 bulk_g2s(sA + stage * LA::TILE_ELEMS + line * TA::STRIDE, TA::src(A, d.a_m, d.a_k, m0, k0, line), TA::LINE_BYTES, &full_bar[stage]);
             } else {
                 const int l = line - TA::LINES;
-                mbar_expect_tx(&full_bar[stage], TB::LINE_BYTES);
-                bulk_g2s(sB + stage * LB::TILE_ELEMS + l * TB::STRIDE, TB::src(B, d.b_n, d.b_k, n0, k0, l), TB::LINE_BYTES, &full_bar[stage]);
+                mbar_expect_tx(&full_bar[stage], b_line_bytes);
+                bulk_g2s(sB + stage * LB::TILE_ELEMS + l * TB::STRIDE, TB::src(B, d.b_n, d.b_k, n0, k0, l), b_line_bytes, &full_bar[stage]);
             }
         }
     };
@@ -283,6 +290,11 @@ using CfgL = GemmCfg<128, 128, 32, 64, 32, 3>;   // 256 threads, 1 CTA/SM, 212 K
 using CfgS = GemmCfg<64, 64, 32, 32, 32, 3>;     // 128 threads, 107 KB smem, 2 CTAs/SM
 using CfgW = GemmCfg<128, 128, 32, 32, 32, 3>;   // 512 threads (4 warps per SM sub-partition), 32x32 warp tiles
 
+// 128 x 112 tiles, 16 warps of 16 x 56: an output of 512 x 4096 (the M.E product of the density-matrix sweep) is 4 x 37 = 148 tiles -- one
+// full wave of the 148 SMs -- where 128 x 128 tiles give 128 (13 % of the machine idle).  TMA-staged only (no cp.async loader exists
+// for 112-wide lines), A k-contiguous, B n-contiguous.
+using CfgT = GemmCfg<128, 112, 32, 16, 56, 3>;
+
 using CfgN = GemmCfg<128, 32, 32, 32, 32, 2>;    // skinny outputs (N <= 32): 128 threads, 92 KB smem
 using CfgM = GemmCfg<32, 128, 32, 32, 32, 2>;    // flat outputs (M <= 32)
 
@@ -336,6 +348,23 @@ static bool tma_eligible(const syn_gemm_desc_t& d, bool am, bool bn, int vec) {
     const bool a_ok = am ? tma_line_ok(d.a_m, d.M, C::BM) : tma_line_ok(d.a_k, d.K, C::BK);
     const bool b_ok = bn ? tma_line_ok(d.b_n, d.N, C::BN) : tma_line_ok(d.b_k, d.K, C::BK);
     return a_ok && b_ok;
+}
+
+// time of the 128 x BN tiling in units of "columns per SM": waves * BN
+static long long wave_cost(const syn_gemm_desc_t& d, int bn) {
+    const long long tiles = (long long)((d.M + 127) / 128) * ((d.N + bn - 1) / bn) * d.batch;
+    const long long sms = sm_count();
+    return ((tiles + sms - 1) / sms) * bn;
+}
+
+// the 128 x 112 TMA configuration: eligible layouts only, and only where it saves a wave
+static bool prefer_cfg_t(const syn_gemm_desc_t& d, bool am, bool bn, int vec) {
+    if (!gemm_env_tma() || vec != 2 || am || !bn) return false;
+    if (d.M % 128 || d.K % 32 || (d.N & 1) || d.N < 112) return false;
+    if (!tma_line_ok(d.a_k, d.K, 32)) return false;
+    // B lines run along n: every tile start n0 = j * 112 must stay inside one contiguous, 16-byte aligned run
+    if (!(d.b_n.inner == 1 && d.b_n.div >= d.N)) return false;
+    return wave_cost(d, 112) * 100 < wave_cost(d, 128) * 95;
 }
 
 template <class C>
@@ -401,6 +430,7 @@ int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double*
     if (forced == 3) return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     if (d.N <= 32 && d.M >= 128) return dispatch_layout<CfgN>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     if (d.M <= 32 && d.N >= 128) return dispatch_layout<CfgM>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (use_large && !forced && prefer_cfg_t(d, a_along_m, b_along_n, vec)) return launch_gemm<CfgT, false, true, 2, true>(d, A, B, C, c_vec, st);
     if (use_large) return dispatch_layout<CfgW>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
 }

@@ -66,3 +66,22 @@ def test_gemm_two_level_indices_site_contraction():
              c_m=(l_ * o_ * b_ * r_, r_, b_), c_n=(b_ * r_, 1, r_),
              batch=l_, a_b=0, b_b=i_ * o_ * r_, c_b=o_ * b_ * r_)
     assert (out - ref).abs().max().item() < 1e-13
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 4096, 128), (512, 4096, 4096), (256, 8232, 64), (128, 16464, 96)])
+def test_gemm_128x112_wave_configuration(M, N, K):
+    """Shapes where 128 x 112 tiles fill the 148 SMs in fewer waves than 128 x 128 (csrc/gemm.cu: CfgT, TMA-staged, the last column tile
+    hangs over the edge: 4096 = 36 * 112 + 64, 8232 = 73 * 112 + 56): the M.E product of the density-matrix sweep takes this path."""
+    from syngular_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn((M, K), dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn((K, N), dtype=torch.float64, device="cuda", generator=g)
+    _check(ops.matmul(a, b), a @ b, a, b)
+    c0 = torch.randn((M, N), dtype=torch.float64, device="cuda", generator=g)
+    _check(ops.matmul(a, b, out=c0.clone(), alpha=0.25, beta=-1.0), 0.25 * (a @ b) - c0, a, b, tol=1e-12)
+    # the sweep's own call: output columns permuted on the fly by a two-level C index (gram_with_environment)
+    if N == 4096:
+        out = torch.empty((M, N), dtype=torch.float64, device="cuda")
+        ops.gemm(a, b, out, M=M, N=N, K=K, a_m=K, a_k=1, b_k=N, b_n=1, c_m=N, c_n=(1, 16, 256))
+        ref = (a @ b).reshape(M, 16, 256).transpose(1, 2).reshape(M, N)
+        _check(out, ref, a, b)
