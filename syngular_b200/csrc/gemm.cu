@@ -113,6 +113,74 @@ struct BulkLoader {
     }
 };
 
+// One k-stage (BK deep) of a warp's WM x WN sub-tile from shared memory: fragments are double-buffered in registers -- the loads of
+// k-step kk+4 are issued before the DMMAs of step kk, into registers the in-flight DMMAs do not read (no WAR/RAW serialisation between
+// the LDS and the tensor pipe).
+template <class C, bool A_ALONG_M, bool B_ALONG_N, int SA, int SB>
+__device__ __forceinline__ void gemm_stage(const double* __restrict__ a_s, const double* __restrict__ b_s, int wm0, int wn0, int g, int t,
+                                           double (&acc)[C::MT][C::NT][2]) {
+    double af[2][C::MT], bf[2][C::NT];
+    auto load_frags = [&](int buf, int kk) {
+#pragma unroll
+        for (int i = 0; i < C::MT; i++) {
+            int r = wm0 + i * 8 + g;
+            af[buf][i] = A_ALONG_M ? a_s[(kk + t) * SA + r] : a_s[r * SA + kk + t];
+        }
+#pragma unroll
+        for (int j = 0; j < C::NT; j++) {
+            int c = wn0 + j * 8 + g;
+            bf[buf][j] = B_ALONG_N ? b_s[(kk + t) * SB + c] : b_s[c * SB + kk + t];
+        }
+    };
+    load_frags(0, 0);
+#pragma unroll
+    for (int kk = 0; kk < C::BK; kk += 4) {
+        const int cur = (kk >> 2) & 1;
+        if (kk + 4 < C::BK) load_frags(cur ^ 1, kk + 4);
+#pragma unroll
+        for (int i = 0; i < C::MT; i++)
+#pragma unroll
+            for (int j = 0; j < C::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+    }
+}
+
+// Epilogue of one warp sub-tile whose first row / column is (mw, nw): the thread owns C[row = g][col = 2t, 2t+1] of every 8x8 block.
+template <class C>
+__device__ __forceinline__ void gemm_store_tile(const syn_gemm_desc_t& d, double* __restrict__ Cmat, const double (&acc)[C::MT][C::NT][2], int mw,
+                                                int nw, int g, int t, int c_vec) {
+    const double alpha = d.alpha, beta = d.beta;
+#pragma unroll
+    for (int i = 0; i < C::MT; i++) {
+        int m = mw + i * 8 + g;
+        if (m >= d.M) continue;
+        int64_t mo = idx2(d.c_m, m);
+#pragma unroll
+        for (int j = 0; j < C::NT; j++) {
+            int n = nw + j * 8 + 2 * t;
+            if (n >= d.N) continue;
+            double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+            int64_t o0 = mo + idx2(d.c_n, n);
+            if (c_vec && (n + 1 < d.N)) {
+                double2* p = reinterpret_cast<double2*>(Cmat + o0);
+                if (beta != 0.0) {
+                    double2 old = *p;
+                    v0 += beta * old.x;
+                    v1 += beta * old.y;
+                }
+                *p = make_double2(v0, v1);
+            } else {
+                if (beta != 0.0) v0 += beta * Cmat[o0];
+                Cmat[o0] = v0;
+                if (n + 1 < d.N) {
+                    int64_t o1 = mo + idx2(d.c_n, n + 1);
+                    if (beta != 0.0) v1 += beta * Cmat[o1];
+                    Cmat[o1] = v1;
+                }
+            }
+        }
+    }
+}
+
 template <class C, bool A_ALONG_M, bool B_ALONG_N, int VEC, bool TMA>
 __global__ void __launch_bounds__(C::THREADS)
 gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const double* __restrict__ B,
@@ -221,67 +289,105 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
             }
             if constexpr (!TMA) cp_async_commit();
         }
-        const double* a_s = sA + (kt % C::STAGES) * LA::TILE_ELEMS;
-        const double* b_s = sB + (kt % C::STAGES) * LB::TILE_ELEMS;
-        // fragments are double-buffered in registers: the loads of k-step kk+4 are issued before the DMMAs of step kk, into
-        // registers the in-flight DMMAs do not read (no WAR/RAW serialisation between the LDS and the tensor pipe)
-        double af[2][C::MT], bf[2][C::NT];
-        auto load_frags = [&](int buf, int kk) {
-#pragma unroll
-            for (int i = 0; i < C::MT; i++) {
-                int r = wm0 + i * 8 + g;
-                af[buf][i] = A_ALONG_M ? a_s[(kk + t) * LA::STRIDE + r] : a_s[r * LA::STRIDE + kk + t];
-            }
-#pragma unroll
-            for (int j = 0; j < C::NT; j++) {
-                int c = wn0 + j * 8 + g;
-                bf[buf][j] = B_ALONG_N ? b_s[(kk + t) * LB::STRIDE + c] : b_s[c * LB::STRIDE + kk + t];
-            }
-        };
-        load_frags(0, 0);
-#pragma unroll
-        for (int kk = 0; kk < C::BK; kk += 4) {
-            const int cur = (kk >> 2) & 1;
-            if (kk + 4 < C::BK) load_frags(cur ^ 1, kk + 4);
-#pragma unroll
-            for (int i = 0; i < C::MT; i++)
-#pragma unroll
-                for (int j = 0; j < C::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
-        }
+        gemm_stage<C, A_ALONG_M, B_ALONG_N, LA::STRIDE, LB::STRIDE>(sA + (kt % C::STAGES) * LA::TILE_ELEMS, sB + (kt % C::STAGES) * LB::TILE_ELEMS,
+                                                                       wm0, wn0, g, t, acc);
     }
     if constexpr (!TMA) cp_async_wait<0>();
 
-    // epilogue: thread owns C[row = g][col = 2t, 2t+1] of every 8x8 tile
-    const double alpha = d.alpha, beta = d.beta;
+    gemm_store_tile<C>(d, Cmat, acc, m0 + wm0, n0 + wn0, g, t, c_vec);
+}
+
+// Persistent TMA variant for problems of many tiles with a short contraction (the X.E product of the environment update: 2048 tiles of
+// 8 k-stages): one CTA per SM walks its tiles and the operand ring runs ON ACROSS TILE BOUNDARIES -- the first stages of the next tile
+// are in flight while the last stages of this one are multiplied and its accumulators are stored, so the per-tile pipeline fill and
+// the epilogue's exposed latency (15 % of a K = 256 tile) disappear.  Tiles are numbered batch-major, then with the shorter tile
+// dimension fastest, and CTA c takes tiles c, c + grid, ...: CTAs that run together share operand tiles through L2 as before.
+template <class C, bool A_ALONG_M, bool B_ALONG_N>
+__global__ void __launch_bounds__(C::THREADS)
+gemm_f64_persistent_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ Cmat,
+                           int tiles_m, int tiles_n, int c_vec) {
+    using LA = OperandLoader<C, C::BM, A_ALONG_M, 2>;
+    using LB = OperandLoader<C, C::BN, B_ALONG_N, 2>;
+    using TA = BulkLoader<C, C::BM, A_ALONG_M>;
+    using TB = BulkLoader<C, C::BN, B_ALONG_N>;
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;
+    double* sB = smem + C::STAGES * LA::TILE_ELEMS;
+    __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp / C::WARPS_N) * C::WM;
+    const int wn0 = (warp % C::WARPS_N) * C::WN;
+    const int per_batch = tiles_m * tiles_n;
+    const long long total = (long long)per_batch * d.batch;
+    const int KT = d.K / C::BK;
+
+    if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < C::MT; i++) {
-        int m = m0 + wm0 + i * 8 + g;
-        if (m >= d.M) continue;
-        int64_t mo = idx2(d.c_m, m);
-#pragma unroll
-        for (int j = 0; j < C::NT; j++) {
-            int n = n0 + wn0 + j * 8 + 2 * t;
-            if (n >= d.N) continue;
-            double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-            int64_t o0 = mo + idx2(d.c_n, n);
-            if (c_vec && (n + 1 < d.N)) {
-                double2* p = reinterpret_cast<double2*>(Cmat + o0);
-                if (beta != 0.0) {
-                    double2 old = *p;
-                    v0 += beta * old.x;
-                    v1 += beta * old.y;
-                }
-                *p = make_double2(v0, v1);
+        for (int s = 0; s < C::STAGES; s++) mbar_init(&full_bar[s], TA::LINES + TB::LINES);
+    }
+    __syncthreads();
+
+    auto coords = [&](long long tile, int& batch, int& m0, int& n0) {
+        batch = (int)(tile / per_batch);
+        const int local = (int)(tile - (long long)batch * per_batch);
+        int tm, tn;
+        if (tiles_m <= tiles_n) { tm = local % tiles_m; tn = local / tiles_m; }
+        else { tn = local % tiles_n; tm = local / tiles_n; }
+        m0 = tm * C::BM;
+        n0 = tn * C::BN;
+    };
+    // producer cursor: (tile, k-stage) of the next fill and its running count (stage = count % STAGES)
+    long long ptile = blockIdx.x;
+    int pkt = 0;
+    unsigned pcount = 0;
+    auto fill_next = [&]() {
+        if (ptile >= total) return;
+        int batch, m0, n0;
+        coords(ptile, batch, m0, n0);
+        const double* Ab = A + idx2(d.a_b, batch);
+        const double* Bb = B + idx2(d.b_b, batch);
+        const int stage = (int)(pcount % C::STAGES), k0 = pkt * C::BK;
+        uint32_t b_line_bytes = TB::LINE_BYTES;
+        if constexpr (B_ALONG_N) {
+            const int left = d.N - n0;
+            if (left < C::BN) b_line_bytes = (uint32_t)left * (uint32_t)sizeof(double);
+        }
+        for (int line = tid; line < TA::LINES + TB::LINES; line += C::THREADS) {
+            if (line < TA::LINES) {
+                mbar_expect_tx(&full_bar[stage], TA::LINE_BYTES);
+                bulk_g2s(sA + stage * LA::TILE_ELEMS + line * TA::STRIDE, TA::src(Ab, d.a_m, d.a_k, m0, k0, line), TA::LINE_BYTES, &full_bar[stage]);
             } else {
-                if (beta != 0.0) v0 += beta * Cmat[o0];
-                Cmat[o0] = v0;
-                if (n + 1 < d.N) {
-                    int64_t o1 = mo + idx2(d.c_n, n + 1);
-                    if (beta != 0.0) v1 += beta * Cmat[o1];
-                    Cmat[o1] = v1;
-                }
+                const int l = line - TA::LINES;
+                mbar_expect_tx(&full_bar[stage], b_line_bytes);
+                bulk_g2s(sB + stage * LB::TILE_ELEMS + l * TB::STRIDE, TB::src(Bb, d.b_n, d.b_k, n0, k0, l), b_line_bytes, &full_bar[stage]);
             }
         }
+        ++pcount;
+        if (++pkt == KT) { pkt = 0; ptile += gridDim.x; }
+    };
+#pragma unroll
+    for (int s = 0; s < C::STAGES - 1; s++) fill_next();
+
+    unsigned ccount = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        double acc[C::MT][C::NT][2];
+#pragma unroll
+        for (int i = 0; i < C::MT; i++)
+#pragma unroll
+            for (int j = 0; j < C::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kt = 0; kt < KT; kt++, ccount++) {
+            const int stage = (int)(ccount % C::STAGES);
+            mbar_wait(&full_bar[stage], (ccount / C::STAGES) & 1u);
+            __syncthreads();          // every warp is done with the stage consumed one iteration ago: it is refilled now
+            fill_next();
+            gemm_stage<C, A_ALONG_M, B_ALONG_N, LA::STRIDE, LB::STRIDE>(sA + stage * LA::TILE_ELEMS, sB + stage * LB::TILE_ELEMS, wm0, wn0, g, t, acc);
+        }
+        int batch, m0, n0;
+        coords(tile, batch, m0, n0);
+        gemm_store_tile<C>(d, Cmat + idx2(d.c_b, batch), acc, m0 + wm0, n0 + wn0, g, t, c_vec);
     }
 }
 
@@ -329,6 +435,31 @@ static int launch_gemm(const syn_gemm_desc_t& d, const double* A, const double* 
     return launch_status("gemm_f64_kernel");
 }
 
+template <class C, bool AM, bool BN>
+static int launch_gemm_persistent(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, int c_vec, cudaStream_t st) {
+    using LA = OperandLoader<C, C::BM, AM, 2>;
+    using LB = OperandLoader<C, C::BN, BN, 2>;
+    constexpr size_t smem = (size_t)C::STAGES * (LA::TILE_ELEMS + LB::TILE_ELEMS) * sizeof(double);
+    auto kern = gemm_f64_persistent_kernel<C, AM, BN>;
+    static PerDevice configured;
+    const int dev_ = current_device();
+    if (!configured.get(dev_)) {
+        SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.set(dev_);
+    }
+    const int tiles_m = (d.M + C::BM - 1) / C::BM, tiles_n = (d.N + C::BN - 1) / C::BN;
+    const long long total = (long long)tiles_m * tiles_n * d.batch;
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    kern<<<grid, C::THREADS, smem, st>>>(d, A, B, Cm, tiles_m, tiles_n, c_vec);
+    return launch_status("gemm_f64_persistent_kernel");
+}
+
+static bool gemm_env_persistent() {   // SYN_GEMM_PERSISTENT=0 disables the persistent variant (A/B comparisons)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SYN_GEMM_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 static bool gemm_env_tma() {   // SYN_GEMM_TMA=0 disables the TMA-staged variant (A/B comparisons)
     static int v = -1;
     if (v < 0) { const char* e = getenv("SYN_GEMM_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -371,8 +502,12 @@ template <class C>
 static int dispatch_layout(const syn_gemm_desc_t& d, const double* A, const double* B, double* Cm, bool am, bool bn, int vec,
                            int c_vec, cudaStream_t st) {
     const bool tma = tma_eligible<C>(d, am, bn, vec);
+    // several tiles per SM and a contraction short enough for the per-tile fill / drain to show: the persistent ring
+    const long long tiles = (long long)((d.M + C::BM - 1) / C::BM) * ((d.N + C::BN - 1) / C::BN) * d.batch;
+    const bool persistent = tma && gemm_env_persistent() && C::BM * C::BN >= 128 * 128 && tiles >= 2ll * sm_count() && d.K <= 1024;
 #define SYN_GEMM_CASE(AM, BN)                                                                  \
     if (am == AM && bn == BN) {                                                                \
+        if (persistent) return launch_gemm_persistent<C, AM, BN>(d, A, B, Cm, c_vec, st);      \
         if (tma) return launch_gemm<C, AM, BN, 2, true>(d, A, B, Cm, c_vec, st);               \
         return vec == 2 ? launch_gemm<C, AM, BN, 2>(d, A, B, Cm, c_vec, st)                    \
                         : launch_gemm<C, AM, BN, 1>(d, A, B, Cm, c_vec, st);                   \
