@@ -198,6 +198,28 @@ int syn_scale_rsqrt_f64(double* x, int64_t n, const double* sumsq, void* stream)
  * (layers/TensorDense.py:139-142).  The TT contraction itself is a chain of syn_gemm_f64 calls. */
 int syn_bias_act_f64(double* y, const double* bias, int64_t rows, int cols, int act, void* stream);
 
+/* ---- whole-chain sweeps: ONE call per `@` + `>>` or per `>>` over arrays of core pointers --------------------------------------- */
+/* syn_apply_round_chain_f64: MatrixProductOperator.__matmul__ (matrix_product_operator.py:181-192: per-site contract of X_k (a,i,b) with
+ * W_k (l,i,o,r), product bonds flattened MPS-bond major) followed by the strict `>> dim` QR-truncation sweep of
+ * MatrixProductState.compress (matrix_product_state.py:432-468), fused: the D = chi * chi_W product cores are never formed, the result is
+ * identical (same projections, same column order).  Natural clamp: kept width = min(dim, rows).
+ *   X, W        HOST arrays of n_sites DEVICE pointers to contiguous float64 cores; xshape = (a,i,b) per site, wshape = (l,i,o,r) per site
+ *   out         HOST array of n_sites DEVICE pointers, core k sized by syn_apply_round_chain_shapes (s_k, o_k, s_{k+1}); the last core
+ *               carries the norm and has right bond b * r
+ *   ws          device workspace of syn_apply_round_chain_workspace_f64 bytes, 256-byte aligned, owned by the caller
+ * syn_round_chain_f64: the same `>>` sweep on the cores of one chain (MPS; an MPO passes its two physical legs flattened into one:
+ * matrix_product_operator.py:544-580), shape = (l, d, r) per site.
+ * The calls synchronise the stream once per bond (8 doubles: the verdict of the Newton-Schulz orthonormalisation that the truncation
+ * step tries before the Householder kernels). */
+int syn_apply_round_chain_shapes(int n_sites, const int* xshape, const int* wshape, int dim, int* out_shape);
+size_t syn_apply_round_chain_workspace_f64(int n_sites, const int* xshape, const int* wshape, int dim);
+int syn_apply_round_chain_f64(int n_sites, const double* const* X, const int* xshape, const double* const* W, const int* wshape, int dim,
+                              double* const* out, void* ws, size_t ws_bytes, void* stream);
+int syn_round_chain_shapes(int n_sites, const int* shape, int dim, int* out_shape);
+size_t syn_round_chain_workspace_f64(int n_sites, const int* shape, int dim);
+int syn_round_chain_f64(int n_sites, const double* const* cores, const int* shape, int dim, double* const* out, void* ws, size_t ws_bytes,
+                        void* stream);
+
 /* ---- TensorDense forward on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, TMEM, TMA) ------------------------------- */
 /* Fused TT-matvec of the MPO-compressed dense layer, reference layers/TensorDense.py:74-142 (`call`: per-sample opt_einsum contract of
  * the reshaped input with the three cores at :103-118, `+ bias` at :139, activation at :142), for three cores with every mode and bond

@@ -174,10 +174,20 @@ def qrt_step(L, q, want_S=True):
     return ops.qrt(L, q, want_S=want_S)
 
 
+CHAIN_CALLS = True             # real float64 chains run their `>>` / `@` + `>>` sweeps as ONE library call (csrc/chain.cu)
+
+
+def _real_cuda_chain(*chains):
+    return CHAIN_CALLS and all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == F64 for ch in chains for t in ch)
+
+
 @complex_aware
 def round_qr(sites, dim):
     """Strict `>>` sweep (MPS:432-468, MPO:544-580): QR-truncation left to right, no canonicalisation.
-    Natural clamp: kept width = min(dim, rows)."""
+    Natural clamp: kept width = min(dim, rows).  Real chains: one call of syn_round_chain_f64; the loop below is the same sweep
+    step by step for planar complex operands (and the CPU-emulated host tests)."""
+    if len(sites) > 1 and _real_cuda_chain(sites):
+        return ops.round_chain(sites, int(dim))
     out = list(sites)
     for k in range(len(out) - 1):
         cur, nxt = out[k], out[k + 1]
@@ -488,7 +498,15 @@ def _carry_from(Ut_or_Q, L, kept, b, r, transposed_basis):
 
 def apply_round_qr(X, W, dim):
     """`W @ X` followed by `>> dim` with the reference's semantics (MPO:181-192 + MPS:432-468), fused: identical numbers
-    to site_mpo_mps + round_qr (same projections, same column order), without the D = chi*chi_W product cores."""
+    to site_mpo_mps + round_qr (same projections, same column order), without the D = chi*chi_W product cores.
+    One call of syn_apply_round_chain_f64 (csrc/chain.cu holds the sweep); apply_round_qr_steps is the same sweep step by step."""
+    if _real_cuda_chain(X, W):
+        return ops.apply_round_chain(X, W, int(dim))
+    return apply_round_qr_steps(X, W, dim)
+
+
+def apply_round_qr_steps(X, W, dim):
+    """The fused reference-semantic sweep driven site by site from the host (what csrc/chain.cu does in one call)."""
     n = len(X)
     out = []
     T = torch.ones((1, 1, 1), dtype=F64, device=X[0].device)

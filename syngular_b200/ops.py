@@ -366,6 +366,63 @@ def bias_act_(y, bias, act="relu"):
     return y
 
 
+lib.syn_apply_round_chain_workspace_f64.restype = ctypes.c_size_t
+lib.syn_round_chain_workspace_f64.restype = ctypes.c_size_t
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def _int_array(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])
+
+
+def apply_round_chain(X, W, dim):
+    """`W @ X` + strict `>> dim` (reference semantics) over the whole chain in ONE library call (csrc/chain.cu).  X: list of contiguous
+    CUDA float64 MPS cores (a,i,b); W: MPO cores (l,i,o,r).  Returns the list of rounded cores."""
+    n = len(X)
+    require_cuda_f64(*X)
+    require_cuda_f64(*W)
+    X = [x.contiguous() for x in X]
+    W = [w.contiguous() for w in W]
+    xs = _int_array([d for x in X for d in x.shape])
+    wsh = _int_array([d for w in W for d in w.shape])
+    oshape = (ctypes.c_int * (3 * n))()
+    check(lib.syn_apply_round_chain_shapes(_i32(n), xs, wsh, _i32(int(dim)), oshape), "syn_apply_round_chain_shapes")
+    dev = X[0].device
+    out = [torch.empty((oshape[3 * k], oshape[3 * k + 1], oshape[3 * k + 2]), dtype=torch.float64, device=dev) for k in range(n)]
+    ws = workspace(lib.syn_apply_round_chain_workspace_f64(_i32(n), xs, wsh, _i32(int(dim))), dev, tag="chain")
+    check(lib.syn_apply_round_chain_f64(_i32(n), _ptr_array(X), xs, _ptr_array(W), wsh, _i32(int(dim)), _ptr_array(out), ptr(ws),
+                                        _sz(ws.numel() * 8), stream_ptr()), "syn_apply_round_chain_f64")
+    return out
+
+
+def round_chain(sites, dim):
+    """Strict `>> dim` sweep (reference semantics) over the whole chain in ONE library call; cores (l, phys..., r) contiguous CUDA float64."""
+    n = len(sites)
+    require_cuda_f64(*sites)
+    cores = [c.contiguous() for c in sites]
+    flat = []
+    for c in cores:
+        d = 1
+        for e in c.shape[1:-1]:
+            d *= int(e)
+        flat += [int(c.shape[0]), d, int(c.shape[-1])]
+    sh = _int_array(flat)
+    oshape = (ctypes.c_int * (3 * n))()
+    check(lib.syn_round_chain_shapes(_i32(n), sh, _i32(int(dim)), oshape), "syn_round_chain_shapes")
+    dev = cores[0].device
+    out = [torch.empty((oshape[3 * k],) + tuple(cores[k].shape[1:-1]) + (oshape[3 * k + 2],), dtype=torch.float64, device=dev) for k in range(n)]
+    ws = workspace(lib.syn_round_chain_workspace_f64(_i32(n), sh, _i32(int(dim))), dev, tag="chain")
+    check(lib.syn_round_chain_f64(_i32(n), _ptr_array(cores), sh, _i32(int(dim)), _ptr_array(out), ptr(ws), _sz(ws.numel() * 8), stream_ptr()),
+          "syn_round_chain_f64")
+    return out
+
+
 lib.syn_tt_dense3_packed_floats.restype = ctypes.c_size_t
 
 

@@ -1,6 +1,7 @@
 // Stand-alone consumer of the C ABI (no Python, no PyTorch): what a non-Python binding of the reference would do.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -I include tests/abi/abi_smoke.cu -L syngular_b200 -lsyngular_b200 -o abi_smoke
-// Checks syn_gemm_f64 (plain + two-level site contraction), syn_qrt_f64 and the Jacobi SVD against CPU loops.
+// Checks syn_gemm_f64 (plain + two-level site contraction), syn_qrt_f64 and the Jacobi SVD against CPU loops, and runs a
+// C2-shaped apply + round (N = 64, chi = 256, chi_W = 16) with ONE call of syn_apply_round_chain_f64.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -84,6 +85,53 @@ int main() {
     // ---- 5. errors are reported, not thrown -------------------------------------------------------------------
     int rc = syn_gemm_f64(nullptr, dA, dB, dC, nullptr);
     ok = ok && rc != 0;
+    // ---- 6. a C2-shaped apply + round (N = 64, d = 2, chi = 256, chi_W = 16 -> 256) in ONE call: syn_apply_round_chain_f64 ----------
+    {
+        const int n = 64, dphys = 2, chi = 256, chiw = 16, dim = 256;
+        std::vector<int> bx(n + 1, 1), bw(n + 1, 1);
+        for (int k = 1; k < n; k++) {
+            int e = k < n - k ? k : n - k;
+            bx[k] = e >= 8 ? chi : (1 << e);  if (bx[k] > chi) bx[k] = chi;
+            bw[k] = e >= 2 ? chiw : (1 << (2 * e));  if (bw[k] > chiw) bw[k] = chiw;
+        }
+        std::vector<int> xs(3 * n), ws4(4 * n), os(3 * n);
+        std::vector<const double*> Xp(n), Wp(n);
+        std::vector<double*> Op(n);
+        for (int k = 0; k < n; k++) {
+            xs[3 * k] = bx[k]; xs[3 * k + 1] = dphys; xs[3 * k + 2] = bx[k + 1];
+            ws4[4 * k] = bw[k]; ws4[4 * k + 1] = dphys; ws4[4 * k + 2] = dphys; ws4[4 * k + 3] = bw[k + 1];
+        }
+        SYN(syn_apply_round_chain_shapes(n, xs.data(), ws4.data(), dim, os.data()));
+        for (int k = 0; k < n; k++) {
+            size_t nx = (size_t)bx[k] * dphys * bx[k + 1], nw = (size_t)bw[k] * dphys * dphys * bw[k + 1];
+            std::vector<double> hx(nx), hw(nw);
+            for (auto& v : hx) v = rnd() / sqrt((double)bx[k]);
+            for (auto& v : hw) v = rnd() / sqrt((double)bw[k]);
+            double *dx, *dw, *dout;
+            CK(cudaMalloc(&dx, nx * 8)); CK(cudaMalloc(&dw, nw * 8)); CK(cudaMalloc(&dout, (size_t)os[3 * k] * os[3 * k + 1] * os[3 * k + 2] * 8));
+            CK(cudaMemcpy(dx, hx.data(), nx * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dw, hw.data(), nw * 8, cudaMemcpyHostToDevice));
+            Xp[k] = dx; Wp[k] = dw; Op[k] = dout;
+        }
+        size_t cwb = syn_apply_round_chain_workspace_f64(n, xs.data(), ws4.data(), dim);
+        void* cws; CK(cudaMalloc(&cws, cwb));
+        long long l0 = syn_launch_count();
+        cudaEvent_t t0, t1; CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+        SYN(syn_apply_round_chain_f64(n, Xp.data(), xs.data(), Wp.data(), ws4.data(), dim, Op.data(), cws, cwb, nullptr));     // warm-up
+        CK(cudaEventRecord(t0));
+        SYN(syn_apply_round_chain_f64(n, Xp.data(), xs.data(), Wp.data(), ws4.data(), dim, Op.data(), cws, cwb, nullptr));
+        CK(cudaEventRecord(t1)); CK(cudaDeviceSynchronize());
+        float ms = 0; CK(cudaEventElapsedTime(&ms, t0, t1));
+        long long launches = (syn_launch_count() - l0) / 2;
+        // plateau core 30 must be left-orthonormal: Q (512 x 256)
+        const int k30 = 30, rows = os[3 * k30] * os[3 * k30 + 1], cols = os[3 * k30 + 2];
+        std::vector<double> Q((size_t)rows * cols);
+        CK(cudaMemcpy(Q.data(), Op[k30], Q.size() * 8, cudaMemcpyDeviceToHost));
+        double e6 = 0;
+        for (int x = 0; x < cols; x += 17) for (int y = 0; y < cols; y += 13) { double s2 = 0; for (int r2 = 0; r2 < rows; r2++) s2 += Q[(size_t)r2 * cols + x] * Q[(size_t)r2 * cols + y]; e6 = fmax(e6, fabs(s2 - (x == y))); }
+        printf("chain apply+round: core 30 is (%d, %d, %d), |QtQ-I| (sampled) %.2e, %lld kernel launches, %.2f ms per sweep in one call\n",
+               os[3 * k30], os[3 * k30 + 1], os[3 * k30 + 2], e6, launches, ms);
+        ok = ok && os[3 * k30] == 256 && os[3 * k30 + 2] == 256 && e6 < 1e-10 && launches > 0;
+    }
     printf("%s\n", ok ? "ABI SMOKE OK" : "ABI SMOKE FAILED");
     return ok ? 0 : 1;
 }
