@@ -253,6 +253,38 @@ def dmrg_left_blocks(state, operator):
     return blocks
 
 
+def dmpo_project(state, operator, index):
+    """DifferentialMatrixProductOperator.project (tensor/differential_matrix_product_operator.py:79-173): the merged ("crumbled") pair
+    of operator cores index, index+1 (:13-27), and the wings -- everything left of `index` / right of `index + 1` of W @ X contracted
+    into (1, prod(out), a, w) / (a, w, prod(out), 1) tensors (:104-149; MPS bond before MPO bond, output legs flattened in site order).
+    The reference's wing einsums have no operand when a wing is empty, so 1 <= index <= n - 3."""
+    n = len(state)
+    if not (0 <= index < n - 1):
+        raise Exception("trying to project on non-existant site (site indices should be between 0 and the number of sites - 1)")
+    if index < 1 or index > n - 3:
+        raise Exception("project needs at least one site on each side of the merged pair (1 <= index <= n - 3)")
+    wl, wr = operator[index], operator[index + 1]
+    center = np.tensordot(wl, wr, axes=(3, 0))                                  # (l, i, o, i', o', r')
+    left = None                                                                 # (prod(out), a, w)
+    for k in range(index):
+        C = np.einsum("aib,wiov->awobv", state[k], operator[k])               # MPS bond major, MPO bond minor on both sides
+        a, w, o, b, v = C.shape
+        if left is None:
+            left = C.reshape(a * w * o, b, v)                                   # a = w = 1 at the chain's left end (np.squeeze, :122)
+        else:
+            left = np.tensordot(left, C, axes=([1, 2], [0, 1])).reshape(-1, b, v)
+    right = None                                                                # (a, w, prod(out))
+    for k in range(n - 1, index + 1, -1):
+        C = np.einsum("aib,wiov->awobv", state[k], operator[k])
+        a, w, o, b, v = C.shape
+        if right is None:
+            right = C.reshape(a, w, o * b * v)                                  # b = v = 1 at the chain's right end (:159)
+        else:
+            right = np.tensordot(C, right, axes=([3, 4], [0, 1])).reshape(a, w, -1)
+    return {"center_site": center, "left_wing": left[None], "left_center": state[index], "right_center": state[index + 1],
+            "right_wing": right[..., None]}
+
+
 def decompose_left(T, shapes):
     """TT decomposition by the qrt step, left to right (matrix_product_state.py:298-319,
     matrix_product_operator.py:430-450).  `T` is the (interleaved, for an MPO) dense tensor and `shapes` the

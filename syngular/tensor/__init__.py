@@ -1,6 +1,7 @@
 """`syngular.tensor` -- same exports as the reference's tensor/__init__.py:1-5 for the hot-path types."""
 from syngular.tensor.matrix_product_state import MatrixProductState
 from syngular.tensor.matrix_product_operator import MatrixProductOperator
+from syngular.tensor.differential_matrix_product_operator import DifferentialMatrixProductOperator
 
 
 def set_rounding(mode, chi_cutoff=0.0):
@@ -15,4 +16,4 @@ def set_rounding(mode, chi_cutoff=0.0):
     MatrixProductOperator.SVD_CUTOFF = float(chi_cutoff)
 
 
-__all__ = ["MatrixProductState", "MatrixProductOperator", "set_rounding"]
+__all__ = ["MatrixProductState", "MatrixProductOperator", "DifferentialMatrixProductOperator", "set_rounding"]

@@ -371,6 +371,35 @@ def mpo_apply_range(sites, op_sites, indices):
     return out
 
 
+@complex_aware
+def crumble(left, right):
+    """Merged operator core (l, i, o, i', o', r') of two neighbouring sites (differential_matrix_product_operator.py:13-27)."""
+    l, i, o, r = left.shape
+    _, i2, o2, r2 = right.shape
+    return _O(left).matmul(left.reshape(l * i * o, r), right.reshape(r, i2 * o2 * r2)).reshape(l, i, o, i2, o2, r2)
+
+
+@complex_aware
+def project_wings(state, operator, index):
+    """Wings of W @ X around the operator cores index, index + 1 (tensor/differential_matrix_product_operator.py:104-163):
+    left (1, prod(out_0..out_{index-1}), a, w) and right (a, w, prod(out_{index+2}..), 1), MPS bond before MPO bond.  Each site is the
+    `@` contraction (one strided GEMM, product bonds flattened MPS-bond major) and the chain is multiplied up with one GEMM per site."""
+    n = len(state)
+    left = None                                            # (prod(out), D) with D = (a, w) flattened
+    for k in range(index):
+        C = site_mpo_mps(state[k], operator[k])            # ((a,w), o, (b,v))
+        D0, o, D1 = C.shape
+        left = C.reshape(D0 * o, D1) if left is None else _O(left).matmul(left, C.reshape(D0, o * D1)).reshape(-1, D1)
+    right = None                                           # (D, prod(out))
+    for k in range(n - 1, index + 1, -1):
+        C = site_mpo_mps(state[k], operator[k])
+        D0, o, D1 = C.shape
+        right = C.reshape(D0, o * D1) if right is None else _O(right).matmul(C.reshape(D0 * o, D1), right).reshape(D0, -1)
+    a, w = state[index].shape[0], operator[index].shape[0]
+    a2, w2 = state[index + 1].shape[2], operator[index + 1].shape[3]
+    return left.reshape(1, -1, a, w), right.reshape(a2, w2, -1, 1)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # three-layer transfer contractions: the DMRG environment blocks (variational/dmrg.py:65-112, SURVEY 8f-4)
 # ---------------------------------------------------------------------------------------------------------
