@@ -870,7 +870,25 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None):
                 trunc.sigma.append(LazySpectrum(A, eye)); trunc.keep.append(nA); trunc.discarded.append(0.0)
                 out.append(eye.reshape(s, o, nA))
                 T = _carry_from(eye, M2, nA, b, r, transposed_basis=False)    # = M2 with its columns re-ordered to (r, b)
-            elif PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff == 0.0 and ne < nA and A.is_contiguous():
+            elif PURIFY_MIN_N and nA >= PURIFY_MIN_N and cutoff > 0.0 and ne < nA and A.is_contiguous():
+                # relative cutoff on the fast path: the projection solver finds the chi_max-dimensional dominant space, the kept
+                # singular values are the spectrum of the SMALL matrix U^T A U (Jacobi on ne x ne instead of nA x nA), and the cutoff
+                # picks a prefix of them; the verdict is read at once (the kept rank is data dependent)
+                U, info = ops.dominant_subspace(A, ne, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
+                ok, disc = _projection_verdict(info.cpu().numpy(), ne, ne >= min(D, right_dim[k + 1]))
+                PURIFY_STATS["taken" if ok else "fallback"] += 1
+                if ok:
+                    Tm = ops.copy_strided(ops.matmul(U.t(), ops.matmul(A, U)))
+                    Vt, sigma, hinfo, winfo = ops.jacobi_solve(Tm, ne, cutoff, rank_tol=rank_tol, sqrt_mode=1, null_rel=0.0)
+                    keep = int(hinfo[0])
+                    if keep < ne:
+                        U = ops.matmul(U, Vt[:keep].t())           # the kept eigenvectors of U^T A U, back in the full space
+                    trunc.sigma.append(sigma); trunc.keep.append(keep); trunc.discarded.append(disc + float(winfo[0].item()))
+                    out.append(U.reshape(s, o, keep))
+                    T = _carry_from(U, M2, keep, b, r, transposed_basis=False)
+                else:
+                    T = jacobi_site(A, M2, s, o, b, r)
+            elif PURIFY_MIN_N and nA >= PURIFY_MIN_N and ne < nA and A.is_contiguous():
                 U, info = ops.dominant_subspace(A, ne, PURIFY_SP2_ITERS, PURIFY_NS_ITERS, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
                 queued = (k, _AsyncVerdict(info) if info.is_cuda else info, ne, ne >= min(D, right_dim[k + 1]), T, len(out))
                 if capture is not None and k in capture:

@@ -148,3 +148,28 @@ def test_polar_truncation_step_falls_back_on_dependent_columns():
     Qn, Sn = Q.cpu().numpy(), S.cpu().numpy()
     assert np.max(np.abs(Qn.T @ Qn - np.eye(128))) < 1e-12
     assert np.max(np.abs((Qn @ Sn)[:, :128] - L[:, :128])) < 1e-11 * np.max(np.abs(L))
+
+
+@pytest.mark.parametrize("n,chi,chiw,cutoff", [(16, 128, 8, 0.05), (18, 128, 16, 0.1)])
+def test_relative_cutoff_stays_on_the_projection_solver(n, chi, chiw, cutoff):
+    """north_star "fuse the singular-value cutoff": with cutoff > 0 the bonds still take the spectral-projection solver; the kept rank comes
+    from the spectrum of U^T A U.  Against the textbook oracle with the same cutoff: ranks, dense tensor, kept spectra, discarded weights."""
+    from syngular.tensor import _sweeps as sw
+    from oracle import ref_numpy as R, svd_numpy as S
+    import bench
+    X, W = bench.make_chain(11, n=n, chi=chi, chiw=chiw)
+    ref, spectra, discarded = S.apply_round_svd(X, W, chi, cutoff)
+    Xd, Wd = [sw.as_core(c) for c in X], [sw.as_core(c) for c in W]
+    sw.PURIFY_STATS.update(taken=0, fallback=0)
+    out, trunc = sw.apply_round_dm(Xd, Wd, chi, cutoff=cutoff)
+    assert sw.PURIFY_STATS["taken"] >= 2
+    assert [tuple(c.shape) for c in out] == [tuple(c.shape) for c in ref]
+    dense_ref = R.to_dense(ref)
+    assert np.max(np.abs(R.to_dense([c.cpu().numpy() for c in out]) - dense_ref)) < 1e-10 * np.max(np.abs(dense_ref))
+    sig, keep, disc = trunc.host()
+    assert min(keep[6:-6]) < chi                            # the cutoff really cuts below chi_max on the plateau (ragged bonds)
+    for k in range(n - 1):
+        kk = ref[k].shape[-1]
+        assert keep[k] == kk
+        assert np.max(np.abs(np.sort(sig[k])[::-1][:kk] - spectra[k][:kk])) < 1e-10 * spectra[k][0]
+        assert abs(disc[k] - discarded[k]) < 1e-10 * float(np.sum(spectra[k] ** 2))
