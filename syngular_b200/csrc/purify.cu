@@ -273,7 +273,7 @@ int dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_
 // Convergence is decided INSIDE the kernel from the accumulated scalars (every CTA reads the same values after the barrier), so the
 // iteration counts adapt to the spectrum with no host round trip: SP2 stops two steps after tr(X - X^2) < 1e-11 ne, Newton-Schulz when
 // max |U^T U - I| < 1e-13.  While the smallest singular value of U is still far from 1 the steeper map 2x - x^3 replaces 1.5x - 0.5x^3.
-constexpr int PF_THREADS = 256, PF_BK = 64, PF_STAGES = 3, PF_LD = PF_BK + 4, PF_T = 32, PF_STEEP = 8;
+constexpr int PF_THREADS = 256, PF_BK = 128, PF_STAGES = 3, PF_LD = PF_BK + 4, PF_T = 32, PF_STEEP = 8;
 constexpr size_t PF_SMEM = (size_t)PF_STAGES * 2 * PF_T * PF_LD * sizeof(double);
 
 struct PurifyArgs {
@@ -304,9 +304,10 @@ __device__ __forceinline__ void pf_grid_barrier(unsigned* ctr, unsigned& target)
     __syncthreads();
 }
 
-// acc[i][j][0..1] of this warp's 16 x 16 sub-tile of  C(32 x 32) = R1[i0.., :K] R2[j0.., :K]^T ; warps 4..7 take the odd 32-wide
-// k-halves of every stage and are folded into warps 0..3 through shared memory at the end.  Returns true for the warps that own
-// the result.  K % 32 == 0 (a last half stage is zero-filled), rows 16-byte aligned.
+// acc[i][j][0..1] of this warp's 16 x 16 sub-tile of  C(32 x 32) = R1[i0.., :K] R2[j0.., :K]^T ; warps 4..7 take the upper half of
+// every PF_BK-wide k-stage and are folded into warps 0..3 through shared memory at the end.  Returns true for the warps that own
+// the result.  K even (the tail of the last stage is zero-filled), rows 16-byte aligned.  128-wide stages: four barriers per 512-long
+// contraction instead of eight, and three quarters of it in flight in the ring.
 __device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_t ld1, const double* __restrict__ R2, int64_t ld2, int i0, int j0, int K,
                                            double* smem, double (&acc)[2][2][2]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -318,10 +319,11 @@ __device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_
         for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     auto fill = [&](int stage, int k0) {
         double* sa = smem + (size_t)stage * 2 * TILE;
+        constexpr int CPR = PF_BK / 2;                       // 16-byte chunks per row of a stage
 #pragma unroll
-        for (int p = 0; p < 8; p++) {
-            const int c = tid + PF_THREADS * p;              // 2048 16-byte chunks: operand | row | chunk
-            const int op = c >> 10, row = (c >> 5) & 31, ch = c & 31;
+        for (int p = 0; p < (2 * PF_T * CPR) / PF_THREADS; p++) {
+            const int c = tid + PF_THREADS * p;              // 16-byte chunks: operand | row | chunk
+            const int op = c / (PF_T * CPR), row = (c / CPR) % PF_T, ch = c % CPR;
             const bool ok = k0 + ch * 2 < K;                 // K may end inside a stage (K % 32 == 0): the tail is zero-filled
             const double* base = op ? (R2 + (int64_t)(j0 + row) * ld2) : (R1 + (int64_t)(i0 + row) * ld1);
             cp_async<16>(sa + op * TILE + row * PF_LD + ch * 2, base + (ok ? k0 + ch * 2 : 0), ok);
@@ -342,7 +344,8 @@ __device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_
         cp_async_commit();
         const double* a_s = smem + (size_t)(kt % PF_STAGES) * 2 * TILE;
         const double* b_s = a_s + TILE;
-        const int kb = wg * 32;
+        constexpr int KH = PF_BK / 2;                        // k-extent of a warp group within a stage
+        const int kb = wg * KH;
         double af[2][2], bf[2][2];
         auto frags = [&](int buf, int kk) {
 #pragma unroll
@@ -352,9 +355,9 @@ __device__ __forceinline__ bool pf_tile_nt(const double* __restrict__ R1, int64_
         };
         frags(0, 0);
 #pragma unroll
-        for (int kk = 0; kk < 32; kk += 4) {
+        for (int kk = 0; kk < KH; kk += 4) {
             const int cur = (kk >> 2) & 1;
-            if (kk + 4 < 32) frags(cur ^ 1, kk + 4);
+            if (kk + 4 < KH) frags(cur ^ 1, kk + 4);
 #pragma unroll
             for (int i = 0; i < 2; i++)
 #pragma unroll
