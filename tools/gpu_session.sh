@@ -17,6 +17,8 @@ for s in $steps; do
     benchc4) python bench.py --workload c4 > gpurun_out/${tag}_bench_c4.json 2> gpurun_out/${tag}_bench_c4.err; tail -c 400 gpurun_out/${tag}_bench_c4.json ;;
     benchc5) python bench.py --workload c5 > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err; tail -c 400 gpurun_out/${tag}_bench_c5.json ;;
     sanitize) tools/sanitize.sh ${tag} ;;
+    gemmncu) ncu --set full --clock-control none --import-source on -k regex:gemm_f64_persistent -s 70 -c 1 -f -o gpurun_out/${tag}_gemm_p1 python tools/profile_sweep.py svd > gpurun_out/${tag}_gemmncu.log 2>&1; tail -2 gpurun_out/${tag}_gemmncu.log ;;
+    purifyncu) ncu --set full --clock-control none --import-source on -k regex:purify_fused -s 30 -c 1 -f -o gpurun_out/${tag}_purify python tools/profile_sweep.py svd > gpurun_out/${tag}_purifyncu.log 2>&1; tail -2 gpurun_out/${tag}_purifyncu.log ;;
     *) echo "unknown step $s" ;;
   esac
 done
