@@ -47,6 +47,11 @@ typedef struct {
     syn_index_t b_k, b_n, b_b;
     syn_index_t c_m, c_n, c_b;
     double alpha, beta;
+    /* optional block-lower output mask (0, 0 = none): with mask_rows = R and mask_cols = C only the elements (m, n) with
+     * n < (m / R + 1) * C are computed, the rest of C is left untouched -- the symmetric right environment E = C E' C^T of the
+     * density-matrix sweep is built from its block-lower part (R = a-block * l rows, C = a-block columns) and mirrored.  Both must be
+     * multiples of 64.  Zero-initialise the struct (= {}) when filling it field by field. */
+    int32_t mask_rows, mask_cols;
 } syn_gemm_desc_t;
 
 int syn_gemm_f64(const syn_gemm_desc_t* desc, const double* A, const double* B, double* C, void* stream);

@@ -661,13 +661,11 @@ def right_environments(X, W):
         # E[(a,l),(l',a')] = sum_{(i',b')} Z[(a,l), l', (i',b')] X[a',(i',b')]        batch over l'
         Ek = empty(a * l, l * a)
         ab = ENV_SYMMETRIC_BLOCK
-        if ab and a % ab == 0 and a >= 2 * ab and l * l <= 65535:      # env_mirror launches gridDim.z = l * l
-            # E is symmetric under (a,l) <-> (a',l'): form only the a-blocks on and below the diagonal (one GEMM per block row,
-            # N grows with the block index), then mirror the rest -- 62.5 % of the flops at four blocks
-            for p in range(a // ab):
-                rows = slice(p * ab * l, (p + 1) * ab * l)
-                ops.gemm(Z[rows], Xk, Ek[rows], M=ab * l, N=(p + 1) * ab, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
-                         batch=l, a_b=i * b, b_b=0, c_b=a)
+        if ab and a % ab == 0 and a >= 2 * ab and l * l <= 65535 and (ab * l) % 128 == 0 and ab % 64 == 0:      # env_mirror launches gridDim.z = l * l
+            # E is symmetric under (a,l) <-> (a',l'): form only the a-blocks on and below the diagonal -- ONE launch with a block-lower
+            # output mask (rows in steps of ab * l, columns in steps of ab: 62.5 % of the flops at four blocks) -- then mirror the rest
+            ops.gemm(Z, Xk, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
+                     batch=l, a_b=i * b, b_b=0, c_b=a, mask=(ab * l, ab))
             ops.env_mirror(Ek, a, l, ab)
         else:
             ops.gemm(Z, Xk, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
@@ -676,7 +674,7 @@ def right_environments(X, W):
     return E
 
 
-ENV_SYMMETRIC_BLOCK = 128      # a-block of the block-lower environment build (0 = full GEMM); 128: every launch is whole 128 x 128 tiles
+ENV_SYMMETRIC_BLOCK = 64       # a-block of the block-lower environment build (0 = full GEMM): one masked launch of 128 x 64 tiles
 
 
 def _w_sandwich_gemms(P1, Wk, a, i, b, l, o, r, D):

@@ -28,6 +28,7 @@ class GemmDesc(ctypes.Structure):
         ("b_k", Index), ("b_n", Index), ("b_b", Index),
         ("c_m", Index), ("c_n", Index), ("c_b", Index),
         ("alpha", ctypes.c_double), ("beta", ctypes.c_double),
+        ("mask_rows", ctypes.c_int32), ("mask_cols", ctypes.c_int32),
     ]
 
 

@@ -254,7 +254,7 @@ static int chol_upper_one(double* G, int64_t ld, int n, double* B, int64_t ldb, 
         chol_panel_kernel<<<ctas, CH_THREADS, smem, st>>>(G, ld, n, k0, nb, B, ldb, shift);
         if (int rc = launch_status("chol_panel_kernel")) return rc;
         if (below > 0) {                 // A22 -= L21 L21^T  (full square: the upper half is not read again, but stays symmetric)
-            syn_gemm_desc_t d;
+            syn_gemm_desc_t d = {};
             d.M = below; d.N = below; d.K = nb; d.batch = 1;
             d.a_m = CIX(ld); d.a_k = CIX(1); d.a_b = CIX(0);
             d.b_k = CIX(1); d.b_n = CIX(ld); d.b_b = CIX(0);

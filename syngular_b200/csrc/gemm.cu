@@ -207,6 +207,8 @@ gemm_f64_kernel(const syn_gemm_desc_t d, const double* __restrict__ A, const dou
     const int n0 = tn * C::BN;
     const int batch = blockIdx.y + gridDim.y * blockIdx.z;
     if (batch >= d.batch) return;
+    // block-lower mask: a tile that lies entirely above the kept staircase has nothing to do (the whole CTA leaves before any barrier)
+    if (d.mask_rows > 0 && n0 >= (m0 / d.mask_rows + 1) * d.mask_cols) return;
 
     A += idx2(d.a_b, batch);
     B += idx2(d.b_b, batch);
@@ -401,6 +403,10 @@ using CfgW = GemmCfg<128, 128, 32, 32, 32, 3>;   // 512 threads (4 warps per SM 
 // for 112-wide lines), A k-contiguous, B n-contiguous.
 using CfgT = GemmCfg<128, 112, 32, 16, 56, 3>;
 
+// 128 x 64 tiles, 16 warps of 32 x 16: outputs with too few 128 x 128 tiles for the 148 SMs (the carry product U^T M: 256 x 4096 = 64 tiles)
+// and the block-lower environment product, whose 64-column staircase wastes a quarter of a 128 x 128 tiling.
+using CfgH = GemmCfg<128, 64, 32, 32, 16, 3>;
+
 using CfgN = GemmCfg<128, 32, 32, 32, 32, 2>;    // skinny outputs (N <= 32): 128 threads, 92 KB smem
 using CfgM = GemmCfg<32, 128, 32, 32, 32, 2>;    // flat outputs (M <= 32)
 
@@ -504,7 +510,7 @@ static int dispatch_layout(const syn_gemm_desc_t& d, const double* A, const doub
     const bool tma = tma_eligible<C>(d, am, bn, vec);
     // several tiles per SM and a contraction short enough for the per-tile fill / drain to show: the persistent ring
     const long long tiles = (long long)((d.M + C::BM - 1) / C::BM) * ((d.N + C::BN - 1) / C::BN) * d.batch;
-    const bool persistent = tma && gemm_env_persistent() && C::BM * C::BN >= 128 * 128 && tiles >= 2ll * sm_count() && d.K <= 1024;
+    const bool persistent = tma && d.mask_rows == 0 && gemm_env_persistent() && C::BM * C::BN >= 128 * 128 && tiles >= 2ll * sm_count() && d.K <= 1024;
 #define SYN_GEMM_CASE(AM, BN)                                                                  \
     if (am == AM && bn == BN) {                                                                \
         if (persistent) return launch_gemm_persistent<C, AM, BN>(d, A, B, Cm, c_vec, st);      \
@@ -541,6 +547,8 @@ int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double*
     const syn_index_t* all[] = {&d.a_m, &d.a_k, &d.a_b, &d.b_k, &d.b_n, &d.b_b, &d.c_m, &d.c_n, &d.c_b};
     for (auto* ix : all) SYN_REQUIRE(ix->div >= 1, "syn_gemm_f64: index div must be >= 1");
     SYN_REQUIRE(A && B && C, "syn_gemm_f64: null operand");
+    SYN_REQUIRE((d.mask_rows == 0 && d.mask_cols == 0) || (d.mask_rows > 0 && d.mask_cols > 0 && d.mask_rows % 64 == 0 && d.mask_cols % 64 == 0),
+                "syn_gemm_f64: mask_rows / mask_cols must both be 0 or both positive multiples of 64");
 
     // orientation: which logical dimension is contiguous in HBM (neither -> scalar loads, k-major tile)
     bool a_along_m = (d.a_m.inner == 1) && (d.a_k.inner != 1 || d.K == 1);
@@ -565,6 +573,16 @@ int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double*
     if (forced == 3) return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     if (d.N <= 32 && d.M >= 128) return dispatch_layout<CfgN>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     if (d.M <= 32 && d.N >= 128) return dispatch_layout<CfgM>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    if (d.mask_rows > 0) {
+        // masked launch: tiles must not straddle the staircase -- 128 x 64 tiles when the steps are 64 columns wide, 64 x 64 for odd row blocks
+        if (d.mask_rows % 128 == 0 && d.M >= 128) return dispatch_layout<CfgH>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+        return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    }
+    if (!forced && !use_large && d.M >= 128 && d.N >= 128) {
+        // too few 128 x 128 tiles: halve the tile width when that fills the machine
+        const long long half_tiles = (long long)((d.M + 127) / 128) * ((d.N + 63) / 64) * d.batch;
+        if (half_tiles * 5 >= (long long)sm_count() * 4) return dispatch_layout<CfgH>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
+    }
     if (use_large && !forced && prefer_cfg_t(d, a_along_m, b_along_n, vec)) return launch_gemm<CfgT, false, true, 2, true>(d, A, B, C, c_vec, st);
     if (use_large) return dispatch_layout<CfgW>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);
     return dispatch_layout<CfgS>(d, A, B, C, a_along_m, b_along_n, vec, c_vec, st);

@@ -35,7 +35,7 @@ static inline syn_index_t PIX(int64_t stride) {
 
 static syn_gemm_desc_t pdesc(int M, int N, int K, int batch, int64_t a_m, int64_t a_k, int64_t a_b, int64_t b_k, int64_t b_n, int64_t b_b,
                              int64_t c_m, int64_t c_n, int64_t c_b, double alpha = 1.0, double beta = 0.0) {
-    syn_gemm_desc_t d;
+    syn_gemm_desc_t d = {};
     d.M = M; d.N = N; d.K = K; d.batch = batch;
     d.a_m = PIX(a_m); d.a_k = PIX(a_k); d.a_b = PIX(a_b);
     d.b_k = PIX(b_k); d.b_n = PIX(b_n); d.b_b = PIX(b_b);

@@ -47,7 +47,7 @@ static inline syn_index_t IX(int64_t stride) {
 
 static syn_gemm_desc_t mk_desc(int M, int N, int K, int batch, int64_t a_m, int64_t a_k, int64_t a_b, int64_t b_k, int64_t b_n,
                                int64_t b_b, int64_t c_m, int64_t c_n, int64_t c_b, double alpha, double beta) {
-    syn_gemm_desc_t d;
+    syn_gemm_desc_t d = {};
     d.M = M; d.N = N; d.K = K; d.batch = batch;
     d.a_m = IX(a_m); d.a_k = IX(a_k); d.a_b = IX(a_b);
     d.b_k = IX(b_k); d.b_n = IX(b_n); d.b_b = IX(b_b);

@@ -13,12 +13,14 @@ from ._lib import GemmDesc, check, ix, lib, ptr, require_cuda_f64, stream_ptr
 GEMM_PROFILE = None
 
 
-def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, c_b=0, alpha=1.0, beta=0.0):
+def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, c_b=0, alpha=1.0, beta=0.0, mask=None):
     """C[m,n] = alpha * sum_k A[m,k] B[k,n] + beta * C[m,n] with two-level strided indices (see syngular_b200.h).
-    A, B, C are CUDA float64 tensors used as base pointers (their own strides are ignored)."""
+    A, B, C are CUDA float64 tensors used as base pointers (their own strides are ignored).
+    mask = (rows, cols): block-lower output, only n < (m // rows + 1) * cols is computed (the rest of C is left untouched)."""
     require_cuda_f64(A, B, C)
+    mr, mc = (int(mask[0]), int(mask[1])) if mask else (0, 0)
     d = GemmDesc(int(M), int(N), int(K), int(batch), ix(a_m), ix(a_k), ix(a_b), ix(b_k), ix(b_n), ix(b_b),
-                 ix(c_m), ix(c_n), ix(c_b), float(alpha), float(beta))
+                 ix(c_m), ix(c_n), ix(c_b), float(alpha), float(beta), mr, mc)
     prof = GEMM_PROFILE
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -28,7 +30,10 @@ def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, 
     if prof is not None:
         e1.record()
         M_, N_, K_, b_ = int(M), int(N), int(K), int(batch)
-        prof.append((e0, e1, 2.0 * M_ * N_ * K_ * b_, 8.0 * b_ * (M_ * K_ + K_ * N_ + M_ * N_), (M_, N_, K_, b_)))
+        frac = 1.0
+        if mr:                     # block-lower mask: the computed fraction of the M x N outputs
+            frac = sum(min(N_, (m0 // mr + 1) * mc) for m0 in range(0, M_, mr)) * float(min(mr, M_)) / (float(M_) * N_)
+        prof.append((e0, e1, 2.0 * M_ * N_ * K_ * b_ * frac, 8.0 * b_ * (M_ * K_ + K_ * N_ + M_ * N_ * frac), (M_, N_, K_, b_) + ((mr, mc) if mr else ())))
     return C
 
 

@@ -29,7 +29,7 @@ def _ix(spec, extent):
     return x * int(spec)
 
 
-def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, c_b=0, alpha=1.0, beta=0.0):
+def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, c_b=0, alpha=1.0, beta=0.0, mask=None):
     fa, oa = _flat(A)
     fb, ob = _flat(B)
     fc, oc = _flat(C)
@@ -41,7 +41,12 @@ def gemm(A, B, C, M, N, K, a_m, a_k, b_k, b_n, c_m, c_n, batch=1, a_b=0, b_b=0, 
         b = fb[ob + bb[z] + bk[:, None] + bn[None, :]]
         idx = oc + cb[z] + cm[:, None] + cn[None, :]
         prod = alpha * (a @ b)
-        fc[idx] = prod + (beta * fc[idx] if beta != 0.0 else 0.0)
+        new = prod + (beta * fc[idx] if beta != 0.0 else 0.0)
+        if mask:                                            # block-lower output mask: the rest of C is left untouched
+            rows, cols = np.arange(int(M))[:, None], np.arange(int(N))[None, :]
+            keep = torch.from_numpy(cols < (rows // int(mask[0]) + 1) * int(mask[1]))
+            new = torch.where(keep, new, fc[idx])
+        fc[idx] = new
     return C
 
 

@@ -85,3 +85,31 @@ def test_gemm_128x112_wave_configuration(M, N, K):
         ops.gemm(a, b, out, M=M, N=N, K=K, a_m=K, a_k=1, b_k=N, b_n=1, c_m=N, c_n=(1, 16, 256))
         ref = (a @ b).reshape(M, 16, 256).transpose(1, 2).reshape(M, N)
         _check(out, ref, a, b)
+
+
+@pytest.mark.parametrize("M,N,K,batch,mr,mc", [(1024, 256, 96, 3, 256, 64), (4096, 256, 64, 2, 1024, 64), (512, 192, 40, 1, 128, 64), (320, 256, 33, 2, 64, 64)])
+def test_gemm_block_lower_mask(M, N, K, batch, mr, mc):
+    """Block-lower output mask (syn_gemm_desc_t.mask_rows / mask_cols): only n < (m // rows + 1) * cols is computed, the rest of C keeps its
+    contents; 128 x 64 tiles when the row blocks allow, 64 x 64 otherwise."""
+    from syngular_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn((batch, M, K), dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn((batch, K, N), dtype=torch.float64, device="cuda", generator=g)
+    out = torch.full((batch, M, N), 7.0, dtype=torch.float64, device="cuda")
+    ops.gemm(a, b, out, M, N, K, K, 1, N, 1, N, 1, batch=batch, a_b=M * K, b_b=K * N, c_b=M * N, mask=(mr, mc))
+    rows = torch.arange(M, device="cuda")[:, None]
+    cols = torch.arange(N, device="cuda")[None, :]
+    keep = cols < (rows // mr + 1) * mc
+    ref = torch.where(keep, a @ b, torch.full_like(out, 7.0))
+    _check(out, ref, a, b)
+
+
+def test_gemm_half_width_tiles_for_few_tiles():
+    """256 x 4096 x 512 (the carry product U^T M of the sweeps): 64 tiles of 128 x 128 -> 128 tiles of 128 x 64."""
+    from syngular_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn((512, 256), dtype=torch.float64, device="cuda", generator=g)
+    l = torch.randn((512, 4096), dtype=torch.float64, device="cuda", generator=g)
+    _check(ops.matmul(q.t(), l), q.t() @ l, q, l)
+    a = torch.randn((256, 512), dtype=torch.float64, device="cuda", generator=g)
+    _check(ops.matmul(a, l), a @ l, a, l)

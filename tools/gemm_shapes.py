@@ -10,7 +10,7 @@ from syngular_b200 import ops
 mode = sys.argv[1] if len(sys.argv) > 1 else "svd"
 X, W = bench.make_chain(2)
 Xd = [sw.as_core(x) for x in X]; Wd = [sw.as_core(w) for w in W]
-fn = (lambda: sw.apply_round_dm(Xd, Wd, 256)) if mode == "svd" else (lambda: sw.apply_round_qr(Xd, Wd, 256))
+fn = (lambda: sw.apply_round_dm(Xd, Wd, 256)) if mode == "svd" else (lambda: sw.apply_round_qr_steps(Xd, Wd, 256))
 fn(); torch.cuda.synchronize()
 ops.GEMM_PROFILE = []
 fn(); torch.cuda.synchronize()
