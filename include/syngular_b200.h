@@ -92,13 +92,6 @@ int syn_jacobi_rows_f64(double* G, int64_t ld, int64_t bs, int n, int batch, voi
  * blocks must have reached (stores earlier in the sweep); cnt[block] = stores of the block per sweep.  Slot A only changes when
  * the recursion descends (log2 P times per sweep), so only slot B is handed from CTA to CTA each round. */
 int syn_jacobi_ring_schedule(int P, uint32_t* table, uint32_t* cnt);
-/* FP32 variant of the same kernel and the helpers of the FP32-preconditioned symmetric eigen-solver
- * (syngular/tensor/_sweeps.py: eigh_gram): FP32 Jacobi gives an approximate eigenbasis, it is re-orthonormalised in FP64
- * (Newton-Schulz, GEMMs), the matrix is transformed with it, and the FP64 Jacobi finishes in ~3 sweeps instead of ~13. */
-int syn_jacobi_rows_f32(float* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes,
-                        int max_sweeps, double tol, double null_rel, void* stream);
-int syn_cast_f64_f32(const double* src, float* dst, int64_t n, void* stream);
-int syn_rows_to_basis_f32_f64(const float* G, double* U, int n, void* stream);      /* U[i] = G[i] / |G[i]| in FP64 */
 int syn_identity_deviation_f64(const double* X, int n, double* out, void* stream);  /* out[0] = max |X - I| */
 /* Sort sigma descending, normalise rows into Ut, apply chi_max / relative cutoff on the device.
  * info[2*b] = kept rank, winfo[2*b] = discarded weight sum_{k>=kept} sigma_k^2, winfo[2*b+1] = sigma_0.

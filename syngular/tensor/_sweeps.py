@@ -711,7 +711,6 @@ def gram_with_environment(M2, E, b, r):
 
 
 CHOLESKY_MIN_N = 129          # multi-CTA Jacobi problems run on the shifted Cholesky factor of the Gram matrix (see eigh_gram); 0 = off
-PRECONDITION_MIN_N = 0        # FP32-preconditioned eigen-solver for Gram matrices at least this large; 0 = off (see eigh_gram)
 
 
 def eigh_gram(A, chi_max, cutoff, rank_tol):
@@ -719,15 +718,8 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
     returns (Ut, sigma, info, winfo) like ops.jacobi_solve(sqrt_mode=True) -- rows of Ut are the eigenvectors, sorted; `info` is on
     the host and the solve has been checked for convergence (a non-converged Jacobi is resumed, never truncated on).
 
-    Large problems are preconditioned in FP32: an FP32 Jacobi pass (cheap rounds) gives an approximate eigenbasis U0; two
-    Newton-Schulz steps U <- U (1.5 I - 0.5 U^T U) (FP64 GEMMs) make it orthonormal to 1e-15; A' = U A U^T is then diagonal to
-    ~1e-6 and the FP64 Jacobi converges in ~3 sweeps instead of ~13 (measured, tools/precond_experiment.py).  All accuracy
-    comes from the FP64 stage: U is exactly orthogonal, so A' has exactly A's spectrum.  If the FP32 basis is not close enough
-    to orthogonal (rank-deficient A), fall back to the plain FP64 sweeps.
-
-    Measured on the B200 at n = 512 (tools/precond_diag.py): FP32 pass 5.3 ms (11 sweeps: its rounds are latency-bound like the
-    FP64 ones, only 1.5x cheaper) + 0.3 ms of GEMMs + 2.1 ms FP64 (3 sweeps) = 7.7 ms versus 8.2 ms for the plain 11 FP64 sweeps:
-    a 6 % gain, not worth the extra moving parts -- OFF by default, kept as an option and as a record of the experiment."""
+    (An FP32-preconditioned variant -- FP32 Jacobi for an approximate basis, two Newton-Schulz steps, three FP64 sweeps -- was measured
+    in round 1 at 7.7 ms against 8.2 ms for the plain sweeps at n = 512 and removed in round 2: not worth its moving parts.)"""
     n = A.shape[0]
     null_rel = rank_tol * rank_tol
     if CHOLESKY_MIN_N and n >= CHOLESKY_MIN_N and A.is_contiguous():
@@ -735,19 +727,6 @@ def eigh_gram(A, chi_max, cutoff, rank_tol):
         # 13 on the C2 plateau, 15 instead of 27 on its rank-deficient sites (tools/chol_experiment.py); sigma comes out directly.
         B, shift = ops.chol_upper(A)
         return ops.jacobi_solve(B, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=2, shift=shift, null_rel=0.0)
-    if PRECONDITION_MIN_N and n >= PRECONDITION_MIN_N:
-        G32 = ops.cast_f32(A)
-        ops.jacobi_rows_f32(G32)
-        U = ops.rows_to_basis(G32)
-        for _ in range(2):
-            X = ops.matmul(U, U.t())
-            Un = ops.copy_strided(U)
-            ops.matmul(X, U, out=Un, alpha=-0.5, beta=1.5)
-            U = Un
-        if float(ops.identity_deviation(ops.matmul(U, U.t())).item()) < 1e-12:
-            Ap = ops.matmul(ops.matmul(U, A), U.t())
-            Ut2, sigma, info, winfo = ops.jacobi_solve(Ap, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True, null_rel=null_rel)
-            return ops.matmul(Ut2, U), sigma, info, winfo
     return ops.jacobi_solve(A, chi_max, cutoff, rank_tol=rank_tol, sqrt_mode=True, null_rel=null_rel)
 
 

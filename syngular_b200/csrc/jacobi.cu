@@ -780,38 +780,6 @@ int jacobi_finalize_f64(const double* G, int64_t ld, int64_t bs, int n, int batc
 }  // namespace syn
 
 namespace syn {
-int jacobi_rows_f32(float* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes, int max_sweeps, double tol,
-                    double null_rel, cudaStream_t st) {
-    SYN_REQUIRE(batch >= 1 && max_sweeps >= 1, "syn_jacobi_rows_f32: bad batch / max_sweeps");
-    SYN_REQUIRE(ctrl_bytes >= jacobi_ctrl_bytes(batch, max_sweeps), "syn_jacobi_rows_f32: control buffer too small");
-    JacPlan pl;
-    if (int rc = jac_plan(n, pl, sizeof(float))) return rc;
-    SYN_CUDA(cudaMemsetAsync(ctrl, 0, jacobi_ctrl_bytes(batch, max_sweeps), st));
-    const int stride = jacobi_ctrl_stride(max_sweeps);
-    switch (pl.nreg) {
-        case 4: return launch_jacobi<float, 4, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        case 8: return launch_jacobi<float, 8, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        case 16: return launch_jacobi<float, 16, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-        default: return launch_jacobi<float, 32, 512>(G, ld, bs, n, batch, pl, (unsigned*)ctrl, stride, max_sweeps, tol, null_rel, st);
-    }
-}
-
-// ---- helpers of the FP32-preconditioned eigen-solver -------------------------------------------------------------------
-__global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
-}
-// U[i][:] = double(G32[i][:]) / |G32[i][:]|   (rows of the FP32 Jacobi result -> approximate eigenvectors)
-__global__ void rows_to_basis_kernel(const float* __restrict__ G, double* __restrict__ U, int n) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (r >= n) return;
-    const float* g = G + (int64_t)r * n;
-    double s = 0.0;
-    for (int c = lane; c < n; c += 32) { double x = (double)g[c]; s = fma(x, x, s); }
-    s = warp_sum(s);
-    const double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
-    for (int c = lane; c < n; c += 32) U[(int64_t)r * n + c] = (s > 0.0) ? (double)g[c] * inv : (c == r ? 1.0 : 0.0);
-}
 // out[0] = max_ij |X[i][j] - delta_ij|   (single CTA)
 __global__ void __launch_bounds__(1024, 1) identity_dev_kernel(const double* __restrict__ X, int n, double* __restrict__ out) {
     __shared__ double red[32];
@@ -834,23 +802,6 @@ __global__ void __launch_bounds__(1024, 1) identity_dev_kernel(const double* __r
 }
 }  // namespace syn
 
-extern "C" int syn_jacobi_rows_f32(float* G, int64_t ld, int64_t bs, int n, int batch, void* ctrl, size_t ctrl_bytes, int max_sweeps,
-                                   double tol, double null_rel, void* stream) {
-    return syn::jacobi_rows_f32(G, ld, bs, n, batch, ctrl, ctrl_bytes, max_sweeps, tol, null_rel, (cudaStream_t)stream);
-}
-extern "C" int syn_cast_f64_f32(const double* src, float* dst, int64_t n, void* stream) {
-    using namespace syn;
-    if (n <= 0) return 0;
-    int64_t b = (n + 255) / 256;
-    cast_f64_f32_kernel<<<(unsigned)(b > 4096 ? 4096 : b), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
-    return launch_status("cast_f64_f32_kernel");
-}
-extern "C" int syn_rows_to_basis_f32_f64(const float* G, double* U, int n, void* stream) {
-    using namespace syn;
-    SYN_REQUIRE(n >= 1, "syn_rows_to_basis_f32_f64: bad n");
-    rows_to_basis_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(G, U, n);
-    return launch_status("rows_to_basis_kernel");
-}
 extern "C" int syn_identity_deviation_f64(const double* X, int n, double* out, void* stream) {
     using namespace syn;
     SYN_REQUIRE(n >= 1, "syn_identity_deviation_f64: bad n");

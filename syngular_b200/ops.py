@@ -460,32 +460,6 @@ def tt_dense3_tf32(x, packed, bias=None, relu=True, out=None):
     return out
 
 
-def jacobi_rows_f32(G, max_sweeps=30, tol=None, null_rel=1e-6):
-    """FP32 one-sided Jacobi on the rows of a contiguous float32 (n x n) matrix, in place (preconditioning sweeps)."""
-    assert G.is_cuda and G.dtype == torch.float32 and G.dim() == 2 and G.is_contiguous()
-    n = G.shape[0]
-    ctrl = workspace(lib.syn_jacobi_ctrl_bytes(1, max_sweeps), G.device, tag="jacobi_ctrl32")
-    t = tol if tol is not None else 4.0 * (float(n) ** 0.5) * 5.96e-8
-    check(lib.syn_jacobi_rows_f32(ptr(G), _i64(n), _i64(n * n), _i32(n), _i32(1), ptr(ctrl), _sz(ctrl.numel() * 8), _i32(max_sweeps),
-                                  _dbl(t), _dbl(null_rel), stream_ptr()), "syn_jacobi_rows_f32")
-    return G
-
-
-def cast_f32(A):
-    require_cuda_f64(A)
-    A = A.contiguous()
-    out = torch.empty(tuple(A.shape), dtype=torch.float32, device=A.device)
-    check(lib.syn_cast_f64_f32(ptr(A), ptr(out), _i64(A.numel()), stream_ptr()), "syn_cast_f64_f32")
-    return out
-
-
-def rows_to_basis(G32):
-    n = G32.shape[0]
-    U = torch.empty((n, n), dtype=torch.float64, device=G32.device)
-    check(lib.syn_rows_to_basis_f32_f64(ptr(G32), ptr(U), _i32(n), stream_ptr()), "syn_rows_to_basis_f32_f64")
-    return U
-
-
 def identity_deviation(X):
     require_cuda_f64(X)
     out = torch.empty((1,), dtype=torch.float64, device=X.device)

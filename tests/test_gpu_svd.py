@@ -107,25 +107,25 @@ def test_site_contractions_and_overlap_vs_oracle():
     assert abs(got - R.overlap(P, Q)) < 1e-12 * abs(R.overlap(P, Q)) + 1e-300
 
 
-def test_fp32_preconditioned_eigensolver_option():
-    """The optional FP32-preconditioned path of eigh_gram gives the same spectrum / subspace as the plain FP64 sweeps."""
+def test_eigh_gram_with_and_without_the_cholesky_start():
+    """eigh_gram (Jacobi on the shifted Cholesky factor, or on the Gram matrix itself) against the singular values of the factor."""
     from syngular.tensor import _sweeps as sw
     rng = np.random.default_rng(21)
     B = rng.normal(size=(256, 1024))
     A = B @ B.T
     ref = np.linalg.svd(B, compute_uv=False)
-    old, old_chol = sw.PRECONDITION_MIN_N, sw.CHOLESKY_MIN_N
-    sw.CHOLESKY_MIN_N = 0
+    old_chol = sw.CHOLESKY_MIN_N
     try:
-        for flag in (0, 256):
-            sw.PRECONDITION_MIN_N = flag
+        for flag in (0, 129):
+            sw.CHOLESKY_MIN_N = flag
             Ut, sigma, info, winfo = sw.eigh_gram(torch.from_numpy(A.copy()).cuda(), 100, 0.0, 3.2e-7)
+            assert int(info[1]) == 256                                   # the convergence verdict of the rows kernel travels in info[1]
             assert np.max(np.abs(sigma.cpu().numpy() - ref)) < 1e-10 * ref[0]
             U = Ut.cpu().numpy()
             assert np.max(np.abs(U @ U.T - np.eye(256))) < 1e-11
             assert np.max(np.abs(U[:100] @ A @ U[:100].T - np.diag(ref[:100] ** 2))) < 1e-9 * ref[0] ** 2
     finally:
-        sw.PRECONDITION_MIN_N, sw.CHOLESKY_MIN_N = old, old_chol
+        sw.CHOLESKY_MIN_N = old_chol
 
 
 @pytest.mark.parametrize("n,rank", [(1, 1), (5, 5), (64, 64), (100, 37), (128, 128), (200, 200), (512, 512), (320, 100), (130, 1), (1024, 700)])
