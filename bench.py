@@ -711,6 +711,12 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            # the batched configs of BASELINE.json ("batched states/s at 1-8 GPU"), whole-job aggregates of this run; `--workload c4 | c5`
+            # print them as full lines of their own (e2e, roofline, cpu_baseline)
+            "batched": [{"metric": "batched_overlap_states_per_s", "value": c4_value, "unit": "states/s", "n_gpus": world, "scaling": "strong",
+                         "workload": "C4: 8192 MPS pairs (N=32, d=2, chi=64), batch-sharded, one all-gather"},
+                        {"metric": "tensordense_forward_samples_per_s", "value": c5_value, "unit": "samples/s", "n_gpus": world, "scaling": "strong",
+                         "workload": "C5: TensorDense 65536 x 4096 float32 on the fused tcgen05 TF32 kernel, batch-sharded"}],
             "extra": {"c1_readme_chain": c1, "c3_circuit": c3, "c4_batched_overlaps_states_per_s": c4_value, "c4_ms_per_batch": ms_c4 / c4_reps,
                       "c4_note": "BASELINE configs[3]: 8192 x (N=32, d=2, chi=64) overlaps, batch-sharded over %d GPU(s), one all-gather of 8192 "
                                  "float64; %.2f TFLOP/s FP64, %.0f GB/s of core traffic; gathered %s" % (

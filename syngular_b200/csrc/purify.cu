@@ -278,7 +278,7 @@ constexpr size_t PF_SMEM = (size_t)PF_STAGES * 2 * PF_T * PF_LD * sizeof(double)
 
 struct PurifyArgs {
     const double* A;
-    double *X0, *X1, *Ua, *Ub, *Va, *Vb, *G, *Uout, *ctrl, *info;
+    double *X0, *X1, *Ua, *Ub, *Va, *Vb, *G, *G2, *Uout, *ctrl, *info;
     unsigned* bar;
     int n, ne, sp2_max, ns_max;
     int ns_only;             // 1: A is an (n x ne) matrix with row stride ld0 whose columns are to be orthonormalised (no projection phase)
@@ -402,7 +402,8 @@ __device__ __forceinline__ void pf_atomic_max(double* addr, double v) {       //
 }
 
 // ctrl layout (doubles, zeroed by the host): [0] |A|_F^2  [1] sum A o P  [2..3] unused  [4 + 2 it] tr X_it  [5 + 2 it] |X_it|_F^2
-//                                            [4 + 2 (sp2_max + 2) + it] max |G_it - I|
+//                                            [4 + 2 (sp2_max + 2) + it] max |G_it - I| (final iterate only)
+//                                            [4 + 2 (sp2_max + 2) + (ns_max + 2) + it] tr G_it
 __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const PurifyArgs a) {
     extern __shared__ __align__(16) double pf_smem[];
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3, q = (tid >> 5) & 3;
@@ -413,8 +414,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     double* ctrl = a.ctrl;
     double* trf = ctrl + 4;
     double* devs = ctrl + 4 + 2 * (a.sp2_max + 2);
+    double* trs = devs + (a.ns_max + 2);
     const int64_t gstride = (int64_t)gridDim.x * PF_THREADS, gid = (int64_t)blockIdx.x * PF_THREADS + tid;
 
+    // both Gram accumulators of the Newton-Schulz phase start at zero (they are accumulated into with atomics)
+    for (int64_t i = gid; i < (int64_t)ne * ne; i += gstride) { a.G[i] = 0.0; a.G2[i] = 0.0; }
     // ---- |A|_F^2 -------------------------------------------------------------------------------------------------------------------
     {
         double s = 0.0;
@@ -519,16 +523,29 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     const double* V = a.ns_only ? a.Vb : Xc;                  // (ne x n), ld n
     double* Un = a.Ua;  double* Vn = a.Va;
     const int TG = ne / PF_T, lower_g = TG * (TG + 1) / 2, tiles_u = (n / PF_T) * TG;
+    // The Gram matrix G = U^T U = V V^T of every step is formed by ALL CTAs: its lower tiles are split KS ways along the contraction
+    // (36 tiles x 4 splits at 512 -> 256 instead of 36 busy CTAs of 136) and the partial tiles are accumulated with FP64 atomics into one of
+    // two buffers (the other one is cleared during the update phase).  Convergence is read from tr G = sum sigma_i^2, which the same
+    // atomics accumulate: after a standard step x -> 1.5 x - 0.5 x^3 every singular value is <= 1, so ne - tr G = sum (1 - sigma_i^2)
+    // bounds every 1 - sigma_i^2; max |G - I| of the final iterate (what the host checks) is taken once at the end.
+    int KS = 1;
+    while (lower_g * KS * 2 <= (int)gridDim.x + (int)gridDim.x / 8 && (n / (KS * 2)) % 2 == 0 && n / (KS * 2) >= 64) KS *= 2;
+    const int Kc = n / KS;
     int ns = 0;
     double dev = 0.0, dev0 = 0.0;
+    int steep_steps = PF_STEEP;
+    bool last_steep = true;              // the map that produced the current iterate (the start counts as "not yet standard")
+    double* Gc = a.G;
     for (;; ++ns) {
-        // G = V V^T (lower tiles + mirror), dev = max |G - I|
-        double dmax = 0.0;
-        for (int tile = blockIdx.x; tile < lower_g; tile += gridDim.x) {
+        Gc = (ns & 1) ? a.G2 : a.G;
+        double* Gnext = (ns & 1) ? a.G : a.G2;
+        double trp = 0.0;
+        for (int item = blockIdx.x; item < lower_g * KS; item += gridDim.x) {
+            const int tile = item % lower_g, ks = item / lower_g;
             int ti, tj;
             pf_lower_tile(tile, ti, tj);
             double acc[2][2][2];
-            const bool owner = pf_tile_nt(V, n, V, n, ti * PF_T, tj * PF_T, n, pf_smem, acc);
+            const bool owner = pf_tile_nt(V + (int64_t)ks * Kc, n, V + (int64_t)ks * Kc, n, ti * PF_T, tj * PF_T, Kc, pf_smem, acc);
             if (owner) {
 #pragma unroll
                 for (int i = 0; i < 2; i++)
@@ -538,28 +555,61 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
                         for (int e = 0; e < 2; e++) {
                             const int r = ti * PF_T + wm0 + i * 8 + g, c = tj * PF_T + wn0 + j * 8 + 2 * t + e;
                             const double gv = acc[i][j][e];
-                            a.G[(int64_t)r * ne + c] = gv;
-                            if (ti != tj) a.G[(int64_t)c * ne + r] = gv;
-                            dmax = fmax(dmax, fabs(gv - (r == c ? 1.0 : 0.0)));
+                            atomicAdd(Gc + (int64_t)r * ne + c, gv);
+                            if (ti != tj) atomicAdd(Gc + (int64_t)c * ne + r, gv);
+                            if (r == c) trp += gv;
                         }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-        if (lane == 0 && dmax > 0.0) pf_atomic_max(devs + ns, dmax);
+        block_accumulate(trp, 0.0, trs + ns, nullptr);
         pf_grid_barrier(a.bar, target);
-        dev = __ldcg(devs + ns);
-        if (ns == 0) dev0 = dev;      // max |1 - |P e_i||^2|: close to 1 unless the leading coordinates already span the subspace
-        if (dev < 1e-13 || ns >= a.ns_max) break;
+        const double tr = __ldcg(trs + ns);
+        double gamma = 1.0;
+        if (ns == 0) {
+            // One scan of the first Gram matrix per CTA (every CTA computes the same numbers from the same data, no extra barrier):
+            //   dev0 = max |G - I| decides whether the steep map is used at all (a start that is already near-orthonormal skips it);
+            //   rho = max column sum of |G| >= sigma_max^2 (Gershgorin).  The Frobenius scaling of the NS-only start leaves
+            //   sigma_max ~ 1 / sqrt(ne) for a generic matrix: gamma = rho^(-1/2) is folded into the coefficients of the first step and
+            //   the steep phase is shortened by the log2(gamma) doublings it replaces.
+            __shared__ double s_col[PF_THREADS], s_dev[PF_THREADS];
+            double best = 0.0, dbest = 0.0;
+            for (int c0 = tid; c0 < ne; c0 += PF_THREADS) {
+                double sum = 0.0;
+                for (int r = 0; r < ne; ++r) {
+                    const double v = __ldcg(Gc + (int64_t)r * ne + c0);
+                    sum += fabs(v);
+                    dbest = fmax(dbest, fabs(v - (r == c0 ? 1.0 : 0.0)));
+                }
+                best = fmax(best, sum);
+            }
+            s_col[tid] = best;
+            s_dev[tid] = dbest;
+            __syncthreads();
+            for (int o = PF_THREADS / 2; o > 0; o >>= 1) {
+                if (tid < o) { s_col[tid] = fmax(s_col[tid], s_col[tid + o]); s_dev[tid] = fmax(s_dev[tid], s_dev[tid + o]); }
+                __syncthreads();
+            }
+            const double rho = s_col[0];
+            dev0 = s_dev[0];
+            __syncthreads();
+            if (a.ns_only && rho > 0.0 && rho < 1.0) {
+                gamma = rsqrt(rho);
+                int cut = 0;
+                for (double x = gamma; x >= 2.0; x *= 0.5) ++cut;
+                steep_steps = PF_STEEP - cut < 2 ? 2 : PF_STEEP - cut;
+            }
+        }
+        if (ns >= 1 && !last_steep && fabs((double)ne - tr) < 8e-13) break;
+        if (ns >= a.ns_max) break;
         // U' = ca U + cb U G   (G symmetric: rows of G are its columns), V' = U'^T
         // the first steps use x -> 2x - x^3 (slope 2 at 0 instead of 1.5; values near 1 stay within [0.88, 1.09]): the smallest
         // singular values of P[:, :ne] (1e-3 .. 1e-1 on the C2 chain) reach the quadratic region in half the steps
-        const bool steep = ns < PF_STEEP && dev0 > 0.5;
-        const double ca = steep ? 2.0 : 1.5, cb = steep ? -1.0 : -0.5;
+        const bool steep = ns < steep_steps && dev0 > 0.5;
+        const double ca = (steep ? 2.0 : 1.5) * gamma, cb = (steep ? -1.0 : -0.5) * gamma * gamma * gamma;
         for (int tile = blockIdx.x; tile < tiles_u; tile += gridDim.x) {
             const int ti = tile / TG, tj = tile - ti * TG;
             double acc[2][2][2];
-            const bool owner = pf_tile_nt(U, ldu, a.G, ne, ti * PF_T, tj * PF_T, ne, pf_smem, acc);
+            const bool owner = pf_tile_nt(U, ldu, Gc, ne, ti * PF_T, tj * PF_T, ne, pf_smem, acc);
             if (owner) {
 #pragma unroll
                 for (int i = 0; i < 2; i++)
@@ -574,10 +624,25 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
                         }
             }
         }
+        for (int64_t i = gid; i < (int64_t)ne * ne; i += gstride) Gnext[i] = 0.0;       // the accumulator of the next step
         pf_grid_barrier(a.bar, target);
+        last_steep = steep;
         U = Un; ldu = ne; V = Vn;
         Un = (Un == a.Ua) ? a.Ub : a.Ua;
         Vn = (Vn == a.Va) ? a.Vb : a.Va;
+    }
+    // max |G - I| of the final iterate (Gc is complete: it was read after the barrier that closed its accumulation)
+    {
+        double dmax = 0.0;
+        for (int64_t i = gid; i < (int64_t)ne * ne; i += gstride) {
+            const int64_t r = i / ne, c = i - r * ne;
+            dmax = fmax(dmax, fabs(__ldcg(Gc + i) - (r == c ? 1.0 : 0.0)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        if (lane == 0 && dmax > 0.0) pf_atomic_max(devs + ns, dmax);
+        pf_grid_barrier(a.bar, target);
+        dev = __ldcg(devs + ns);
     }
     // ---- results -------------------------------------------------------------------------------------------------------------------
     for (int64_t i = gid; i < (int64_t)n * ne; i += gstride) {
@@ -598,7 +663,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
 }
 
 static size_t purify_fused_ws_doubles(int n, int ne, int sp2_max, int ns_max) {
-    return (size_t)2 * n * n + (size_t)4 * n * ne + (size_t)ne * ne + 4 + 2 * (sp2_max + 2) + (ns_max + 2) + 64;
+    return (size_t)2 * n * n + (size_t)4 * n * ne + (size_t)2 * ne * ne + 4 + 2 * (sp2_max + 2) + 2 * (ns_max + 2) + 64;
 }
 
 static bool ortho_fused_fits(int m, int q) { return m % PF_T == 0 && q % PF_T == 0 && m >= 128 && q >= 32 && q <= m; }
@@ -631,8 +696,9 @@ int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int
     a.X0 = ws; a.X1 = a.X0 + nn;
     a.Ua = a.X1 + nn; a.Ub = a.Ua + nk; a.Va = a.Ub + nk; a.Vb = a.Va + nk;
     a.G = a.Vb + nk;
-    a.ctrl = a.G + (int64_t)ne * ne;
-    const size_t ctrl_doubles = 4 + 2 * (sp2_max + 2) + (ns_max + 2);
+    a.G2 = a.G + (int64_t)ne * ne;
+    a.ctrl = a.G2 + (int64_t)ne * ne;
+    const size_t ctrl_doubles = 4 + 2 * (sp2_max + 2) + 2 * (ns_max + 2);
     a.bar = reinterpret_cast<unsigned*>(a.ctrl + ctrl_doubles);
     a.Uout = U; a.info = info;
     a.n = n; a.ne = ne; a.sp2_max = sp2_max; a.ns_max = ns_max;
