@@ -65,6 +65,12 @@ static_assert(NB1 % GROUPS == 0, "a D1 buffer must always be drained by the same
 // mbarrier waits are by parity: a waiter may run at most one phase ahead.  An epilogue group takes every GROUPS-th chunk and its wait on
 // a slot proves that the chunk SLOTS uses earlier was consumed, so it stays within one phase only if GROUPS <= SLOTS.
 static_assert(GROUPS <= SLOTS, "epilogue groups could run two phases ahead of an operand slot");
+// The issue loops are fully unrolled so that every ring position is a compile-time constant (the issuing warp's instruction stream,
+// not the tensor pipe, paces this kernel: a group of four tcgen05.mma with run-time descriptors costs ~460 cycles of R2UR moves): a
+// sample must use every D1 buffer and every operand slot an EVEN number of times, so that neither the position nor the barrier parity
+// depends on the sample index.
+static_assert(16 % NB1 == 0 && (16 / NB1) % 2 == 0, "D1 buffer position / parity must not depend on the sample");
+static_assert(24 % SLOTS == 0 && (24 / SLOTS) % 2 == 0, "operand slot position / parity must not depend on the sample");
 
 // byte offset of element (row, kbyte) in a K-major operand block with 128-byte rows / 128B swizzle, resp. 64-byte rows / 64B swizzle
 __host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t kbyte) {
@@ -151,16 +157,21 @@ __device__ __forceinline__ void tt_wait(uint64_t* bars, int id, uint32_t parity)
 }
 
 #ifdef SYN_TT_DEBUG
-__device__ uint32_t* g_tt_dbg = nullptr;      // host-mapped progress words: [block][warp][4]
+// timeline trace of CTA 0 (compile with -DSYN_TT_DEBUG): every mark appends (value, clock) to its warp's lane of a device buffer
+__device__ uint32_t* g_tt_dbg = nullptr;      // [warp][TT_TRACE_LEN][2]
+constexpr int TT_TRACE_LEN = 8192;
+#define TT_TRACE_DECL uint32_t tt_cnt_ = 0;
 #define TT_MARK(slot_, val_)                                                                            \
     do {                                                                                                \
-        if (g_tt_dbg && (threadIdx.x & 31) == 0) {                                                      \
-            volatile uint32_t* w_ = g_tt_dbg + ((size_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 + (slot_); \
-            *w_ = (uint32_t)(val_);                                                                     \
-            __threadfence_system();                                                                     \
+        if (g_tt_dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tt_cnt_ < TT_TRACE_LEN) {         \
+            uint32_t* w_ = g_tt_dbg + ((size_t)(threadIdx.x >> 5) * TT_TRACE_LEN + tt_cnt_) * 2;        \
+            w_[0] = (uint32_t)(val_);                                                                   \
+            w_[1] = (uint32_t)clock64();                                                                \
+            ++tt_cnt_;                                                                                  \
         }                                                                                               \
     } while (0)
 #else
+#define TT_TRACE_DECL
 #define TT_MARK(slot_, val_) do { } while (0)
 #endif
 
@@ -214,6 +225,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TT_TRACE_DECL
     const int h = blockIdx.x & 1;                                   // which half of o2 this CTA computes
     const int first = blockIdx.x >> 1, step = gridDim.x >> 1;       // its samples: first, first + step, ...
     const int my_samples = first < batch ? (batch - first + step - 1) / step : 0;
@@ -271,11 +283,12 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             tt_wait(bars, X_FULL, (uint32_t)(j & 1));
             // step 1, chunk c (= i2): D1[c % NB1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16); runs ahead of step 2 as far as
             // the D1 buffers allow
+#pragma unroll
             for (int c = 0; c < 16; c++) {
-                const uint32_t g1 = (uint32_t)(16 * j + c);          // running chunk count: D1 buffer g1 % NB1, its use g1 / NB1
-                const uint32_t b = g1 % NB1, use = g1 / NB1;
+                const uint32_t b = c % NB1, use = c / NB1;           // position and parity are the same in every sample (static_asserts above)
                 TT_MARK(0, 0x10000 + j * 256 + c);
                 tt_wait(bars, D1_EMPTY0 + b, (use & 1u) ^ 1u);
+                TT_MARK(0, 0x11000 + j * 256 + c);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t xd = x_desc + (uint64_t)(c * 64);
@@ -288,6 +301,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                     if (c == 15) umma_commit(&bars[X_EMPTY]);
                 }
                 __syncwarp();
+                TT_MARK(0, 0x12000 + j * 256 + c);
             }
         }
     } else if (warp == 1) {
@@ -303,11 +317,13 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             tt_wait(bars, W_FULL, 0);
             for (int j = 0; j < my_samples; j++) {
                 // step 2, chunk cc: D2[t] += T1 chunk (slot: 2 tiles of 128 x 16) . G2 half [(b1,o2l), (i2 = cc, b2)]^T
+#pragma unroll
                 for (int cc = 0; cc < 16; cc++) {
-                    const uint32_t u = (uint32_t)(24 * j + cc), slot = u % SLOTS;
+                    const uint32_t u = (uint32_t)cc, slot = u % SLOTS;          // compile-time ring position and parity
                     TT_MARK(0, 0x20000 + j * 256 + cc);
                     tt_wait(bars, SLOT_FULL0 + slot, (u / SLOTS) & 1u);
                     if (cc == 0) tt_wait(bars, D2_EMPTY, (uint32_t)(j & 1) ^ 1u);
+                    TT_MARK(0, 0x21000 + j * 256 + cc);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = slot64_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
@@ -322,13 +338,16 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                         if (cc == 15) umma_commit(&bars[D2_FULL]);
                     }
                     __syncwarp();
+                    TT_MARK(0, 0x22000 + j * 256 + cc);
                 }
                 // step 3, chunk p (= b1 pair): D3 += T2 chunk (slot: 128 x 32) . G1 [o1, (b1, i1)]^T
+#pragma unroll
                 for (int p = 0; p < 8; p++) {
-                    const uint32_t u = (uint32_t)(24 * j + 16 + p), slot = u % SLOTS;
+                    const uint32_t u = (uint32_t)(16 + p), slot = u % SLOTS;
                     TT_MARK(0, 0x30000 + j * 256 + p);
                     tt_wait(bars, SLOT_FULL0 + slot, (u / SLOTS) & 1u);
                     if (p == 0) tt_wait(bars, D3_EMPTY, (uint32_t)(j & 1) ^ 1u);
+                    TT_MARK(0, 0x31000 + j * 256 + p);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = slot128_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
@@ -359,13 +378,14 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         const int hb2 = lane & 1, i1_2 = lane >> 1;
         for (int j = 0; j < my_samples; j++) {
             const int s = first + j * step;
+#pragma unroll
             for (int c = 0; c < 16; c++) {
-                const uint32_t g1 = (uint32_t)(16 * j + c);          // running chunk count: group g1 % GROUPS, D1 buffer g1 % NB1
-                if (g1 % GROUPS != (uint32_t)grp) continue;
-                const uint32_t b = g1 % NB1, use = g1 / NB1;
-                const uint32_t u = (uint32_t)(24 * j + c), slot = u % SLOTS;
+                if ((16 * j + c) % GROUPS != grp) continue;          // running chunk count: the groups take the chunks in turn
+                const uint32_t b = c % NB1, use = c / NB1;
+                const uint32_t u = (uint32_t)c, slot = u % SLOTS;
                 TT_MARK(0, 0x40000 + j * 256 + c);
                 tt_wait(bars, D1_FULL0 + b, use & 1u);
+                TT_MARK(0, 0x41000 + j * 256 + c);
                 tc_fence_after();
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tq + TM_D1 + b * 32, r0);
@@ -375,6 +395,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 mbar_arrive(&bars[D1_EMPTY0 + b]);
                 TT_MARK(0, 0x50000 + j * 256 + c);
                 tt_wait(bars, SLOT_EMPTY0 + slot, ((u / SLOTS) & 1u) ^ 1u);
+                TT_MARK(0, 0x51000 + j * 256 + c);
                 uint8_t* dst = smem + OFF_SLOT + slot * SLOT_BYTES + r1_base;
 #pragma unroll
                 for (int i1 = 0; i1 < 16; i1++) {
@@ -382,18 +403,22 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                     *reinterpret_cast<uint32_t*>(dst + off) = r0[i1];
                     *reinterpret_cast<uint32_t*>(dst + 8192 + off) = r1[i1];
                 }
+                TT_MARK(0, 0x52000 + j * 256 + c);
                 fence_async_smem();
                 mbar_arrive(&bars[SLOT_FULL0 + slot]);
+                TT_MARK(0, 0x53000 + j * 256 + c);
             }
             TT_MARK(0, 0x60000 + j * 256);
             tt_wait(bars, D2_FULL, (uint32_t)(j & 1));
+            TT_MARK(0, 0x61000 + j * 256);
             tc_fence_after();
             int last_p = -1;                                         // this group's last T2 chunk of the sample: its last read of D2
             for (int p = 0; p < 8; p++)
                 if ((uint32_t)(8 * j + p) % GROUPS == (uint32_t)grp) last_p = p;
+#pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((uint32_t)(8 * j + p) % GROUPS != (uint32_t)grp) continue;
-                const uint32_t u = (uint32_t)(24 * j + 16 + p), slot = u % SLOTS;
+                const uint32_t u = (uint32_t)(16 + p), slot = u % SLOTS;
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tq + TM_D2 + p * 16, r0);
                 tmem_ld16(tq + TM_D2 + 128 + p * 16, r1);
@@ -417,6 +442,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             if (j % GROUPS != grp) continue;
             TT_MARK(0, 0x80000 + j * 256);
             tt_wait(bars, D3_FULL, (uint32_t)(j & 1));
+            TT_MARK(0, 0x81000 + j * 256);
             tc_fence_after();
             uint32_t acc[16];
             tmem_ld16(tq + TM_D3, acc);
