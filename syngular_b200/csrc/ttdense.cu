@@ -41,7 +41,8 @@ namespace syn {
 namespace tt {
 
 constexpr int GROUPS = 2;                                       // epilogue groups of four warps
-constexpr int THREADS = 64 + 128 * GROUPS;
+constexpr int THREADS = 64 + 128 * GROUPS + 64;                 // 2 issuer warps + epilogue warps + 2 more issuer warps
+constexpr int WARP_S1B = 2 + 4 * GROUPS, WARP_S23B = WARP_S1B + 1;
 constexpr int SLOTS = 3;
 constexpr int NB1 = 4;                                          // D1 (step-1 accumulator) buffers: step 1 runs up to NB1 chunks ahead
 constexpr uint32_t SLOT_BYTES = 16384;
@@ -56,8 +57,8 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;           // + slack for t
 // packed weight image in global memory (floats): [A1 16 KB][B3 16 KB][B2 half 0 128 KB][B2 half 1 128 KB]
 constexpr size_t IMG_A1 = 0, IMG_B3 = 4096, IMG_B2 = 8192, IMG_FLOATS = 8192 + 2 * 32768;
 // TMEM columns
-constexpr uint32_t TM_D1 = 0, TM_D2 = 32 * NB1, TM_D3 = TM_D2 + 256, TM_COLS = 512;
-static_assert(TM_D3 + 16 <= TM_COLS, "TMEM columns");
+constexpr uint32_t TM_D1 = 0, TM_D2 = 32 * NB1, TM_D3 = TM_D2 + 256, TM_COLS = 512;      // D3: two partial accumulators of 16 columns
+static_assert(TM_D3 + 32 <= TM_COLS, "TMEM columns");
 
 enum Bar { W_FULL = 0, X_FULL, X_EMPTY, D1_FULL0, D1_EMPTY0 = D1_FULL0 + NB1, SLOT_FULL0 = D1_EMPTY0 + NB1, SLOT_EMPTY0 = SLOT_FULL0 + SLOTS,
            D2_FULL = SLOT_EMPTY0 + SLOTS, D2_EMPTY, D3_FULL, D3_EMPTY, NUM_BARS };
@@ -233,18 +234,18 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
     if (threadIdx.x == 0) {
         mbar_init(&bars[W_FULL], 1);
         mbar_init(&bars[X_FULL], 1);
-        mbar_init(&bars[X_EMPTY], 1);
+        mbar_init(&bars[X_EMPTY], 2);
         for (int b = 0; b < NB1; b++) {
-            mbar_init(&bars[D1_FULL0 + b], 1);
+            mbar_init(&bars[D1_FULL0 + b], 2);
             mbar_init(&bars[D1_EMPTY0 + b], 128);
         }
         for (int s = 0; s < SLOTS; s++) {
             mbar_init(&bars[SLOT_FULL0 + s], 128);
-            mbar_init(&bars[SLOT_EMPTY0 + s], 1);
+            mbar_init(&bars[SLOT_EMPTY0 + s], 2);
         }
-        mbar_init(&bars[D2_FULL], 1);
+        mbar_init(&bars[D2_FULL], 2);
         mbar_init(&bars[D2_EMPTY], 128 * GROUPS);
-        mbar_init(&bars[D3_FULL], 1);
+        mbar_init(&bars[D3_FULL], 2);
         mbar_init(&bars[D3_EMPTY], 128);
         fence_async_smem();
     }
@@ -256,12 +257,15 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
-    if (warp == 0) {
-        // ===== TMA producer + step-1 issuer (the whole warp runs the loop; one elected lane issues) =========================================
+    if (warp == 0 || warp == WARP_S1B) {
+        // ===== step-1 issuers: warp 0 (tile 0; it is also the TMA producer) and warp WARP_S1B (tile 1).  Each issuing warp's instruction
+        // stream (descriptor moves into uniform registers, ~100 cycles per tcgen05.mma), not the tensor pipe, bounds the issue rate, so
+        // every MMA group is split over two warps by accumulator tile.  The whole warp runs the loop; one elected lane issues. =========
+        const int tile = warp == 0 ? 0 : 1;
         constexpr uint32_t ID_S1 = idesc_tf32(128, 16);
         const uint64_t d64 = smem_desc(0, 512, LAYOUT_SW64);
         const uint64_t a1_desc = d64 + ((sbase + OFF_A1) >> 4), x_desc = d64 + ((sbase + OFF_X) >> 4);
-        if (elect_one()) {
+        if (warp == 0 && elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
             // weights: A1 (16 KB), B3 (16 KB), this CTA's half of B2 (128 KB in 8 copies)
             mbar_expect_tx(&bars[W_FULL], 16384u + 16384u + 131072u);
@@ -274,12 +278,14 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
         tt_wait(bars, W_FULL, 0);
         for (int j = 0; j < my_samples; j++) {
             TT_MARK(0, 0x100 + j);
-            tt_wait(bars, X_EMPTY, (uint32_t)(j & 1) ^ 1u);          // a fresh barrier passes a wait on the "previous" phase
-            if (elect_one()) {
-                mbar_expect_tx(&bars[X_FULL], 16384u);
-                tma_load_4d(smem + OFF_X, &xmap, 0, 0, 0, first + j * step, &bars[X_FULL]);
+            if (warp == 0) {
+                tt_wait(bars, X_EMPTY, (uint32_t)(j & 1) ^ 1u);      // a fresh barrier passes a wait on the "previous" phase
+                if (elect_one()) {
+                    mbar_expect_tx(&bars[X_FULL], 16384u);
+                    tma_load_4d(smem + OFF_X, &xmap, 0, 0, 0, first + j * step, &bars[X_FULL]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
             tt_wait(bars, X_FULL, (uint32_t)(j & 1));
             // step 1, chunk c (= i2): D1[c % NB1][t] = A1[t] (128 x 16) . x[(i2 = c, i1), i3]^T (16 x 16); runs ahead of step 2 as far as
             // the D1 buffers allow
@@ -293,10 +299,8 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 if (elect_one()) {
                     const uint64_t xd = x_desc + (uint64_t)(c * 64);
 #pragma unroll
-                    for (int t = 0; t < 2; t++)
-#pragma unroll
-                        for (int k = 0; k < 2; k++)
-                            umma_tf32(tmem + TM_D1 + b * 32 + t * 16, a1_desc + (uint64_t)(t * 512 + k * 2), xd + (uint64_t)(k * 2), ID_S1, k);
+                    for (int k = 0; k < 2; k++)
+                        umma_tf32(tmem + TM_D1 + b * 32 + tile * 16, a1_desc + (uint64_t)(tile * 512 + k * 2), xd + (uint64_t)(k * 2), ID_S1, k);
                     umma_commit(&bars[D1_FULL0 + b]);
                     if (c == 15) umma_commit(&bars[X_EMPTY]);
                 }
@@ -304,8 +308,10 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                 TT_MARK(0, 0x12000 + j * 256 + c);
             }
         }
-    } else if (warp == 1) {
-        // ===== step-2 / step-3 issuer (the whole warp runs the loop; one elected lane issues) ===============================================
+    } else if (warp == 1 || warp == WARP_S23B) {
+        // ===== step-2 / step-3 issuers: warp 1 takes accumulator tile 0 of step 2 and the first two k-steps of every step-3 chunk, warp
+        // WARP_S23B tile 1 and the last two k-steps (two partial D3 accumulators, added by the epilogue) ======================================
+        const int tile = warp == 1 ? 0 : 1;
         // Every ring position has a running use count u (24 operand-slot uses per sample: 16 T1 chunks, 8 T2 chunks):
         // slot = u % SLOTS, and the parity to wait for is (u / SLOTS) & 1 on a "full" barrier, the opposite on an "empty" one.
         {
@@ -329,11 +335,9 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                         const uint64_t ad = slot64_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
                         const uint64_t bd = b2_desc + (uint64_t)((cc >> 1) * 1024 + (cc & 1) * 4);
 #pragma unroll
-                        for (int t = 0; t < 2; t++)
-#pragma unroll
-                            for (int k = 0; k < 2; k++)
-                                umma_tf32(tmem + TM_D2 + t * 128, ad + (uint64_t)(t * 512 + k * 2), bd + (uint64_t)(k * 2), ID_S2,
-                                          (cc > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 2; k++)
+                            umma_tf32(tmem + TM_D2 + tile * 128, ad + (uint64_t)(tile * 512 + k * 2), bd + (uint64_t)(k * 2), ID_S2,
+                                      (cc > 0 || k > 0) ? 1u : 0u);
                         umma_commit(&bars[SLOT_EMPTY0 + slot]);
                         if (cc == 15) umma_commit(&bars[D2_FULL]);
                     }
@@ -353,8 +357,9 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
                         const uint64_t ad = slot128_desc + (uint64_t)(slot * (SLOT_BYTES >> 4));
                         const uint64_t bd = b3_desc + (uint64_t)(p * 128);
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            umma_tf32(tmem + TM_D3, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), ID_S3, (p > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 2; k++)
+                            umma_tf32(tmem + TM_D3 + tile * 16, ad + (uint64_t)((2 * tile + k) * 2), bd + (uint64_t)((2 * tile + k) * 2), ID_S3,
+                                      (p > 0 || k > 0) ? 1u : 0u);
                         umma_commit(&bars[SLOT_EMPTY0 + slot]);
                         if (p == 7) umma_commit(&bars[D3_FULL]);
                     }
@@ -444,8 +449,9 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             tt_wait(bars, D3_FULL, (uint32_t)(j & 1));
             TT_MARK(0, 0x81000 + j * 256);
             tc_fence_after();
-            uint32_t acc[16];
+            uint32_t acc[16], acc2[16];
             tmem_ld16(tq + TM_D3, acc);
+            tmem_ld16(tq + TM_D3 + 16, acc2);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[D3_EMPTY]);
@@ -455,7 +461,7 @@ tt_dense3_tf32_kernel(const __grid_constant__ CUtensorMap xmap, const float* __r
             const float* bo = bias ? bias + o2 * 16 + o3 : nullptr;
 #pragma unroll
             for (int o1 = 0; o1 < 16; o1++) {
-                float v = __uint_as_float(acc[o1]) + (bo ? __ldg(bo + o1 * 256) : 0.0f);
+                float v = __uint_as_float(acc[o1]) + __uint_as_float(acc2[o1]) + (bo ? __ldg(bo + o1 * 256) : 0.0f);
                 if (relu) v = fmaxf(v, 0.0f);
                 yo[o1 * 256] = v;
             }
