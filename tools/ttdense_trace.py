@@ -10,7 +10,7 @@ G = [torch.from_numpy(rng.normal(scale=0.05, size=s).astype(np.float32)).to(dev)
 packed = ops.tt_dense3_pack(*G)
 B = 74 * 6
 x = torch.randn((B, 4096), dtype=torch.float32, device=dev)
-NW, LEN = 10, 8192
+NW, LEN = 12, 8192
 buf = torch.zeros((NW, LEN, 2), dtype=torch.int32, device=dev)
 ops.tt_dense3_tf32(x, packed, None, relu=True)           # warm
 torch.cuda.synchronize()
@@ -18,8 +18,8 @@ ops.lib.syn_tt_debug_buffer(ctypes.c_void_p(buf.data_ptr()))
 ops.tt_dense3_tf32(x, packed, None, relu=True)
 torch.cuda.synchronize()
 t = buf.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-names = {0: "tma", 1: "mma23", 2: "epi g0 q2", 6: "epi g1 q2"}
-for w in (0, 1, 2, 6):
+names = {0: "tma+s1 t0", 1: "s23 t0", 2: "epi g0 q2", 6: "epi g1 q2", 10: "s1 t1", 11: "s23 t1"}
+for w in (0, 1, 2, 6, 11):
     ev = [(int(v), int(c)) for v, c in t[w] if v != 0]
     if not ev:
         continue
