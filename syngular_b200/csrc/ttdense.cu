@@ -55,7 +55,7 @@ constexpr uint32_t OFF_X = OFF_B3 + 16384;                      // 256 rows x 64
 constexpr uint32_t OFF_BAR = OFF_X + 16384;                     // mbarriers + TMEM base pointer
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;           // + slack for the 1024-byte alignment of the base
 // packed weight image in global memory (floats): [A1 16 KB][B3 16 KB][B2 half 0 128 KB][B2 half 1 128 KB]
-constexpr size_t IMG_A1 = 0, IMG_B3 = 4096, IMG_B2 = 8192, IMG_FLOATS = 8192 + 2 * 32768;
+constexpr size_t IMG_A1 = 0, IMG_B3 = 4096, IMG_B2 = 8192, IMG_FLOATS = 8192 + 2 * 32768 + 4096;      // + the G1 halves of the CTA-pair kernel
 // TMEM columns
 constexpr uint32_t TM_D1 = 0, TM_D2 = 32 * NB1, TM_D3 = TM_D2 + 256, TM_COLS = 512;      // D3: two partial accumulators of 16 columns
 static_assert(TM_D3 + 32 <= TM_COLS, "TMEM columns");
@@ -520,6 +520,10 @@ int tt_dense3_tf32(const float* x, const float* img, const float* bias, float* y
 }
 
 }  // namespace tt
+namespace ttp {
+int tt_dense3_tf32_pair(const float* x, const float* img, const float* bias, float* y, int batch, int relu, cudaStream_t st);
+int tt_pack_pair(const float* G1, float* img, cudaStream_t st);
+}  // namespace ttp
 }  // namespace syn
 
 #ifdef SYN_TT_DEBUG
@@ -534,9 +538,19 @@ extern "C" int syn_tt_dense3_pack_tf32(const float* G1, const float* G2, const f
     using namespace syn;
     SYN_REQUIRE(G1 && G2 && G3 && packed, "syn_tt_dense3_pack_tf32: null argument");
     tt::tt_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(G1, G2, G3, packed);
-    return launch_status("tt_pack_kernel");
+    if (int rc = launch_status("tt_pack_kernel")) return rc;
+    return ttp::tt_pack_pair(G1, packed, (cudaStream_t)stream);
 }
 
 extern "C" int syn_tt_dense3_tf32(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream) {
+    // SYN_TT_PAIR=1: the CTA-pair kernel (tcgen05 cta_group::2, csrc/ttdense_pair.cu); default: the single-CTA kernel
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char* e = getenv("SYN_TT_PAIR"); pair_mode = (e && e[0] == '1') ? 1 : 0; }
+    if (pair_mode == 1 && batch > 0) {
+        using namespace syn;
+        SYN_REQUIRE(x && packed && y, "syn_tt_dense3_tf32: null argument");
+        SYN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)packed) | ((uintptr_t)y)) & 15) == 0, "syn_tt_dense3_tf32: x, weights and y must be 16-byte aligned");
+        return syn::ttp::tt_dense3_tf32_pair(x, packed, bias, y, batch, relu, (cudaStream_t)stream);
+    }
     return syn::tt::tt_dense3_tf32(x, packed, bias, y, batch, relu, (cudaStream_t)stream);
 }
