@@ -231,6 +231,10 @@ int syn_round_chain_f64(int n_sites, const double* const* cores, const int* shap
 size_t syn_tt_dense3_packed_floats(void);
 int syn_tt_dense3_pack_tf32(const float* G1, const float* G2, const float* G3, float* packed, void* stream);
 int syn_tt_dense3_tf32(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream);
+/* Variant on CTA pairs (tcgen05.mma.cta_group::2, M = 256: the pair shares one sample, each CTA holds one half of G2 and of the output).
+ * Same arguments and tolerance.  Measured slower than the single-CTA kernel at batch 65536 (6.6 vs 6.2 ms), so nothing selects it by
+ * default; it is kept as a checked alternative. */
+int syn_tt_dense3_tf32_pair(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream);
 
 #ifdef __cplusplus
 }

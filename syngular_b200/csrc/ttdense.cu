@@ -542,15 +542,20 @@ extern "C" int syn_tt_dense3_pack_tf32(const float* G1, const float* G2, const f
     return ttp::tt_pack_pair(G1, packed, (cudaStream_t)stream);
 }
 
+static int tt_check_args(const float* x, const float* packed, const float* y) {
+    using namespace syn;
+    SYN_REQUIRE(x && packed && y, "syn_tt_dense3_tf32: null argument");
+    SYN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)packed) | ((uintptr_t)y)) & 15) == 0, "syn_tt_dense3_tf32: x, weights and y must be 16-byte aligned");
+    return 0;
+}
+
 extern "C" int syn_tt_dense3_tf32(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream) {
-    // SYN_TT_PAIR=1: the CTA-pair kernel (tcgen05 cta_group::2, csrc/ttdense_pair.cu); default: the single-CTA kernel
-    static int pair_mode = -1;
-    if (pair_mode < 0) { const char* e = getenv("SYN_TT_PAIR"); pair_mode = (e && e[0] == '1') ? 1 : 0; }
-    if (pair_mode == 1 && batch > 0) {
-        using namespace syn;
-        SYN_REQUIRE(x && packed && y, "syn_tt_dense3_tf32: null argument");
-        SYN_REQUIRE(((((uintptr_t)x) | ((uintptr_t)packed) | ((uintptr_t)y)) & 15) == 0, "syn_tt_dense3_tf32: x, weights and y must be 16-byte aligned");
-        return syn::ttp::tt_dense3_tf32_pair(x, packed, bias, y, batch, relu, (cudaStream_t)stream);
-    }
     return syn::tt::tt_dense3_tf32(x, packed, bias, y, batch, relu, (cudaStream_t)stream);
+}
+
+// the same layer on CTA pairs (tcgen05 cta_group::2, csrc/ttdense_pair.cu): same arguments, same results to rounding order
+extern "C" int syn_tt_dense3_tf32_pair(const float* x, const float* packed, const float* bias, float* y, int batch, int relu, void* stream) {
+    if (batch <= 0) return 0;
+    if (int rc = tt_check_args(x, packed, y)) return rc;
+    return syn::ttp::tt_dense3_tf32_pair(x, packed, bias, y, batch, relu, (cudaStream_t)stream);
 }

@@ -25,7 +25,7 @@ namespace syn {
 namespace ttp {
 
 constexpr int GROUPS = 2;                                       // epilogue groups of four warps (per CTA)
-constexpr int THREADS = 64 + 128 * GROUPS;
+constexpr int THREADS = 64 + 128 * GROUPS;                      // TMA + step 1, steps 2 / 3, the epilogue groups
 constexpr int UNITS = 8;                                        // ring of 8 KB operand units: a T1 chunk takes one, a T2 chunk an aligned pair
 constexpr int NB1 = 4;                                          // step-1 accumulator buffers
 constexpr uint32_t UNIT_BYTES = 8192;
@@ -45,8 +45,11 @@ static_assert(TM_D3 + 16 <= TM_COLS, "TMEM columns");
 static_assert(16 % UNITS == 0 && (16 / UNITS) % 2 == 0 && UNITS % 2 == 0, "unit ring: every unit is used an even number of times by each phase of a sample");
 static_assert(16 % NB1 == 0 && (16 / NB1) % 2 == 0, "D1 ring");
 
-enum Bar { W_FULL = 0, X_FULL, X_PEER, X_EMPTY, D1_FULL0, D1_EMPTY0 = D1_FULL0 + NB1, U_FULL0 = D1_EMPTY0 + NB1, U_EMPTY0 = U_FULL0 + UNITS,
-           D2_FULL = U_EMPTY0 + UNITS, D2_EMPTY, D3_FULL, D3_EMPTY, NUM_BARS };
+enum Bar { W_FULL = 0, X_FULL, X_PEER, X_EMPTY, D1_FULL0, D1_EMPTY0 = D1_FULL0 + NB1, 
+           // the unit ring has separate barriers for its T1 uses (uses 0 / 1 of a sample: re-layout 1 -> step 2) and its T2 uses (uses 2 / 3:
+           // re-layout 2 -> step 3), so that each issuing warp sees the phases of its own barriers strictly in order
+           U1_FULL0 = D1_EMPTY0 + NB1, U2_FULL0 = U1_FULL0 + UNITS, U1_EMPTY0 = U2_FULL0 + UNITS, U2_EMPTY0 = U1_EMPTY0 + UNITS,
+           D2_FULL = U2_EMPTY0 + UNITS, D2_EMPTY, D3_FULL, D3_EMPTY, NUM_BARS };
 static_assert(NUM_BARS * 8 + 8 <= 512, "barrier area");
 
 __host__ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t kbyte) {
@@ -71,21 +74,24 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (release at cluster scope)
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics, the form CUTLASS's
+// ClusterBarrier::arrive(cta_id) uses: an explicit .release.cluster compiled to MEMBAR.ALL.GPU (+ CCTL.IVALL behind every .acquire.cluster wait)
+// and cost ~1000 cycles per hand-over (measured with the SYN_TT_DEBUG timeline).  Nothing the waiter consumes travels through generic
+// memory: the operands go writer -> fence.proxy.async -> tensor core, the accumulators through tcgen05 fences.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // ONE arrival per warp on the leader's barrier: the warp's lanes have finished (and fenced) their part, __syncwarp orders their accesses
-// before lane 0's cluster-scope release -- 8 arrivals per hand-over instead of 256, and only 4 of them cross the cluster network
+// before lane 0's arrival -- 8 arrivals per hand-over instead of 256, and only 4 of them cross the cluster network
 __device__ __forceinline__ void warp_arrive_leader(uint64_t* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(bar, 0);
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope: remote arrivals
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {      // barriers that receive remote arrivals
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
@@ -152,6 +158,23 @@ __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+#ifdef SYN_TT_DEBUG
+// timeline trace of the first pair (compile with -DSYN_TT_DEBUG): every mark appends (value, clock) to [cta][warp][PT_TRACE_LEN][2]
+__device__ uint32_t* g_ttp_dbg = nullptr;
+constexpr int PT_TRACE_LEN = 4096;
+#define PT_MARK(tag_, j_, c_)                                                                                        \
+    do {                                                                                                             \
+        if (g_ttp_dbg && blockIdx.x < 2 && (threadIdx.x & 31) == 0 && pt_cnt_ < PT_TRACE_LEN) {                      \
+            uint32_t* w_ = g_ttp_dbg + (((size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * PT_TRACE_LEN + pt_cnt_) * 2; \
+            w_[0] = ((uint32_t)(tag_) << 12) + ((uint32_t)(j_) & 15u) * 256u + (uint32_t)(c_);                        \
+            w_[1] = (uint32_t)clock64();                                                                             \
+            ++pt_cnt_;                                                                                               \
+        }                                                                                                            \
+    } while (0)
+#else
+#define PT_MARK(tag_, j_, c_) do { } while (0)
+#endif
+
 // the pair's extra piece of the weight image: B3 halves -- [r][atom a][row = o1l (8)][kk = (b1 & 1)*16 + i1], b1 = 2a + (kk >> 4) = G1[i1, 8r + o1l, b1]
 __global__ void __launch_bounds__(256) tt_pack_pair_kernel(const float* __restrict__ G1, float* __restrict__ img) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 4096; e += gridDim.x * blockDim.x) {
@@ -172,6 +195,9 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef SYN_TT_DEBUG
+    uint32_t pt_cnt_ = 0;
+#endif
     const uint32_t rank = cluster_rank();                                    // 0 = leader: issues every MMA; r owns o3-half r, supplies o2-half r
     const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
     const int my_samples = pair < batch ? (batch - pair + pairs - 1) / pairs : 0;
@@ -186,8 +212,10 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
             mbar_init(&bars[D1_EMPTY0 + b], 8);                              // one arrival per epilogue warp of the group, both CTAs
         }
         for (int u = 0; u < UNITS; u++) {
-            mbar_init(&bars[U_FULL0 + u], 8);
-            mbar_init(&bars[U_EMPTY0 + u], 1);
+            mbar_init(&bars[U1_FULL0 + u], 8);
+            mbar_init(&bars[U2_FULL0 + u], 8);
+            mbar_init(&bars[U1_EMPTY0 + u], 1);
+            mbar_init(&bars[U2_EMPTY0 + u], 1);
         }
         mbar_init(&bars[D2_FULL], 1);
         mbar_init(&bars[D2_EMPTY], 8 * GROUPS);
@@ -233,11 +261,14 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
                 __syncwarp();
                 continue;
             }
+            PT_MARK(0x10, j, 0);
             bwait(bars, X_PEER, (uint32_t)(j & 1));
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const uint32_t b = c % NB1, use = c / NB1;
+                PT_MARK(0x11, j, c);
                 bwait(bars, D1_EMPTY0 + b, (use & 1u) ^ 1u);
+                PT_MARK(0x12, j, c);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t xd = x_desc + (uint64_t)(c * 32);         // chunk c: 8 rows x 64 B = 512 B
@@ -247,10 +278,11 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
                     if (c == 15) umma2_commit(&bars[X_EMPTY]);
                 }
                 __syncwarp();
+                PT_MARK(0x13, j, c);
             }
         }
     } else if (warp == 1) {
-        // ===== step-2 / step-3 issuer (leader only) ===========================================================================================
+        // ===== step-2 / step-3 issuer (leader only; a separate step-3 warp measured slower: 7.24 vs 6.65 ms) ===========================================================================================
         if (rank == 0) {
             constexpr uint32_t ID_S2 = idesc_tf32(256, 256), ID_S3 = idesc_tf32(256, 16);
             const uint64_t d64 = smem_desc(0, 512, LAYOUT_SW64), d128 = smem_desc(0, 1024, LAYOUT_SW128);
@@ -260,8 +292,11 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
 #pragma unroll
                 for (int cc = 0; cc < 16; cc++) {
                     const uint32_t unit = cc % UNITS, par = (cc / UNITS) & 1u;                 // this unit's use 0 / 1 of the sample
-                    bwait(bars, U_FULL0 + unit, par);
+                    PT_MARK(0x20, j, cc);
+                    bwait(bars, U1_FULL0 + unit, par);
+                    PT_MARK(0x21, j, cc);
                     if (cc == 0) bwait(bars, D2_EMPTY, (uint32_t)(j & 1) ^ 1u);
+                    PT_MARK(0x22, j, cc);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = unit64_desc + (uint64_t)(unit * (UNIT_BYTES >> 4));
@@ -269,19 +304,23 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
 #pragma unroll
                         for (int k = 0; k < 2; k++)
                             umma2_tf32(tmem + TM_D2, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), ID_S2, (cc > 0 || k > 0) ? 1u : 0u);
-                        umma2_commit(&bars[U_EMPTY0 + unit]);
+                        umma2_commit(&bars[U1_EMPTY0 + unit]);
                         if (cc == 15) umma2_commit(&bars[D2_FULL]);
                     }
                     __syncwarp();
+                    PT_MARK(0x23, j, cc);
                 }
 #pragma unroll
                 for (int p = 0; p < 8; p++) {
                     // a T2 chunk occupies the aligned unit pair (unit, unit + 1); BOTH units carry the full / empty protocol, so that every
                     // unit sees four uses per sample (two T1 chunks, two T2 chunks) and the next T1 chunk in either of them waits for this MMA
-                    const uint32_t unit = (2 * p) % UNITS, par = ((2 + p / (UNITS / 2)) & 1u);   // uses 2 / 3 of the sample
-                    bwait(bars, U_FULL0 + unit, par);
-                    bwait(bars, U_FULL0 + unit + 1, par);
+                    const uint32_t unit = (2 * p) % UNITS, par = (p / (UNITS / 2)) & 1u;         // uses 2 / 3 of the sample
+                    PT_MARK(0x30, j, p);
+                    bwait(bars, U2_FULL0 + unit, par);
+                    bwait(bars, U2_FULL0 + unit + 1, par);
+                    PT_MARK(0x31, j, p);
                     if (p == 0) bwait(bars, D3_EMPTY, (uint32_t)(j & 1) ^ 1u);
+                    PT_MARK(0x32, j, p);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = unit128_desc + (uint64_t)(unit * (UNIT_BYTES >> 4));
@@ -289,11 +328,12 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             umma2_tf32(tmem + TM_D3, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), ID_S3, (p > 0 || k > 0) ? 1u : 0u);
-                        umma2_commit(&bars[U_EMPTY0 + unit]);
-                        umma2_commit(&bars[U_EMPTY0 + unit + 1]);
+                        umma2_commit(&bars[U2_EMPTY0 + unit]);
+                        umma2_commit(&bars[U2_EMPTY0 + unit + 1]);
                         if (p == 7) umma2_commit(&bars[D3_FULL]);
                     }
                     __syncwarp();
+                    PT_MARK(0x33, j, p);
                 }
             }
         }
@@ -315,14 +355,18 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
                 if ((16 * j + c) % GROUPS != grp) continue;
                 const uint32_t b = c % NB1, use = c / NB1;
                 const uint32_t unit = c % UNITS, par = (c / UNITS) & 1u;
+                PT_MARK(0x40, j, c);
                 lwait(bars, D1_FULL0 + b, use & 1u);
+                PT_MARK(0x41, j, c);
                 tc_fence_after();
                 uint32_t r0[16];
                 tmem_ld16(tq + TM_D1 + b * 16, r0);
                 tmem_ld_wait();
                 tc_fence_before();
                 warp_arrive_leader(&bars[D1_EMPTY0 + b]);
-                lwait(bars, U_EMPTY0 + unit, par ^ 1u);
+                PT_MARK(0x42, j, c);
+                lwait(bars, (par == 0 ? U2_EMPTY0 : U1_EMPTY0) + unit, par ^ 1u);    // use 0 follows use 3 of the previous sample, use 1 follows use 0
+                PT_MARK(0x43, j, c);
                 uint8_t* dst = smem + OFF_UNIT + unit * UNIT_BYTES + r1_base;
 #pragma unroll
                 for (int i1 = 0; i1 < 16; i1++) {
@@ -330,9 +374,12 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
                     *reinterpret_cast<uint32_t*>(dst + off) = r0[i1];
                 }
                 fence_async_smem();
-                warp_arrive_leader(&bars[U_FULL0 + unit]);
+                warp_arrive_leader(&bars[U1_FULL0 + unit]);
+                PT_MARK(0x44, j, c);
             }
+            PT_MARK(0x50, j, 0);
             lwait(bars, D2_FULL, (uint32_t)(j & 1));
+            PT_MARK(0x51, j, 0);
             tc_fence_after();
             int last_p = -1;
             for (int p = 0; p < 8; p++)
@@ -340,14 +387,16 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
 #pragma unroll
             for (int p = 0; p < 8; p++) {
                 if ((8 * j + p) % GROUPS != grp) continue;
-                const uint32_t unit = (2 * p) % UNITS, par = ((2 + p / (UNITS / 2)) & 1u);
+                const uint32_t unit = (2 * p) % UNITS, par = (p / (UNITS / 2)) & 1u;
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tq + TM_D2 + p * 16, r0);                            // osrc = 0: columns (2p + b1l)*8 + o2l
                 tmem_ld16(tq + TM_D2 + 128 + p * 16, r1);                      // osrc = 1
                 tmem_ld_wait();
                 if (p == last_p) { tc_fence_before(); warp_arrive_leader(&bars[D2_EMPTY]); }
-                lwait(bars, U_EMPTY0 + unit, par ^ 1u);
-                lwait(bars, U_EMPTY0 + unit + 1, par ^ 1u);
+                PT_MARK(0x52, j, p);
+                lwait(bars, (par == 0 ? U1_EMPTY0 : U2_EMPTY0) + unit, par ^ 1u);        // use 2 follows use 1 (step 2), use 3 follows use 2 (step 3)
+                lwait(bars, (par == 0 ? U1_EMPTY0 : U2_EMPTY0) + unit + 1, par ^ 1u);
+                PT_MARK(0x53, j, p);
                 uint8_t* dst = smem + OFF_UNIT + unit * UNIT_BYTES;
 #pragma unroll
                 for (int cidx = 0; cidx < 16; cidx++) {
@@ -358,12 +407,15 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
                     *reinterpret_cast<uint32_t*>(dst + sw128_off(row0 + 64, kbyte)) = r1[cidx];
                 }
                 fence_async_smem();
-                warp_arrive_leader(&bars[U_FULL0 + unit]);
-                warp_arrive_leader(&bars[U_FULL0 + unit + 1]);
+                warp_arrive_leader(&bars[U2_FULL0 + unit]);
+                warp_arrive_leader(&bars[U2_FULL0 + unit + 1]);
+                PT_MARK(0x54, j, p);
             }
             // output: D3 lane m' = o2*8 + hb*4 + q' (o3 = 8 rank + 2q' + hb), column o1; the groups take the samples' outputs in turn
             if (j % GROUPS != grp) continue;
+            PT_MARK(0x60, j, 0);
             lwait(bars, D3_FULL, (uint32_t)(j & 1));
+            PT_MARK(0x61, j, 0);
             tc_fence_after();
             uint32_t acc[16];
             tmem_ld16(tq + TM_D3, acc);
@@ -380,6 +432,7 @@ tt_dense3_tf32_pair_kernel(const __grid_constant__ CUtensorMap xmap, const float
                 if (relu) v = fmaxf(v, 0.0f);
                 yo[o1 * 256] = v;
             }
+            PT_MARK(0x62, j, 0);
         }
     }
     tc_fence_before();
@@ -432,3 +485,9 @@ int tt_pack_pair(const float* G1, float* img, cudaStream_t st) {
 
 }  // namespace ttp
 }  // namespace syn
+
+#ifdef SYN_TT_DEBUG
+extern "C" int syn_ttp_debug_buffer(uint32_t* device_ptr) {
+    return cudaMemcpyToSymbol(syn::ttp::g_ttp_dbg, &device_ptr, sizeof(uint32_t*)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -446,7 +446,7 @@ def tt_dense3_pack(G1, G2, G3):
     return packed
 
 
-def tt_dense3_tf32(x, packed, bias=None, relu=True, out=None):
+def tt_dense3_tf32(x, packed, bias=None, relu=True, out=None, pair=False):
     """y = act(TT-matvec(x) + bias) for a (batch, 4096) float32 CUDA input, on tcgen05.mma.kind::tf32 (one fused launch)."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[1] == 4096):
         raise SynError("tt_dense3_tf32: expected a contiguous CUDA float32 (batch, 4096) input")
@@ -455,8 +455,9 @@ def tt_dense3_tf32(x, packed, bias=None, relu=True, out=None):
     assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape
     if bias is not None:
         assert bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == 4096
-    check(lib.syn_tt_dense3_tf32(ptr(x), ptr(packed), ptr(bias) if bias is not None else None, ptr(out), _i32(x.shape[0]), _i32(1 if relu else 0),
-                                 stream_ptr()), "syn_tt_dense3_tf32")
+    fn = lib.syn_tt_dense3_tf32_pair if pair else lib.syn_tt_dense3_tf32            # pair: the cta_group::2 variant (checked alternative)
+    check(fn(ptr(x), ptr(packed), ptr(bias) if bias is not None else None, ptr(out), _i32(x.shape[0]), _i32(1 if relu else 0), stream_ptr()),
+          "syn_tt_dense3_tf32")
     return out
 
 

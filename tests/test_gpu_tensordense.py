@@ -72,6 +72,35 @@ def test_tensordense_tf32_is_exact_on_exactly_representable_data():
     assert np.array_equal(layer(x).cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("batch", [1, 3, 75, 1111])
+def test_tensordense_tf32_cta_pair_variant_matches_restatement_and_the_default_kernel(batch):
+    """syn_tt_dense3_tf32_pair (tcgen05 cta_group::2; two CTAs share a sample) against the float64 restatement, and against the single-CTA
+    kernel: both accumulate the same TF32 products in FP32, in different orders."""
+    import torch
+    from syngular_b200 import ops
+    from oracle import tensordense_numpy as TD
+    rng = np.random.default_rng(100 + batch)
+    cores = [rng.normal(scale=0.05, size=s).astype(np.float32) for s in ((16, 16, 16), (16, 16, 16, 16), (16, 16, 16))]
+    bias = (0.01 * rng.normal(size=4096)).astype(np.float32)
+    x = rng.normal(size=(batch, 4096)).astype(np.float32)
+    dev = torch.device("cuda")
+    packed = ops.tt_dense3_pack(*[torch.from_numpy(c).to(dev) for c in cores])
+    xd, bd = torch.from_numpy(x).to(dev), torch.from_numpy(bias).to(dev)
+    got = ops.tt_dense3_tf32(xd, packed, bd, relu=True, pair=True).cpu().numpy()
+    one = ops.tt_dense3_tf32(xd, packed, bd, relu=True).cpu().numpy()
+    ref = TD.forward(x.astype(np.float64), [c.astype(np.float64) for c in cores], bias.astype(np.float64).reshape(16, 16, 16), "relu")
+    assert np.max(np.abs(got - ref)) < TF32_TOL * np.max(np.abs(ref))
+    assert np.max(np.abs(got - one)) < 1e-5 * np.max(np.abs(ref))
+    # exactly representable data: a permutation layer must come out bit-exact
+    P1 = np.zeros((16, 16, 16), np.float32); P2 = np.zeros((16, 16, 16, 16), np.float32); P3 = np.zeros((16, 16, 16), np.float32)
+    for i in range(16):
+        P1[i, 15 - i, 3] = 1; P2[i, (i + 5) % 16, 3, 7] = 1; P3[i, 15 - i, 7] = 1
+    pk = ops.tt_dense3_pack(*[torch.from_numpy(c).to(dev) for c in (P1, P2, P3)])
+    xi = (np.arange(batch * 4096) % 1021).astype(np.float32).reshape(batch, 4096)
+    want = np.roll(xi.reshape(batch, 16, 16, 16)[:, ::-1, :, ::-1], 5, axis=2).reshape(batch, 4096)
+    assert np.array_equal(ops.tt_dense3_tf32(torch.from_numpy(xi).to(dev), pk, None, relu=False, pair=True).cpu().numpy(), want)
+
+
 def test_tensordense_tf32_rejects_uncovered_shapes():
     from syngular.layers import TensorDense
     with pytest.raises(NotImplementedError):
