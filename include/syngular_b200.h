@@ -157,6 +157,14 @@ int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
                                     double* info, void* stream);
 
+/* The projection solver for a BATCH of small bond problems (csrc/purify_batched.cu): one CTA per problem, the iterate and the basis stay in
+ * shared memory, products in registers, two CTA barriers per step; a persistent grid walks the batch.  A: batch x n x n contiguous symmetric
+ * PSD matrices (16-byte aligned), U: batch x n x ne, info: batch x 8 doubles with the meaning above.  n, ne multiples of 32,
+ * 32 <= ne < n <= 128 (syn_dominant_subspace_batched_fits).  Replaces the per-state truncation of a batch of chains
+ * (reference: a Python loop over tensor/matrix_product_state.py:432-468). */
+int syn_dominant_subspace_batched_fits(int n, int ne);
+int syn_dominant_subspace_batched_f64(const double* A, int batch, int n, int ne, int sp2_max, int ns_max, double* U, double* info, void* stream);
+
 /* out[i] = sum_p parts[p * part_stride + i], i < count: the reduction after a split-K syn_gemm_f64 (partials as the batch index). */
 int syn_sum_parts_f64(const double* parts, int64_t part_stride, int nparts, double* out, int64_t count, void* stream);
 

@@ -11,6 +11,20 @@ import torch
 from . import ops
 
 F64 = torch.float64
+PROJECTION_BATCHED = True                      # bond problems that fit csrc/purify_batched.cu use it (False: Jacobi only)
+PROJECTION_STATS = {"taken": 0, "fallback": 0}
+
+
+def _rejected(h, ne, rank_gap):
+    """Indices of the batch members whose projection result is not accepted: the per-member form of _sweeps._projection_verdict on the
+    (B, 8) host copy of the info doubles."""
+    from syngular.tensor import _sweeps as sw
+    tr, f2, dev, idem = h[:, 0], h[:, 1], h[:, 4], h[:, 6]
+    lift = (h[:, 7] // 1000000).astype(np.int64)
+    with np.errstate(invalid="ignore"):
+        ok = ((np.abs(tr - ne) < 1e-9 * ne) & (np.abs(f2 - ne) < 1e-9 * ne) & (np.abs(idem) < 1e-11 * ne) & (dev < 1e-12)
+              & np.isfinite(h).all(axis=1) & (lift <= (sw.PURIFY_MAX_LIFT_RANK_GAP if rank_gap else sw.PURIFY_MAX_LIFT)))
+    return np.nonzero(~ok)[0]
 
 
 class BatchedMatrixProductState:
@@ -113,6 +127,14 @@ class BatchedMatrixProductState:
             outs = [[c] for c in part] if outs is None else [o + [c] for o, c in zip(outs, part)]
         return BatchedMatrixProductState([torch.cat(o, dim=0) if len(o) > 1 else o[0] for o in outs])
 
+    @staticmethod
+    def _jacobi_basis(A, chi, keep):
+        """(B, rows, keep) orthonormal bases of the dominant eigenspaces of the Gram matrices A by one-sided Jacobi on the rows of the
+        shifted Cholesky factor (fewer sweeps than on A itself, see csrc/chol.cu)."""
+        Bf, shift = ops.chol_upper(A)
+        Ut, sigma, info, winfo = ops.jacobi_solve(Bf, chi, rank_tol=0.0, sqrt_mode=2, shift=shift, null_rel=0.0)
+        return ops.copy_strided(Ut[:, :keep, :].transpose(1, 2))
+
     def _apply_round_svd_chunk(self, W, chi):
         B, n = self.batch, self.sites_number
         dev = self.sites[0].device
@@ -176,13 +198,23 @@ class BatchedMatrixProductState:
             ops.gemm(M, E[k + 1], ME, M=rows, N=D, K=D, a_m=D, a_k=1, b_k=D, b_n=1, c_m=D, c_n=(1, r, b),
                      batch=B, a_b=rows * D, b_b=D * D, c_b=rows * D)
             A = ops.matmul(ME, M.transpose(1, 2))
-            # Jacobi on the rows of the shifted Cholesky factor of A (fewer sweeps than on A itself, see csrc/chol.cu)
-            Bf, shift = ops.chol_upper(A)
-            Ut, sigma, info, winfo = ops.jacobi_solve(Bf, chi, rank_tol=0.0, sqrt_mode=2, shift=shift, null_rel=0.0)
-            core = ops.copy_strided(Ut[:, :keep, :].transpose(1, 2))   # (B, rows, keep)
-            out.append(core.reshape(B, s, o, keep))
+            U = None
+            if PROJECTION_BATCHED and ops.dominant_subspace_batched_fits(rows, keep):
+                # spectral projection, one CTA per state (csrc/purify_batched.cu); the verdict of every member is read once per bond and
+                # the members without a usable gap at the cut (or with the cut too deep in the spectrum, see _sweeps.PURIFY_MAX_LIFT) are
+                # redone by the Jacobi route
+                U, info = ops.dominant_subspace_batched(A, keep)
+                bad = _rejected(info.cpu().numpy(), keep, keep >= min(D, right_dim))
+                PROJECTION_STATS["taken"] += B - len(bad)
+                PROJECTION_STATS["fallback"] += len(bad)
+                if len(bad):
+                    idx = torch.as_tensor(bad, device=dev)
+                    U[idx] = self._jacobi_basis(A[idx].contiguous(), chi, keep)
+            else:
+                U = self._jacobi_basis(A, chi, keep)
+            out.append(U.reshape(B, s, o, keep))
             Tn = empty(B, keep, r, b)
-            ops.gemm(Ut, M, Tn, M=keep, N=D, K=rows, a_m=rows, a_k=1, b_k=D, b_n=1, c_m=r * b, c_n=(1, b, r),
-                     batch=B, a_b=rows * rows, b_b=rows * D, c_b=keep * r * b)
+            ops.gemm(U, M, Tn, M=keep, N=D, K=rows, a_m=1, a_k=keep, b_k=D, b_n=1, c_m=r * b, c_n=(1, b, r),
+                     batch=B, a_b=rows * keep, b_b=rows * D, c_b=keep * r * b)
             T = Tn
         return out

@@ -262,6 +262,23 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return U, info
 
 
+def dominant_subspace_batched_fits(n, ne):
+    return bool(lib.syn_dominant_subspace_batched_fits(_i32(int(n)), _i32(int(ne))))
+
+
+def dominant_subspace_batched(A, ne, sp2_max=90, ns_max=60):
+    """The projection solver for a batch of small problems: A (B x n x n contiguous, symmetric PSD) -> (U (B x n x ne), info (B x 8)),
+    both on the device, one launch with one CTA per problem (csrc/purify_batched.cu).  n, ne multiples of 32, ne < n <= 128."""
+    require_cuda_f64(A)
+    assert A.dim() == 3 and A.shape[1] == A.shape[2] and A.is_contiguous()
+    B, n = int(A.shape[0]), int(A.shape[1])
+    U = torch.empty((B, n, int(ne)), dtype=torch.float64, device=A.device)
+    info = torch.empty((B, 8), dtype=torch.float64, device=A.device)
+    check(lib.syn_dominant_subspace_batched_f64(ptr(A), _i32(B), _i32(n), _i32(int(ne)), _i32(int(sp2_max)), _i32(int(ns_max)), ptr(U), ptr(info),
+                                                stream_ptr()), "syn_dominant_subspace_batched_f64")
+    return U, info
+
+
 lib.syn_orthonormalize_columns_workspace_f64.restype = ctypes.c_size_t
 lib.syn_orthonormalize_columns_workspace_f64.argtypes = [_i32, _i32, _i32]
 
