@@ -21,7 +21,6 @@ namespace syn {
 void note_launch();
 
 constexpr int PB_THREADS = 256;
-constexpr int PB_MT = 8, PB_NT = 4;          // warp tile in 8 x 8 DMMA tiles at n = 128
 
 struct PurifyBatchedArgs {
     const double* A;         // [batch][n][n], symmetric positive semi-definite
@@ -30,27 +29,28 @@ struct PurifyBatchedArgs {
     int batch, n, ne, sp2_max, ns_max;
 };
 
-// acc[i][j] (+)= R1 rows x R2 rows over K: element (row r, k) of operand x is Rx[r * rs + k * ks]; mt x nt of the MT x NT tiles are live
-__device__ __forceinline__ void pb_mma(double (&acc)[PB_MT][PB_NT][2], const double* __restrict__ R1, int rs1, int ks1,
-                                       const double* __restrict__ R2, int rs2, int ks2, int K, int mt, int nt) {
+// acc[i][j] = R1 rows x R2 rows over K: element (row r, k) of operand x is Rx[r * RSx + k * KSx]; everything but the pointers is a compile-time
+// constant, so the fragment addresses fold into the LDS immediates and the k loop unrolls
+template <int MT, int NT, int RS1, int KS1, int RS2, int KS2, int K>
+__device__ __forceinline__ void pb_mma(double (&acc)[MT][NT][2], const double* __restrict__ R1, const double* __restrict__ R2) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < PB_MT; i++)
+    for (int i = 0; i < MT; i++)
 #pragma unroll
-        for (int j = 0; j < PB_NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const double* p1 = R1 + g * rs1 + t * ks1;
-    const double* p2 = R2 + g * rs2 + t * ks2;
+        for (int j = 0; j < NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* p1 = R1 + g * RS1 + t * KS1;
+    const double* p2 = R2 + g * RS2 + t * KS2;
+#pragma unroll 4
     for (int k = 0; k < K; k += 4) {
-        double af[PB_MT], bf[PB_NT];
+        double af[MT], bf[NT];
 #pragma unroll
-        for (int i = 0; i < PB_MT; i++) af[i] = i < mt ? p1[8 * i * rs1 + k * ks1] : 0.0;
+        for (int i = 0; i < MT; i++) af[i] = p1[8 * i * RS1 + k * KS1];
 #pragma unroll
-        for (int j = 0; j < PB_NT; j++) bf[j] = j < nt ? p2[8 * j * rs2 + k * ks2] : 0.0;
+        for (int j = 0; j < NT; j++) bf[j] = p2[8 * j * RS2 + k * KS2];
 #pragma unroll
-        for (int i = 0; i < PB_MT; i++)
+        for (int i = 0; i < MT; i++)
 #pragma unroll
-            for (int j = 0; j < PB_NT; j++)
-                if (i < mt && j < nt) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            for (int j = 0; j < NT; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
 }
 
@@ -80,17 +80,20 @@ __device__ __forceinline__ double pb_max(double v, double* red) {
     return v;
 }
 
+// n = 32 NB, ne = 32 EB
+template <int NB, int EB>
 __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const PurifyBatchedArgs a) {
     extern __shared__ __align__(16) double pb_smem[];
-    const int n = a.n, ne = a.ne, LD = n + 4, LDG = ne + 4;
+    constexpr int n = 32 * NB, ne = 32 * EB, LD = n + 4, LDG = ne + 4;
     double* X = pb_smem;
     double* G = X + n * LD;
     double* red = G + ne * LDG;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp >> 2, wc = warp & 3;
     // warp tiles: X X^T and U G take rows [i0, i0 + n/2); X X^T columns [j0, j0 + n/4); G = U^T U is (ne/2) x (ne/4) per warp
-    const int i0 = wr * (n / 2), j0 = wc * (n / 4), mt = n / 16, nt = n / 32;
-    const int gi0 = wr * (ne / 2), gj0 = wc * (ne / 4), gmt = ne / 16, gnt = ne / 32;
+    constexpr int mt = 2 * NB, nt = NB, gmt = 2 * EB, gnt = EB;
+    const int i0 = wr * (n / 2), j0 = wc * (n / 4);
+    const int gi0 = wr * (ne / 2), gj0 = wc * (ne / 4);
     const double dne = (double)ne;
 
     for (int p = blockIdx.x; p < a.batch; p += gridDim.x) {
@@ -124,15 +127,14 @@ __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const Pur
             }
             const bool square = extra == 1 ? true : (extra == 2 ? false : fabs(f0 - dne) < fabs(2.0 * tr0 - f0 - dne));
             if (lifting && !square) ++lift; else lifting = false;
-            double acc[PB_MT][PB_NT][2];
-            pb_mma(acc, X + i0 * LD, LD, 1, X + j0 * LD, LD, 1, n, mt, nt);
+            double acc[mt][nt][2];
+            pb_mma<mt, nt, LD, 1, LD, 1, n>(acc, X + i0 * LD, X + j0 * LD);
             __syncthreads();                                   // every warp has read the old iterate
             double tr = 0.0, f2 = 0.0;
 #pragma unroll
-            for (int i = 0; i < PB_MT; i++)
+            for (int i = 0; i < mt; i++)
 #pragma unroll
-                for (int j = 0; j < PB_NT; j++)
-                    if (i < mt && j < nt) {
+                for (int j = 0; j < nt; j++) {
                         const int r = i0 + 8 * i + g, c = j0 + 8 * j + 2 * t;
                         double2* px = reinterpret_cast<double2*>(X + r * LD + c);
                         double2 x = *px;
@@ -162,19 +164,18 @@ __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const Pur
         double dev0 = 0.0;
         bool last_steep = true;
         for (;; ++ns) {
-            double acc[PB_MT][PB_NT][2];
-            pb_mma(acc, X + gi0, 1, LD, X + gj0, 1, LD, n, gmt, gnt);        // G = U^T U: both operands read down the columns of U
+            double gacc[gmt][gnt][2];
+            pb_mma<gmt, gnt, 1, LD, 1, LD, n>(gacc, X + gi0, X + gj0);         // G = U^T U: both operands read down the columns of U
             double trg = 0.0, dmax = 0.0;
 #pragma unroll
-            for (int i = 0; i < PB_MT; i++)
+            for (int i = 0; i < gmt; i++)
 #pragma unroll
-                for (int j = 0; j < PB_NT; j++)
-                    if (i < gmt && j < gnt) {
+                for (int j = 0; j < gnt; j++) {
                         const int r = gi0 + 8 * i + g, c = gj0 + 8 * j + 2 * t;
-                        *reinterpret_cast<double2*>(G + r * LDG + c) = make_double2(acc[i][j][0], acc[i][j][1]);
-                        if (r == c) trg += acc[i][j][0];
-                        if (r == c + 1) trg += acc[i][j][1];
-                        dmax = fmax(dmax, fmax(fabs(acc[i][j][0] - (r == c ? 1.0 : 0.0)), fabs(acc[i][j][1] - (r == c + 1 ? 1.0 : 0.0))));
+                        *reinterpret_cast<double2*>(G + r * LDG + c) = make_double2(gacc[i][j][0], gacc[i][j][1]);
+                        if (r == c) trg += gacc[i][j][0];
+                        if (r == c + 1) trg += gacc[i][j][1];
+                        dmax = fmax(dmax, fmax(fabs(gacc[i][j][0] - (r == c ? 1.0 : 0.0)), fabs(gacc[i][j][1] - (r == c + 1 ? 1.0 : 0.0))));
                     }
             double unused2 = 0.0;
             pb_sum2(trg, unused2, red);                        // (its barriers publish G)
@@ -183,13 +184,13 @@ __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const Pur
             if (ns >= a.ns_max) break;
             const bool steep = ns < 8 && dev0 > 0.5;
             const double ca = steep ? 2.0 : 1.5, cb = steep ? -1.0 : -0.5;
-            pb_mma(acc, X + i0 * LD, LD, 1, G + gj0 * LDG, LDG, 1, ne, mt, gnt);   // U G (G symmetric: its rows are its columns)
+            double acc[mt][gnt][2];
+            pb_mma<mt, gnt, LD, 1, LDG, 1, ne>(acc, X + i0 * LD, G + gj0 * LDG);   // U G (G symmetric: its rows are its columns)
             __syncthreads();                                   // every warp has read the old U
 #pragma unroll
-            for (int i = 0; i < PB_MT; i++)
+            for (int i = 0; i < mt; i++)
 #pragma unroll
-                for (int j = 0; j < PB_NT; j++)
-                    if (i < mt && j < gnt) {
+                for (int j = 0; j < gnt; j++) {
                         const int r = i0 + 8 * i + g, c = gj0 + 8 * j + 2 * t;
                         double2* pu = reinterpret_cast<double2*>(X + r * LD + c);
                         double2 u = *pu;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const Pur
 static size_t pb_smem_bytes(int n, int ne) { return ((size_t)n * (n + 4) + (size_t)ne * (ne + 4) + 16) * sizeof(double); }
 
 static bool purify_batched_fits(int n, int ne) {
-    return n % 32 == 0 && ne % 32 == 0 && n >= 32 && n <= 128 && ne >= 32 && ne < n && pb_smem_bytes(n, ne) <= 227 * 1024;
+    return n % 32 == 0 && ne % 32 == 0 && n >= 64 && n <= 128 && ne >= 32 && ne < n && pb_smem_bytes(n, ne) <= 227 * 1024;
 }
 
 }  // namespace syn
@@ -247,11 +248,21 @@ extern "C" int syn_dominant_subspace_batched_f64(const double* A, int batch, int
     SYN_REQUIRE(purify_batched_fits(n, ne), "syn_dominant_subspace_batched_f64: n, ne multiples of 32 with 32 <= ne < n <= 128 (n=%d ne=%d)", n, ne);
     SYN_REQUIRE(sp2_max >= 1 && sp2_max <= 400 && ns_max >= 0 && ns_max <= 400, "syn_dominant_subspace_batched_f64: bad iteration limits");
     SYN_REQUIRE((((uintptr_t)A) & 15) == 0, "syn_dominant_subspace_batched_f64: A must be 16-byte aligned");
-    static PerDevice configured;
-    const int dev = current_device();
-    if (!configured.get(dev)) {
-        SYN_CUDA(cudaFuncSetAttribute(purify_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured.set(dev);
+    void (*kern)(const PurifyBatchedArgs) = nullptr;
+    switch ((n / 32) * 10 + ne / 32) {
+        case 21: kern = purify_batched_kernel<2, 1>; break;
+        case 31: kern = purify_batched_kernel<3, 1>; break;
+        case 32: kern = purify_batched_kernel<3, 2>; break;
+        case 41: kern = purify_batched_kernel<4, 1>; break;
+        case 42: kern = purify_batched_kernel<4, 2>; break;
+        case 43: kern = purify_batched_kernel<4, 3>; break;
+    }
+    SYN_REQUIRE(kern != nullptr, "syn_dominant_subspace_batched_f64: no kernel for n=%d ne=%d", n, ne);
+    static PerDevice configured[6];
+    const int dev = current_device(), slot = (n / 32 - 2) * (n / 32 - 1) / 2 + ne / 32 - 1;
+    if (!configured[slot].get(dev)) {
+        SYN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured[slot].set(dev);
     }
     PurifyBatchedArgs a;
     a.A = A; a.U = U; a.info = info;
@@ -260,7 +271,7 @@ extern "C" int syn_dominant_subspace_batched_f64(const double* A, int batch, int
     // balanced waves: ceil(batch / waves) CTAs for the smallest number of waves that covers the batch
     const int waves = (batch + sms - 1) / sms;
     const int grid = (batch + waves - 1) / waves;
-    purify_batched_kernel<<<grid, PB_THREADS, pb_smem_bytes(n, ne), (cudaStream_t)stream>>>(a);
+    kern<<<grid, PB_THREADS, pb_smem_bytes(n, ne), (cudaStream_t)stream>>>(a);
     note_launch();
     return launch_status("purify_batched_kernel");
 }

@@ -26,3 +26,5 @@ else:
     A.apply_round_svd(W, 64, chunk=256)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+from syngular_b200 import batched
+print("projection: taken %d, fallback %d" % (batched.PROJECTION_STATS["taken"], batched.PROJECTION_STATS["fallback"]))
