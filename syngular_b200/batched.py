@@ -154,11 +154,13 @@ class BatchedMatrixProductState:
             ops.gemm(X, En, P1, M=a * i, N=r * D, K=b, a_m=b, a_k=1, b_k=r * D, b_n=1, c_m=r * D, c_n=1,
                      batch=B, a_b=a * i * b, b_b=D * D, c_b=a * i * r * D)
             P2 = empty(B, a, l, o, D)
-            ops.gemm(Wk, P1, P2, M=l * o, N=D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=1, c_m=D, c_n=1,
-                     batch=B * a, a_b=0, b_b=i * r * D, c_b=l * o * D)
+            # the shared MPO core against ALL (state, a) slices at once: the slice index is the outer level of the column index, so this is
+            # one (l o) x (B a D) x (i r) product instead of B a products with 8 x 8 operands
+            ops.gemm(Wk, P1, P2, M=l * o, N=B * a * D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=(i * r * D, 1, D),
+                     c_m=D, c_n=(l * o * D, 1, D))
             Z = empty(B, a * l, l, i, b)
-            ops.gemm(P2, Wk, Z, M=b, N=l * i, K=o * r, a_m=1, a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i), c_m=1, c_n=b,
-                     batch=B * a * l, a_b=o * D, b_b=0, c_b=l * i * b)
+            ops.gemm(P2, Wk, Z, M=B * a * l * b, N=l * i, K=o * r, a_m=(o * D, 1, b), a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i),
+                     c_m=(l * i * b, 1, b), c_n=b)                    # likewise: rows (state, a, l', b')
             Ek = empty(B, a * l, l * a)
             ops.gemm(Z, X, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
                      batch=B * l, a_b=(a * l * l * i * b, i * b, l), b_b=(a * i * b, 0, l), c_b=(a * l * a * l, a, l))
