@@ -781,7 +781,7 @@ def run_ours(args):
                       "c5_note": "configs[4] forward, float32 in/out on the fused tcgen05.mma.kind::tf32 kernel (%.0f TFLOP/s; `--workload c5` prints the "
                                  "full line); the FP64 DMMA-GEMM path of the same layer: %.0f samples/s" % (3.7748736e7 * 65536 / (ms_c5 * 1e-3) / 1e12, c5_f64_value),
                       "c4_apply_qr_round_states_per_s": c4_apply_qr, "c4_apply_svd_round_states_per_s": c4_apply_svd,
-                      "c4_apply_note": "configs[3](ii): shared MPO chi_W=4 applied + rounded to chi=64, batched over 256 states per rank",
+                      "c4_apply_note": "configs[3](ii): shared MPO chi_W=4 applied + rounded to chi=64, batched over 256 states per rank; SVD rounding by the batched projection kernel (one CTA per state and bond, csrc/purify_batched.cu), Jacobi for the members it rejects",
                       "qr_round_sweeps_per_s": qr_value, "qr_round_ms_per_sweep": 1e3 / (qr_value / world),
                       "qr_round_note": "reference-semantic `>>` (QR truncation, fused apply+round) on the same chain"},
         }

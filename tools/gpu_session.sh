@@ -19,6 +19,7 @@ for s in $steps; do
     sanitize) tools/sanitize.sh ${tag} ;;
     gemmncu) ncu --set full --clock-control none --import-source on -k regex:gemm_f64_persistent -s 70 -c 1 -f -o gpurun_out/${tag}_gemm_p1 python tools/profile_sweep.py svd > gpurun_out/${tag}_gemmncu.log 2>&1; tail -2 gpurun_out/${tag}_gemmncu.log ;;
     purifyncu) ncu --set full --clock-control none --import-source on -k regex:purify_fused -s 30 -c 1 -f -o gpurun_out/${tag}_purify python tools/profile_sweep.py svd > gpurun_out/${tag}_purifyncu.log 2>&1; tail -2 gpurun_out/${tag}_purifyncu.log ;;
+    purifybncu) ncu --set full --clock-control none --import-source on -k regex:purify_batched -s 3 -c 1 -f -o gpurun_out/${tag}_purify_batched python tools/purify_batched_bench.py > gpurun_out/${tag}_purifybncu.log 2>&1; tail -2 gpurun_out/${tag}_purifybncu.log ;;
     *) echo "unknown step $s" ;;
   esac
 done

@@ -1,6 +1,7 @@
 """Small invocations of every kernel that synchronises by hand (grid barriers, version words, DSMEM exchanges, mbarrier pipelines),
 for compute-sanitizer (tools/sanitize.sh): purify / orthonormalise, Jacobi (single- and multi-CTA), cluster QR, Householder QR,
-Cholesky, fused overlap, environment sandwich, strided GEMM (TMA and cp.async variants), the TF32 tcgen05 layer kernel."""
+Cholesky, fused overlap, environment sandwich, strided GEMM (TMA and cp.async variants), the TF32 tcgen05 layer kernel and its CTA-pair
+variant (cluster barriers, remote mbarrier arrivals), the batched projection kernel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,7 +10,7 @@ from syngular_b200 import ops
 from syngular.tensor import _sweeps as sw
 import bench
 
-which = sys.argv[1:] or ["gemm", "purify", "ortho", "jacobi", "qr", "chol", "overlap", "sweep", "ttdense"]
+which = sys.argv[1:] or ["gemm", "purify", "ortho", "jacobi", "qr", "chol", "overlap", "sweep", "ttdense", "ttpair", "purifyb"]
 dev = torch.device("cuda")
 rng = np.random.default_rng(0)
 
@@ -60,5 +61,16 @@ if "ttdense" in which:
     from syngular.layers import TensorDense
     layer = TensorDense((16, 16, 16), (16, 16, 16), (16, 16), seed=1, precision="tf32").build()
     layer(np.random.default_rng(1).normal(size=(5, 4096)).astype(np.float32))
+if "ttpair" in which:
+    G = [torch.from_numpy(rng.normal(scale=0.05, size=sh).astype(np.float32)).to(dev) for sh in ((16, 16, 16), (16, 16, 16, 16), (16, 16, 16))]
+    packed = ops.tt_dense3_pack(*G)
+    x = torch.randn((5, 4096), dtype=torch.float32, device=dev)
+    y1 = ops.tt_dense3_tf32(x, packed, None, relu=True, pair=True)
+    y0 = ops.tt_dense3_tf32(x, packed, None, relu=True)
+    assert float((y1 - y0).abs().max()) < 1e-5
+if "purifyb" in which:
+    A = torch.stack([spd(64, 32) for _ in range(3)]).contiguous()
+    U, info = ops.dominant_subspace_batched(A, 32)
+    assert float((U[1].t() @ U[1] - torch.eye(32, dtype=torch.float64, device=dev)).abs().max()) < 1e-10
 torch.cuda.synchronize()
 print("sanitize cases ok:", " ".join(which))
