@@ -157,6 +157,18 @@ int syn_dominant_subspace_fused_fits(int n, int ne);
 int syn_dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, void* ws, size_t ws_bytes,
                                     double* info, void* stream);
 
+/* The same solver for a complex HERMITIAN positive semi-definite matrix H = Hre + i Him (planar, m x m each, contiguous): orthonormal basis
+ * U = Ure + i Uim (m x k planar) of the span of its k dominant eigenvectors.  The kernel runs on the interleaved real embedding (every entry
+ * a + ib as [[a, -b], [b, a]]: 2m x 2m, built and taken apart on the device by this call) and uses its structure: every iterate is an
+ * embedding again, so only the even rows of each product are formed (one accumulator pair = one complex entry) and the odd rows are written
+ * from them -- the DMMA work of a native complex product, half of the plain embedded one.  info as above in the embedded convention
+ * (traces count every eigenvalue twice: tr P = 2k).  m, k multiples of 32, k < m.  Caller: the bond SVD of complex chains
+ * (reference: tensor/matrix_product_state.py:487-534 apply with the complex gates of quantum/gate.py:9-37). */
+int syn_dominant_subspace_c128_fits(int m, int k);
+size_t syn_dominant_subspace_c128_workspace(int m, int k, int sp2_max, int ns_max);
+int syn_dominant_subspace_c128(const double* Hre, const double* Him, int m, int k, int sp2_max, int ns_max, double* Ure, double* Uim,
+                               void* ws, size_t ws_bytes, double* info, void* stream);
+
 /* The projection solver for a BATCH of small bond problems (csrc/purify_batched.cu): one CTA per problem, the iterate and the basis stay in
  * shared memory, products in registers, two CTA barriers per step; a persistent grid walks the batch.  A: batch x n x n contiguous symmetric
  * PSD matrices (16-byte aligned), U: batch x n x ne, info: batch x 8 doubles with the meaning above.  n, ne multiples of 32,

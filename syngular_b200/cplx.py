@@ -30,6 +30,7 @@ PURIFY_SP2_MAX = 90
 PURIFY_NS_MAX = 60
 PURIFY_MAX_LIFT = 14           # see syngular/tensor/_sweeps.py: cuts deeper in the spectrum go to the Jacobi route (when it fits)
 PURIFY_MAX_LIFT_RANK_GAP = 24
+STRUCTURED_PROJECTION = True   # use syn_dominant_subspace_c128 (even rows of the embedded products only) when the sizes fit
 
 
 class Cx:
@@ -276,13 +277,18 @@ def svd_basis(M, chi_max, cutoff, eigh, rank_tol=3.2e-7):
         # Spectral projection on the INTERLEAVED embedding: the projector is a polynomial of the embedded matrix, hence itself an
         # embedding, and its first 2*target columns are the pairs (P e_j, J P e_j) -- Newton-Schulz keeps that structure, so the even
         # columns of the orthonormalised basis are the complex basis (no pairing problem, no size limit from the Jacobi kernel).
-        V, info = ops.dominant_subspace(embed(H), 2 * target, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
+        if STRUCTURED_PROJECTION and ops.dominant_subspace_c128_fits(m, target):
+            # planar in / planar out; the kernel computes only the even rows of every embedded product (half the DMMA work)
+            Ure, Uim, info = ops.dominant_subspace_c128(H.re.contiguous(), H.im.contiguous(), target, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
+            V = None
+        else:
+            V, info = ops.dominant_subspace(embed(H), 2 * target, sp2_max=PURIFY_SP2_MAX, ns_max=PURIFY_NS_MAX)
         h = info.cpu()
         tr, f2, kept_w, dev, tr_a, idem = (float(h[k]) for k in (0, 1, 2, 4, 5, 6))
         if (abs(tr - 2 * target) < 2e-9 * target and abs(f2 - 2 * target) < 2e-9 * target and abs(idem) < 2e-11 * target and dev < 1e-12
                 and bool(torch.isfinite(h).all())
                 and (int(h[7]) // 1000000 <= (PURIFY_MAX_LIFT_RANK_GAP if target >= min(m, c) else PURIFY_MAX_LIFT) or 2 * m > JACOBI_MAX_N)):
-            U = polish_columns(unembed_columns(V, m, target))
+            U = polish_columns(Cx(Ure, Uim) if V is None else unembed_columns(V, m, target))
             return U, target, None, torch.tensor(max(0.5 * (tr_a - kept_w), 0.0), dtype=F64)
     if 2 * m > JACOBI_MAX_N:
         raise NotImplementedError("complex bond SVD without a spectral gap at the cut needs 2 * rows <= %d (got rows = %d)" % (JACOBI_MAX_N, m))

@@ -283,6 +283,9 @@ struct PurifyArgs {
     int n, ne, sp2_max, ns_max;
     int ns_only;             // 1: A is an (n x ne) matrix with row stride ld0 whose columns are to be orthonormalised (no projection phase)
     int64_t ld0;
+    int cx;                  // 1: A is the interleaved real embedding of a complex Hermitian matrix (every entry a + ib as [[a, -b], [b, a]]):
+                             //    every iterate is an embedding too, so only the EVEN rows of each product are computed (a thread's accumulator
+                             //    pair is one complex entry (a, -b)) and the odd rows are written from them -- half the DMMA work
 };
 
 __device__ __forceinline__ unsigned pf_ld_acquire(const unsigned* p) {
@@ -480,6 +483,41 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
         const bool square = extra == 1 ? true : (extra == 2 ? false : fabs(f0 - ne) < fabs(2.0 * tr0 - f0 - ne));
         if (lifting && !square) ++lift; else lifting = false;
         double tr = 0.0, f2 = 0.0;
+        if (a.cx) {
+            // tall tiles: 32 EVEN rows of the 64-row block I against the 32 columns of block J, J <= 2 I + 1 (the lower triangle in 64-blocks)
+            const int TI = n / 64, tall = TI * (TI + 1);
+            for (int tile = blockIdx.x; tile < tall; tile += gridDim.x) {
+                int I = (int)((sqrt(4.0 * tile + 1.0) - 1.0) * 0.5);
+                while ((I + 1) * (I + 2) <= tile) ++I;
+                while (I * (I + 1) > tile) --I;
+                const int J = tile - I * (I + 1);
+                double acc[2][2][2];
+                const bool owner = pf_tile_nt(Xc, 2 * (int64_t)n, Xc, n, I * PF_T, J * PF_T, n, pf_smem, acc);
+                if (owner) {
+                    const bool mirror = J < 2 * I;
+                    const double w = mirror ? 4.0 : 2.0;
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int r = 2 * (I * PF_T + wm0 + i * 8 + g), c = J * PF_T + wn0 + j * 8 + 2 * t;
+                            double x0 = acc[i][j][0], x1 = acc[i][j][1];
+                            if (!square) {
+                                x0 = fma(2.0, __ldcg(Xc + (int64_t)r * n + c), -x0);
+                                x1 = fma(2.0, __ldcg(Xc + (int64_t)r * n + c + 1), -x1);
+                            }
+                            *reinterpret_cast<double2*>(Xn + (int64_t)r * n + c) = make_double2(x0, x1);
+                            *reinterpret_cast<double2*>(Xn + (int64_t)(r + 1) * n + c) = make_double2(-x1, x0);
+                            if (mirror) {
+                                *reinterpret_cast<double2*>(Xn + (int64_t)c * n + r) = make_double2(x0, -x1);
+                                *reinterpret_cast<double2*>(Xn + (int64_t)(c + 1) * n + r) = make_double2(x1, x0);
+                            }
+                            f2 = fma(w * x0, x0, fma(w * x1, x1, f2));
+                            if (r == c) tr += 2.0 * x0;
+                        }
+                }
+            }
+        } else
         for (int tile = blockIdx.x; tile < lower; tile += gridDim.x) {
             int ti, tj;
             pf_lower_tile(tile, ti, tj);
@@ -529,7 +567,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     // atomics accumulate: after a standard step x -> 1.5 x - 0.5 x^3 every singular value is <= 1, so ne - tr G = sum (1 - sigma_i^2)
     // bounds every 1 - sigma_i^2; max |G - I| of the final iterate (what the host checks) is taken once at the end.
     int KS = 1;
-    while (lower_g * KS * 2 <= (int)gridDim.x + (int)gridDim.x / 8 && (n / (KS * 2)) % 2 == 0 && n / (KS * 2) >= 64) KS *= 2;
+    const int gram_items = a.cx ? (ne / 64) * (ne / 64 + 1) : lower_g;
+    while (gram_items * KS * 2 <= (int)gridDim.x + (int)gridDim.x / 8 && (n / (KS * 2)) % 2 == 0 && n / (KS * 2) >= 64) KS *= 2;
     const int Kc = n / KS;
     int ns = 0;
     double dev = 0.0, dev0 = 0.0;
@@ -540,6 +579,39 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
         Gc = (ns & 1) ? a.G2 : a.G;
         double* Gnext = (ns & 1) ? a.G : a.G2;
         double trp = 0.0;
+        if (a.cx) {
+            const int TI = ne / 64, tall = TI * (TI + 1);
+            for (int item = blockIdx.x; item < tall * KS; item += gridDim.x) {
+                const int tile = item % tall, ks = item / tall;
+                int I = (int)((sqrt(4.0 * tile + 1.0) - 1.0) * 0.5);
+                while ((I + 1) * (I + 2) <= tile) ++I;
+                while (I * (I + 1) > tile) --I;
+                const int J = tile - I * (I + 1);
+                double acc[2][2][2];
+                const bool owner = pf_tile_nt(V + (int64_t)ks * Kc, 2 * (int64_t)n, V + (int64_t)ks * Kc, n, I * PF_T, J * PF_T, Kc, pf_smem, acc);
+                if (owner) {
+                    const bool mirror = J < 2 * I;
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int r = 2 * (I * PF_T + wm0 + i * 8 + g), c = J * PF_T + wn0 + j * 8 + 2 * t;
+                            const double g0 = acc[i][j][0], g1 = acc[i][j][1];
+                            atomicAdd(Gc + (int64_t)r * ne + c, g0);
+                            atomicAdd(Gc + (int64_t)r * ne + c + 1, g1);
+                            atomicAdd(Gc + (int64_t)(r + 1) * ne + c, -g1);
+                            atomicAdd(Gc + (int64_t)(r + 1) * ne + c + 1, g0);
+                            if (mirror) {
+                                atomicAdd(Gc + (int64_t)c * ne + r, g0);
+                                atomicAdd(Gc + (int64_t)c * ne + r + 1, -g1);
+                                atomicAdd(Gc + (int64_t)(c + 1) * ne + r, g1);
+                                atomicAdd(Gc + (int64_t)(c + 1) * ne + r + 1, g0);
+                            }
+                            if (r == c) trp += 2.0 * g0;
+                        }
+                }
+            }
+        } else
         for (int item = blockIdx.x; item < lower_g * KS; item += gridDim.x) {
             const int tile = item % lower_g, ks = item / lower_g;
             int ti, tj;
@@ -606,6 +678,27 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
         // singular values of P[:, :ne] (1e-3 .. 1e-1 on the C2 chain) reach the quadratic region in half the steps
         const bool steep = ns < steep_steps && dev0 > 0.5;
         const double ca = (steep ? 2.0 : 1.5) * gamma, cb = (steep ? -1.0 : -0.5) * gamma * gamma * gamma;
+        if (a.cx) {
+            for (int tile = blockIdx.x; tile < (n / 64) * TG; tile += gridDim.x) {
+                const int I = tile / TG, J = tile - I * TG;
+                double acc[2][2][2];
+                const bool owner = pf_tile_nt(U, 2 * ldu, Gc, ne, I * PF_T, J * PF_T, ne, pf_smem, acc);
+                if (owner) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int r = 2 * (I * PF_T + wm0 + i * 8 + g), c = J * PF_T + wn0 + j * 8 + 2 * t;
+                            const double u0 = fma(ca, __ldcg(U + (int64_t)r * ldu + c), cb * acc[i][j][0]);
+                            const double u1 = fma(ca, __ldcg(U + (int64_t)r * ldu + c + 1), cb * acc[i][j][1]);
+                            *reinterpret_cast<double2*>(Un + (int64_t)r * ne + c) = make_double2(u0, u1);
+                            *reinterpret_cast<double2*>(Un + (int64_t)(r + 1) * ne + c) = make_double2(-u1, u0);
+                            *reinterpret_cast<double2*>(Vn + (int64_t)c * n + r) = make_double2(u0, -u1);
+                            *reinterpret_cast<double2*>(Vn + (int64_t)(c + 1) * n + r) = make_double2(u1, u0);
+                        }
+                }
+            }
+        } else
         for (int tile = blockIdx.x; tile < tiles_u; tile += gridDim.x) {
             const int ti = tile / TG, tj = tile - ti * TG;
             double acc[2][2][2];
@@ -671,8 +764,9 @@ static bool ortho_fused_fits(int m, int q) { return m % PF_T == 0 && q % PF_T ==
 static bool purify_fused_fits(int n, int ne) { return n % PF_T == 0 && ne % PF_T == 0 && n >= 128 && ne >= 32 && ne < n; }
 
 int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int ns_max, double* U, double* ws, size_t ws_bytes, double* info,
-                                cudaStream_t st, int ns_only = 0, int64_t ld0 = 0) {
+                                cudaStream_t st, int ns_only = 0, int64_t ld0 = 0, int cx = 0) {
     SYN_REQUIRE(A && U && ws && info, "syn_dominant_subspace_f64: null argument");
+    SYN_REQUIRE(!cx || (!ns_only && n % 64 == 0 && ne % 64 == 0), "syn_dominant_subspace_c128: embedded sizes must be multiples of 64 (n=%d ne=%d)", n, ne);
     SYN_REQUIRE(ns_only ? ortho_fused_fits(n, ne) : purify_fused_fits(n, ne),
                 "syn_dominant_subspace_f64 (fused): n and ne must be multiples of 32, n >= 128 (n=%d ne=%d)", n, ne);
     SYN_REQUIRE(sp2_max >= 1 && sp2_max <= 400 && ns_max >= 0 && ns_max <= 400, "syn_dominant_subspace_f64: bad iteration limits");
@@ -702,9 +796,9 @@ int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int
     a.bar = reinterpret_cast<unsigned*>(a.ctrl + ctrl_doubles);
     a.Uout = U; a.info = info;
     a.n = n; a.ne = ne; a.sp2_max = sp2_max; a.ns_max = ns_max;
-    a.ns_only = ns_only; a.ld0 = ld0;
+    a.ns_only = ns_only; a.ld0 = ld0; a.cx = cx;
     SYN_CUDA(cudaMemsetAsync(a.ctrl, 0, sizeof(double) * (ctrl_doubles + 2), st));
-    const int T = n / PF_T, lower = T * (T + 1) / 2;
+    const int T = n / PF_T, lower = cx ? (n / 64) * (n / 64 + 1) : T * (T + 1) / 2;
     int grid = lower < max_ctas ? lower : max_ctas;
     void* args[] = {&a};
     SYN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(PF_THREADS), args, PF_SMEM, st));
@@ -712,7 +806,63 @@ int dominant_subspace_fused_f64(const double* A, int n, int ne, int sp2_max, int
     return 0;
 }
 
+// ---- complex Hermitian problems: planar in / planar out around the embedded solver ----------------------------------------------------
+// E (2m x 2m) = interleaved real embedding of H = Hre + i Him: entry (i, j) -> [[re, -im], [im, re]]
+__global__ void __launch_bounds__(256) embed_hermitian_kernel(const double* __restrict__ Hre, const double* __restrict__ Him, int m,
+                                                              double* __restrict__ E) {
+    const int64_t total = (int64_t)m * m;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / m, j = e - i * m;
+        const double re = Hre[e], im = Him[e];
+        *reinterpret_cast<double2*>(E + (2 * i) * 2 * m + 2 * j) = make_double2(re, -im);
+        *reinterpret_cast<double2*>(E + (2 * i + 1) * 2 * m + 2 * j) = make_double2(im, re);
+    }
+}
+
+// even columns of the embedded basis Ue (2m x 2k): complex column j = Ue[0::2, 2j] + i Ue[1::2, 2j]
+__global__ void __launch_bounds__(256) unembed_columns_kernel(const double* __restrict__ Ue, int m, int k, double* __restrict__ Ure,
+                                                              double* __restrict__ Uim) {
+    const int64_t total = (int64_t)m * k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / k, j = e - i * k;
+        Ure[e] = Ue[(2 * i) * 2 * k + 2 * j];
+        Uim[e] = Ue[(2 * i + 1) * 2 * k + 2 * j];
+    }
+}
+
+static bool purify_c128_fits(int m, int k) { return m % 32 == 0 && k % 32 == 0 && m >= 64 && k >= 32 && k < m; }
+
+static size_t purify_c128_ws_doubles(int m, int k, int sp2_max, int ns_max) {
+    return purify_fused_ws_doubles(2 * m, 2 * k, sp2_max, ns_max) + (size_t)4 * m * m + (size_t)4 * m * k;
+}
+
 }  // namespace syn
+
+extern "C" int syn_dominant_subspace_c128_fits(int m, int k) { return syn::purify_c128_fits(m, k) ? 1 : 0; }
+
+extern "C" size_t syn_dominant_subspace_c128_workspace(int m, int k, int sp2_max, int ns_max) {
+    return syn::purify_c128_ws_doubles(m, k, sp2_max, ns_max) * sizeof(double);
+}
+
+extern "C" int syn_dominant_subspace_c128(const double* Hre, const double* Him, int m, int k, int sp2_max, int ns_max, double* Ure, double* Uim,
+                                          void* ws, size_t ws_bytes, double* info, void* stream) {
+    using namespace syn;
+    SYN_REQUIRE(Hre && Him && Ure && Uim && ws && info, "syn_dominant_subspace_c128: null argument");
+    SYN_REQUIRE(purify_c128_fits(m, k), "syn_dominant_subspace_c128: m and k must be multiples of 32 with 32 <= k < m, m >= 64 (m=%d k=%d)", m, k);
+    SYN_REQUIRE(ws_bytes >= purify_c128_ws_doubles(m, k, sp2_max, ns_max) * sizeof(double), "syn_dominant_subspace_c128: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* E = (double*)ws;                                   // (2m x 2m) embedding
+    double* Ue = E + (size_t)4 * m * m;                        // (2m x 2k) embedded basis
+    double* inner = Ue + (size_t)4 * m * k;
+    const size_t inner_bytes = ws_bytes - ((size_t)4 * m * m + (size_t)4 * m * k) * sizeof(double);
+    const int blocks = (int)(((int64_t)m * m + 255) / 256 < 4096 ? ((int64_t)m * m + 255) / 256 : 4096);
+    embed_hermitian_kernel<<<blocks, 256, 0, st>>>(Hre, Him, m, E);
+    if (int rc = launch_status("embed_hermitian_kernel")) return rc;
+    if (int rc = dominant_subspace_fused_f64(E, 2 * m, 2 * k, sp2_max, ns_max, Ue, inner, inner_bytes, info, st, 0, 0, 1)) return rc;
+    const int blocks2 = (int)(((int64_t)m * k + 255) / 256 < 4096 ? ((int64_t)m * k + 255) / 256 : 4096);
+    unembed_columns_kernel<<<blocks2, 256, 0, st>>>(Ue, m, k, Ure, Uim);
+    return launch_status("unembed_columns_kernel");
+}
 
 extern "C" size_t syn_dominant_subspace_workspace_f64(int n, int ne, int sp2_iters) {
     if (n < 2 || ne < 1 || sp2_iters < 1) return 0;

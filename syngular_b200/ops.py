@@ -262,6 +262,30 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return U, info
 
 
+lib.syn_dominant_subspace_c128_workspace.restype = ctypes.c_size_t
+lib.syn_dominant_subspace_c128_workspace.argtypes = [_i32, _i32, _i32, _i32]
+
+
+def dominant_subspace_c128_fits(m, k):
+    return PURIFY_FUSED and bool(lib.syn_dominant_subspace_c128_fits(_i32(int(m)), _i32(int(k))))
+
+
+def dominant_subspace_c128(Hre, Him, k, sp2_max=90, ns_max=60):
+    """Planar complex Hermitian PSD H (m x m) -> planar orthonormal basis (Ure, Uim) (m x k) of its k dominant eigenvectors and the 8 info
+    doubles (embedded convention: traces count twice), all on the device; one fused kernel on the real embedding that computes only the
+    even rows of every product (csrc/purify.cu, cx mode)."""
+    require_cuda_f64(Hre); require_cuda_f64(Him)
+    m = int(Hre.shape[0])
+    assert Hre.shape == (m, m) and Him.shape == (m, m) and Hre.is_contiguous() and Him.is_contiguous()
+    Ure = torch.empty((m, int(k)), dtype=torch.float64, device=Hre.device)
+    Uim = torch.empty_like(Ure)
+    info = torch.zeros((8,), dtype=torch.float64, device=Hre.device)
+    ws = workspace(lib.syn_dominant_subspace_c128_workspace(m, int(k), int(sp2_max), int(ns_max)), Hre.device, tag="purify_c128")
+    check(lib.syn_dominant_subspace_c128(ptr(Hre), ptr(Him), _i32(m), _i32(int(k)), _i32(int(sp2_max)), _i32(int(ns_max)), ptr(Ure), ptr(Uim),
+                                         ptr(ws), _sz(ws.numel() * 8), ptr(info), stream_ptr()), "syn_dominant_subspace_c128")
+    return Ure, Uim, info
+
+
 def dominant_subspace_batched_fits(n, ne):
     return bool(lib.syn_dominant_subspace_batched_fits(_i32(int(n)), _i32(int(ne))))
 

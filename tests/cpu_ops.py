@@ -177,6 +177,25 @@ def dominant_subspace(A, ne, sp2_iters=40, ns_iters=20, fused=None, sp2_max=160,
     return torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(info)
 
 
+def dominant_subspace_c128_fits(m, k):
+    return m % 32 == 0 and k % 32 == 0 and m >= 64 and 32 <= k < m
+
+
+def dominant_subspace_c128(Hre, Him, k, sp2_max=90, ns_max=60):
+    """Planar complex Hermitian H -> planar basis of the k dominant eigenvectors; info in the embedded convention (traces count twice)."""
+    H = Hre.numpy() + 1j * Him.numpy()
+    w, V = np.linalg.eigh(0.5 * (H + H.conj().T))
+    U = V[:, ::-1][:, :k]
+    ne = 2 * k
+    gap_ok = w[::-1][k - 1] - w[::-1][k] > 1e-13 * abs(w[-1])
+    info = np.array([ne if gap_ok else ne + 0.5, ne, 2 * w[::-1][:k].sum(), np.sqrt(2.0) * np.linalg.norm(H), 1e-16, 2 * w.sum(), 0.0, 30 + 1000 * 8 + 1e6 * 6])
+    return torch.from_numpy(np.ascontiguousarray(U.real)), torch.from_numpy(np.ascontiguousarray(U.imag)), torch.from_numpy(info)
+
+
+def dominant_subspace_batched_fits(n, ne):
+    return False
+
+
 def dominant_subspace_fused_fits(n, ne):
     return n % 32 == 0 and ne % 32 == 0 and n >= 128 and ne >= 32 and ne < n
 
@@ -259,7 +278,7 @@ def overlap_fits(a, b, batched=True):
     return False
 
 
-_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "jacobi_solve", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "sum_parts", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
+_NAMES = ("gemm", "matmul", "qrt", "qr_r", "copy_strided", "jacobi_rows", "chol_upper", "jacobi_finalize", "jacobi_solve", "identity_deviation", "dominant_subspace", "dominant_subspace_fused_fits", "dominant_subspace_c128", "dominant_subspace_c128_fits", "dominant_subspace_batched_fits", "env_sandwich_fits", "env_sandwich", "env_mirror", "sum_parts", "orthonormalize_columns_fits", "orthonormalize_columns", "add_site",
           "kron_site", "sumsq", "scale_rsqrt_", "overlap_fits")
 
 

@@ -40,7 +40,7 @@ def test_brickwall_12_qubits_chi_64_against_state_vector():
 
 
 def test_brickwall_16_qubits_truncated_to_chi_128_matches_numpy_tebd():
-    """Saturated complex bonds (unfoldings 256 x 256, embedded 512 x 512) are cut by the fused spectral-projection kernel; the whole
+    """Saturated complex bonds (unfoldings 256 x 256, embedded 512 x 512) are cut by the fused spectral-projection kernel (complex-structured mode); the whole
     truncated evolution is compared with the same sequence of truncations done by numpy SVDs."""
     from syngular.quantum import Circuit
     from syngular_b200 import ops
@@ -48,17 +48,21 @@ def test_brickwall_16_qubits_truncated_to_chi_128_matches_numpy_tebd():
     n, depth, chi = 16, 9, 128
     structure = [(cc.haar(rng, 4).reshape(2, 2, 2, 2), i) for layer in range(depth) for i in range(layer % 2, n - 1, 2)]
     calls = [0]
-    orig = ops.dominant_subspace
+    orig, orig_c = ops.dominant_subspace, ops.dominant_subspace_c128
 
     def spy(*a, **k):
         calls[0] += 1
         return orig(*a, **k)
-    ops.dominant_subspace = spy
+
+    def spy_c(*a, **k):
+        calls[0] += 1
+        return orig_c(*a, **k)
+    ops.dominant_subspace, ops.dominant_subspace_c128 = spy, spy_c
     try:
         c = Circuit(n, structure=structure, chi_max=chi)
         c.run()
     finally:
-        ops.dominant_subspace = orig
+        ops.dominant_subspace, ops.dominant_subspace_c128 = orig, orig_c
     st = c.get().state
     assert max(s.shape[2] for s in st.sites[:-1]) == chi and calls[0] >= 1
     ref = cc._tebd_numpy(n, structure, chi)

@@ -173,3 +173,35 @@ def test_relative_cutoff_stays_on_the_projection_solver(n, chi, chiw, cutoff):
         assert keep[k] == kk
         assert np.max(np.abs(np.sort(sig[k])[::-1][:kk] - spectra[k][:kk])) < 1e-10 * spectra[k][0]
         assert abs(disc[k] - discarded[k]) < 1e-10 * float(np.sum(spectra[k] ** 2))
+
+
+@pytest.mark.parametrize("m,k", [(64, 32), (128, 64), (160, 96), (512, 256)])
+def test_complex_hermitian_projection_solver_matches_eigh(m, k):
+    """syn_dominant_subspace_c128: planar complex Hermitian in, planar basis out; the fused kernel forms only the even rows of the embedded
+    products.  Projector U U^H against LAPACK's, orthonormality, info doubles in the embedded convention (traces count twice), and the
+    plain embedded route (the same kernel without the structure) for the same matrix."""
+    import torch
+    from syngular_b200 import ops, cplx
+    rng = np.random.default_rng(m + k)
+    Z = rng.normal(size=(m, m)) + 1j * rng.normal(size=(m, m))
+    Q, _ = np.linalg.qr(Z)
+    lam = np.concatenate([np.exp(-rng.uniform(0.0, 4.0, size=k)), 1e-3 * np.exp(-rng.uniform(0.0, 6.0, size=m - k))])
+    H = (Q * lam) @ Q.conj().T
+    H = 0.5 * (H + H.conj().T)
+    assert ops.dominant_subspace_c128_fits(m, k)
+    Hre, Him = torch.from_numpy(np.ascontiguousarray(H.real)).cuda(), torch.from_numpy(np.ascontiguousarray(H.imag)).cuda()
+    Ure, Uim, info = ops.dominant_subspace_c128(Hre, Him, k)
+    U = Ure.cpu().numpy() + 1j * Uim.cpu().numpy()
+    h = info.cpu().numpy()
+    w, V = np.linalg.eigh(H)
+    P = V[:, -k:] @ V[:, -k:].conj().T
+    assert np.max(np.abs(U.conj().T @ U - np.eye(k))) < 1e-12
+    assert np.max(np.abs(U @ U.conj().T - P)) < 1e-10
+    assert abs(h[0] - 2 * k) < 2e-9 * k and abs(h[1] - 2 * k) < 2e-9 * k and h[4] < 1e-12
+    assert abs(h[2] - 2 * w[-k:].sum()) < 1e-11 * w.sum() and abs(h[5] - 2 * w.sum()) < 1e-11 * w.sum()
+    # the unstructured embedded route gives the same space
+    Ve, info_e = ops.dominant_subspace(cplx.embed(cplx.Cx(Hre, Him)), 2 * k, sp2_max=90, ns_max=60)
+    Ue = cplx.unembed_columns(Ve, m, k)
+    Ue = Ue.re.cpu().numpy() + 1j * Ue.im.cpu().numpy()
+    assert np.max(np.abs(Ue @ Ue.conj().T - U @ U.conj().T)) < 1e-10
+    assert int(info_e.cpu()[7]) % 1000 == int(h[7]) % 1000           # the same number of SP2 steps: the iterates agree
