@@ -21,6 +21,7 @@ def haar4():
 
 structure = [(haar4(), i) for layer in range(depth) for i in range(layer % 2, nq - 1, 2)]
 Circuit(8, structure=[(g, i % 7) for g, i in structure[:40]], chi_max=16).run()
+Circuit(nq, structure=structure, chi_max=chi).run()          # warm-up at full size: the caching allocator has seen every shape (cold run: ~1.4x slower)
 torch.cuda.synchronize()
 l0 = ops.lib.syn_launch_count()
 t0 = time.perf_counter()
