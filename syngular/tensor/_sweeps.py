@@ -806,7 +806,13 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None):
     waits for the solver of site k only, with site k+1 already queued, so the GPU never waits for the host.  A rejected bond (no gap at the cut, or the
     accuracy guard) rolls the sweep back to that site, which is then solved by Cholesky + Jacobi.
 
+    A relative cutoff BELOW rank_tol asks for singular values the Gram matrix cannot resolve (its eigenvalues carry ~1e-16 sigma_0^2 of
+    noise): such calls take the textbook route -- product cores, right-QR, left-to-right Jacobi SVD of the triangular factors
+    (round_svd), which is accurate relative to every singular value -- so the result follows the cutoff exactly as the oracle's does.
+
     `capture` (tests only): a dict {site: None}; the Gram matrix of that bond and the basis the solver kept are stored in it."""
+    if 0.0 < cutoff < rank_tol:
+        return round_svd([site_mpo_mps(x, w) for x, w in zip(X, W)], chi_max, cutoff)
     n = len(X)
     E = right_environments(X, W)
     trunc = Truncation()

@@ -187,3 +187,37 @@ def test_eigh_gram_on_cholesky_factor(n, rank):
     finally:
         sw.CHOLESKY_MIN_N = old
     assert sweeps[129] <= sweeps[0]
+
+
+def test_apply_round_dm_with_a_cutoff_below_the_gram_resolution_follows_the_textbook_oracle():
+    """The density-matrix sweep drops singular values below rank_tol = 3.2e-7 sigma_0 (squared values are noise there).  A user cutoff
+    below that must still be honoured: the call takes the textbook route.  State = a dominant part + a 1e-9 perturbation with its own
+    bond space: with cutoff 1e-11 the oracle keeps both parts, with the default cutoff 0 the density-matrix mode keeps the dominant one."""
+    from syngular.tensor import _sweeps as sw
+    from oracle import ref_numpy as R, svd_numpy as S
+    rng = np.random.default_rng(77)
+    n, d = 8, 2
+
+    def chain(chi, phys=1):
+        b = [1] + [min(chi, d ** (phys * min(k, n - k))) for k in range(1, n)] + [1]
+        return [rng.normal(size=(b[k],) + (d,) * phys + (b[k + 1],)) / np.sqrt(b[k] * d) for k in range(n)]
+    A, Bp, W = chain(3), chain(2), chain(2, phys=2)
+    Bp[3] = Bp[3] * 1e-9
+    X = [R.site_add(a, b, k == 0, k == n - 1) for k, (a, b) in enumerate(zip(A, Bp))]
+    Xd, Wd = [sw.as_core(x) for x in X], [sw.as_core(w) for w in W]
+    ref, spectra, _ = S.apply_round_svd(X, W, 64, cutoff=1e-11)
+    out, trunc = sw.apply_round_dm(Xd, Wd, 64, cutoff=1e-11)
+    got = [c.cpu().numpy() for c in out]
+    assert [c.shape for c in got] == [c.shape for c in ref]
+    assert got[n // 2 - 1].shape[-1] == 7                    # middle bond: the dominant part's 3 x 2 plus one direction of the perturbation (4.9e-11 sigma_0)
+    dr, dg = R.to_dense(ref), R.to_dense(got)
+    assert np.max(np.abs(dr - dg)) < 1e-10 * np.max(np.abs(dr))
+    # the small singular values themselves are resolved (relative accuracy of the Jacobi SVD on the triangular factor)
+    mid = n // 2
+    s_ref = spectra[mid - 1]
+    s_got = np.sort(trunc.sigma[mid - 1].cpu().numpy())[::-1]
+    k = got[mid - 1].shape[-1]
+    assert np.max(np.abs(s_got[:k] - s_ref[:k]) / s_ref[:k]) < 1e-6
+    # default cutoff: the density-matrix mode declares the 1e-9 part noise
+    out0, _ = sw.apply_round_dm(Xd, Wd, 64)
+    assert out0[n // 2 - 1].shape[-1] == 6
