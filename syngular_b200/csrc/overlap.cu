@@ -8,9 +8,10 @@
 // Design (B200): one CTA walks one pair of chains from the first site to the last; the transfer matrix E (<= 64 x 64) and the
 // half-contracted F = E B_k never leave shared memory, so HBM sees each core exactly once (the GEMM-per-site path re-reads and
 // re-writes E and F through L2/HBM every site: 320 KB instead of 128 KB per plateau site of BASELINE configs[3]).  The cores
-// stream through a 4-stage cp.async ring of K-chunks (16-byte LDGSTS along the contiguous dimension, rows padded to a stride
+// stream through a 3-stage cp.async ring of K-chunks (16-byte LDGSTS along the contiguous dimension, rows padded to a stride
 // = 4 (mod 16) doubles so that the DMMA fragment loads are bank-conflict free) that runs ahead across the two steps of a site
-// and across sites; both steps run on the FP64 tensor pipe (DMMA.8x8x4), 8 warps in a 2 x 4 grid:
+// and across sites; both steps run on the FP64 tensor pipe (DMMA.8x8x4), 16 warps (four per SM sub-partition: with eight the pipe was 49 % busy,
+// 38 % of the stall samples on fixed-latency waits) as 2 x 8 (step 0, warp tile 32 x 16) and 4 x 4 (step 1, warp tile 16 x 16):
 //   step 0:  F[a, (i, b')]  = sum_a'    E[a, a']  Bk[a', (i, b')]      M = la, N = d rb, K = lb      (A operand: E, shared memory)
 //   step 1:  E'[b, b']      = sum_(a,i) Ak[(a,i), b] F[(a,i), b']      M = ra, N = rb,   K = la d    (B operand: F, shared memory)
 // The grid is persistent: min(batch, #SM) CTAs stride over the states.  Per plateau site of configs[3] (chi = 64, d = 2):
@@ -24,9 +25,9 @@ namespace syn {
 constexpr int OV_MAXB = SYN_OVERLAP_MAX_BOND;       // largest bond of either chain
 constexpr int OV_MAXK = 2 * OV_MAXB;                // largest round8(la) * d and d * rb
 constexpr int OV_ES = OV_MAXB + 4;                  // row stride of E and F in shared memory (= 4 mod 16)
-constexpr int OV_STAGE_ELEMS = 32 * OV_ES;          // one K-chunk: 32 rows of a 64-wide core or 16 rows of a 128-wide one
-constexpr int OV_STAGES = 4;
-constexpr int OV_THREADS = 256;
+constexpr int OV_STAGE_ELEMS = 64 * OV_ES;          // one K-chunk: 64 rows of a 64-wide core or 32 rows of a 128-wide one (half the CTA barriers of 32-row chunks)
+constexpr int OV_STAGES = 3;
+constexpr int OV_THREADS = 512;
 constexpr int OV_SMEM_DOUBLES = OV_MAXB * OV_ES + OV_MAXK * OV_ES + OV_STAGES * OV_STAGE_ELEMS + 8;   // + slack: tiles read up to round8(len)
 
 struct OverlapParams {
@@ -51,7 +52,7 @@ struct OvCursor {        // position in the flat (site, step, K-chunk) sequence 
 // fragments double-buffered in registers like the GEMM kernel).  A fragment (i, kk): a0[i * A_MS + kk * A_KS]; B fragment
 // (j, kk): b0[kk * B_KS + j * 8].
 template <int MT, int NT, int ROWS, int A_MS, int A_KS, int B_KS>
-__device__ __forceinline__ void ov_mma_full(double (&acc)[4][4][2], const double* __restrict__ a0, const double* __restrict__ b0) {
+__device__ __forceinline__ void ov_mma_full(double (&acc)[4][2][2], const double* __restrict__ a0, const double* __restrict__ b0) {
     double af[2][MT], bf[2][NT];
     auto load_frags = [&](int buf, int kk) {
 #pragma unroll
@@ -73,7 +74,7 @@ __device__ __forceinline__ void ov_mma_full(double (&acc)[4][4][2], const double
 
 // Edge-tile inner loop: runtime tile counts, strides and rows (first / last sites of a chain, odd bonds).
 template <int NTMAX>
-__device__ __forceinline__ void ov_mma_edge(double (&acc)[4][4][2], const double* a0, const double* b0, int mt, int nt, int rows, int a_ms,
+__device__ __forceinline__ void ov_mma_edge(double (&acc)[4][2][2], const double* a0, const double* b0, int mt, int nt, int rows, int a_ms,
                                             int a_ks, int b_ks) {
     double af[2][4], bf[2][NTMAX];
     auto load_frags = [&](int buf, int kk) {
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(OV_THREADS, 1) overlap_chain_kernel(const __gr
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wmi = warp >> 2, wni = warp & 3;          // 2 x 4 warps
+    const int wmi0 = warp >> 3, wni0 = warp & 7;        // step 0: 2 x 8 warps, tile 32 x 16
+    const int wmi1 = warp >> 2, wni1 = warp & 3;        // step 1: 4 x 4 warps, tile 16 x 16
 
     for (int idx = tid; idx < 2 * p.n_sites; idx += OV_THREADS) {
         const syn_overlap_site_t& s = p.site[idx >> 1];
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(OV_THREADS, 1) overlap_chain_kernel(const __gr
         }
     };
 
-    double acc[4][4][2];
+    double acc[4][2][2];
     const int first = p.site[0].la * p.site[0].lb;
     const syn_overlap_site_t& last = p.site[p.n_sites - 1];
 
@@ -200,24 +202,24 @@ __global__ void __launch_bounds__(OV_THREADS, 1) overlap_chain_kernel(const __gr
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             }
             if (cons.step == 0) {
-                // F = E Bk : warp tile 32 x 32 of (round8(la) x round8(d rb))
-                const int wm0 = wmi * 32, wn0 = wni * 32;
+                // F = E Bk : warp tile 32 x 16 of (round8(la) x round8(d rb))
+                const int wm0 = wmi0 * 32, wn0 = wni0 * 16;
                 const int Mp = (s.la + 7) & ~7, Np = (len + 7) & ~7;
-                const int mt = min(4, max(0, (Mp - wm0) >> 3)), nt = min(4, max(0, (Np - wn0) >> 3));
+                const int mt = min(4, max(0, (Mp - wm0) >> 3)), nt = min(2, max(0, (Np - wn0) >> 3));
                 if (mt > 0 && nt > 0) {
                     const double* eA = sE + (wm0 + g) * OV_ES + cons.row0 + t;
                     const double* bB = st + t * stride + wn0 + g;
-                    if (mt == 4 && nt == 4 && stride == 2 * OV_MAXB + 4 && rows == 16)
-                        ov_mma_full<4, 4, 16, 8 * OV_ES, 1, 2 * OV_MAXB + 4>(acc, eA, bB);
+                    if (mt == 4 && nt == 2 && stride == 2 * OV_MAXB + 4 && rows == 32)
+                        ov_mma_full<4, 2, 32, 8 * OV_ES, 1, 2 * OV_MAXB + 4>(acc, eA, bB);
                     else
-                        ov_mma_edge<4>(acc, eA, bB, mt, nt, rows, 8 * OV_ES, 1, stride);
+                        ov_mma_edge<2>(acc, eA, bB, mt, nt, rows, 8 * OV_ES, 1, stride);
                     if (last_chunk) {       // F[a, n = (i, b')] -> sF[(a d + i)][b'];  columns n >= d rb do not exist
-                        int off[4][2];      // the split of n does not depend on the row tile: 8 divisions per lane and site
+                        int off[2][2];      // the split of n does not depend on the row tile: 4 divisions per lane and site
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 2; ++j)
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const int n = wn0 + j * 8 + 2 * t + h;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(OV_THREADS, 1) overlap_chain_kernel(const __gr
                             if (i < mt) {
                                 double* row = sF + (wm0 + i * 8 + g) * s.d * OV_ES;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
+                                for (int j = 0; j < 2; ++j)
 #pragma unroll
                                     for (int h = 0; h < 2; ++h)
                                         if (off[j][h] >= 0) row[off[j][h]] = acc[i][j][h];
@@ -238,20 +240,20 @@ __global__ void __launch_bounds__(OV_THREADS, 1) overlap_chain_kernel(const __gr
                     }
                 }
             } else {
-                // E' = Ak^T F : warp tile 32 x 16 of (round8(ra) x round8(rb))
-                const int wm0 = wmi * 32, wn0 = wni * 16;
+                // E' = Ak^T F : warp tile 16 x 16 of (round8(ra) x round8(rb))
+                const int wm0 = wmi1 * 16, wn0 = wni1 * 16;
                 const int Mp = (s.ra + 7) & ~7, Np = (s.rb + 7) & ~7;
-                const int mt = min(4, max(0, (Mp - wm0) >> 3)), nt = min(2, max(0, (Np - wn0) >> 3));
+                const int mt = min(2, max(0, (Mp - wm0) >> 3)), nt = min(2, max(0, (Np - wn0) >> 3));
                 if (mt > 0 && nt > 0) {
                     const double* aA = st + t * stride + wm0 + g;
                     const double* fB = sF + (cons.row0 + t) * OV_ES + wn0 + g;
-                    if (mt == 4 && nt == 2 && stride == OV_ES && rows == 32)
-                        ov_mma_full<4, 2, 32, 8, OV_ES, OV_ES>(acc, aA, fB);
+                    if (mt == 2 && nt == 2 && stride == OV_ES && rows == 64)
+                        ov_mma_full<2, 2, 64, 8, OV_ES, OV_ES>(acc, aA, fB);
                     else
                         ov_mma_edge<2>(acc, aA, fB, mt, nt, rows, 8, stride, OV_ES);
                     if (last_chunk) {       // nobody reads E during step 1; pad rows / columns are written as exact zeros
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
+                        for (int i = 0; i < 2; ++i)
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 if (i < mt && j < nt) {
