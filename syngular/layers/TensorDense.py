@@ -13,6 +13,8 @@ Two arithmetic paths:
                     intermediates in TMEM / shared memory (csrc/ttdense.cu).  Covered shape: three cores with every mode and bond 16
                     (BASELINE configs[4]); anything else raises.  Stated tolerance against the float64 restatement: 4e-3 of the output's
                     largest magnitude (TF32 keeps 10 mantissa bits of every operand, three chained contractions).
+                    `layer(x_host, out=y_host)` with pinned host tensors streams the batch through the device in pieces: upload, kernel
+                    and download overlap on three streams (the host-resident use of a Keras layer: arrays in, arrays out).
 """
 import numpy as np
 import torch
@@ -45,6 +47,7 @@ class TensorDense:
             raise NotImplementedError("the fused TF32 kernel applies relu or no activation")
         self.precision = precision
         self._packed = self._bias32 = None
+        self._streams = self._stream_bufs = None
 
     def core_shapes(self):
         n, i, o, b = self.cores_number, self.tt_input_shape, self.tt_output_shape, self.tt_bond_shape
@@ -72,12 +75,58 @@ class TensorDense:
         n, b = self.cores_number, self.tt_bond_shape
         return self.tt_input_shape[k], self.tt_output_shape[k], (1 if k == 0 else b[k - 1]), (1 if k == n - 1 else b[k])
 
-    def __call__(self, inputs, chunk=None):
-        return self.call(inputs, chunk)
+    def __call__(self, inputs, chunk=None, out=None):
+        return self.call(inputs, chunk, out)
 
-    def call(self, inputs, chunk=None):
+    STREAM_CHUNK = 8192            # samples per piece of the host-in / host-out pipeline (128 MB each way at 4096 float32)
+
+    def _call_streamed(self, x_host, out_host, chunk=None):
+        """Host batch in, host batch out (both pinned float32): the batch is cut into pieces and the upload of piece c + 1, the kernel of
+        piece c and the download of piece c - 1 run concurrently on three streams (PCIe is full duplex), double-buffered on the device.
+        The caller's current stream waits for the last download, so a synchronize / event on it covers the whole call."""
+        dev = sw.device()
+        n = int(x_host.shape[0])
+        step = int(chunk or self.STREAM_CHUNK)
+        cur = torch.cuda.current_stream(dev)
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._streams
+        if self._stream_bufs is None or self._stream_bufs[0][0].shape[0] < min(step, n):
+            rows = min(step, n)
+            self._stream_bufs = [[torch.empty((rows, 4096), dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(2)]
+        xin, yout = self._stream_bufs
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        comp_done = [torch.cuda.Event() for _ in range(2)]
+        out_done = [torch.cuda.Event() for _ in range(2)]
+        s_in.wait_stream(cur)                       # earlier work of the caller on these buffers
+        s_out.wait_stream(cur)
+        for c, lo in enumerate(range(0, n, step)):
+            hi, b = min(lo + step, n), c & 1
+            if c >= 2:
+                s_in.wait_event(comp_done[b])       # the kernel that read xin[b] two pieces ago is done
+            with torch.cuda.stream(s_in):
+                xin[b][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                in_ready[b].record(s_in)
+            cur.wait_event(in_ready[b])
+            if c >= 2:
+                cur.wait_event(out_done[b])         # yout[b] of two pieces ago has left the device
+            ops.tt_dense3_tf32(xin[b][: hi - lo], self._packed, self._bias32, relu=self.activation == "relu", out=yout[b][: hi - lo])
+            comp_done[b].record(cur)
+            s_out.wait_event(comp_done[b])
+            with torch.cuda.stream(s_out):
+                out_host[lo:hi].copy_(yout[b][: hi - lo], non_blocking=True)
+                out_done[b].record(s_out)
+        cur.wait_stream(s_out)
+        return out_host
+
+    def call(self, inputs, chunk=None, out=None):
         if not self.cores:
             self.build()
+        if (self.precision == "tf32" and out is not None and isinstance(inputs, torch.Tensor) and not inputs.is_cuda and not out.is_cuda):
+            if not (inputs.is_pinned() and out.is_pinned() and inputs.dtype == torch.float32 and out.dtype == torch.float32
+                    and inputs.is_contiguous() and out.is_contiguous() and tuple(out.shape) == (inputs.reshape(-1, 4096).shape[0], 4096)):
+                raise ValueError("the streamed host path needs pinned, contiguous float32 host tensors of shape (batch, 4096) for inputs and out")
+            return self._call_streamed(inputs.reshape(-1, self.tt_input_shape_unfold), out, chunk)
         if self.precision == "tf32":
             x32 = inputs if isinstance(inputs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inputs, dtype=np.float32))
             x32 = x32.to(device=sw.device(), dtype=torch.float32).reshape(-1, self.tt_input_shape_unfold).contiguous()

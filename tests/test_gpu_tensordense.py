@@ -109,3 +109,23 @@ def test_tensordense_tf32_rejects_uncovered_shapes():
     from syngular.layers import TensorDense
     with pytest.raises(NotImplementedError):
         TensorDense((8, 8, 8), (8, 8, 8), (4, 4), precision="tf32")
+
+
+def test_tensordense_tf32_streamed_host_path_equals_the_device_path():
+    """layer(x_host, out=y_host) with pinned host tensors: pieces are uploaded, computed and downloaded on three overlapping streams; the
+    result is bit-identical to the one-shot device call (same kernel, same per-sample arithmetic), for a ragged last piece too."""
+    import torch
+    from syngular.layers import TensorDense
+    shape = (16, 16, 16)
+    layer = TensorDense(shape, shape, (16, 16), seed=11, precision="tf32").build()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((1000, 4096), dtype=torch.float32, generator=g).pin_memory()
+    y = torch.empty_like(x).pin_memory()
+    want = layer(x.cuda()).cpu()
+    for chunk in (128, 300, 4096):                    # several pieces, a ragged tail, one piece
+        y.zero_()
+        got = layer(x, chunk=chunk, out=y)
+        torch.cuda.synchronize()
+        assert got is y and torch.equal(y, want)
+    with pytest.raises(ValueError):
+        layer(torch.randn(4, 4096), out=torch.empty(4, 4096))        # not pinned
