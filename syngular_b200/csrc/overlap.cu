@@ -144,7 +144,20 @@ __global__ void __launch_bounds__(OV_THREADS, 1) overlap_chain_kernel(const __gr
         const int rows = (valid + 3) & ~3;
         const bool vec2 = ((len & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
         const int U = vec2 ? (len >> 1) : len;          // copies per row
-        if (U <= OV_THREADS && (U & (U - 1)) == 0) {    // power-of-two rows: a thread keeps its column and walks down the rows
+        if (vec2 && valid == rows && ((U == 64 && rows == 32) || (U == 32 && rows == 64))) {
+            // plateau chunks (full 64-row x 64-wide or 32-row x 128-wide K-chunks of aligned cores): exactly four 16-byte copies per thread
+            // at constant pointer increments (the general loops below cost 21 instructions per copy).  Tried instead: a dedicated producer
+            // warp issuing every copy, so that the DMMA warps run no copy code at all -- no faster (503 k vs 511 k states/s): the issue
+            // phase was not what idles the tensor pipe.
+            const int sh = U == 64 ? 6 : 5;
+            const int col = (tid & (U - 1)) * 2, r0 = tid >> sh, rstep = OV_THREADS >> sh;
+            const double* from = src + (int64_t)r0 * len + col;
+            double* to = stage + r0 * stride + col;
+            const int64_t fstep = (int64_t)rstep * len;
+            const int tstep = rstep * stride;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cp_async<16>(to + k * tstep, from + k * fstep, true);
+        } else if (U <= OV_THREADS && (U & (U - 1)) == 0) {    // power-of-two rows: a thread keeps its column and walks down the rows
             const int sh = 31 - __clz(U);
             const int col = (tid & (U - 1)) * (vec2 ? 2 : 1), step = OV_THREADS >> sh;
             for (int r = tid >> sh; r < rows; r += step) {
