@@ -30,6 +30,7 @@ PURIFY_SP2_MAX = 90
 PURIFY_NS_MAX = 60
 PURIFY_MAX_LIFT = 14           # see syngular/tensor/_sweeps.py: cuts deeper in the spectrum go to the Jacobi route (when it fits)
 PURIFY_MAX_LIFT_RANK_GAP = 24
+IDENTITY_MIN_M = 128           # complex bonds of at least this many rows that keep their whole space skip the eigen-solve (0 = never)
 STRUCTURED_PROJECTION = True   # use syn_dominant_subspace_c128 (even rows of the embedded products only) when the sizes fit
 
 
@@ -271,8 +272,17 @@ def svd_basis(M, chi_max, cutoff, eigh, rank_tol=3.2e-7):
     returns (U (m x keep) planar with orthonormal columns, keep, sigma (device, m values, descending), discarded weight).
     `eigh(S, chi, cutoff, rank_tol)` is the real symmetric eigen-solver (syngular.tensor._sweeps.eigh_gram)."""
     m, c = M.shape
-    H = matmul(M, M.h())                                         # Hermitian Gram matrix (squared singular values)
     target = min(int(chi_max), m, c)
+    if IDENTITY_MIN_M and cutoff == 0.0 and target == m and m >= IDENTITY_MIN_M:
+        # nothing is truncated at this bond: every unitary basis of the whole row space is a valid gauge -- the split U (U^H M) is exact for
+        # any unitary U, and later truncations see the same state (their local SVDs differ by that unitary on the bond index only) -- so
+        # the identity is taken and no eigen-problem is solved (the growth phase of a circuit: one-sided Jacobi on the 2m x 2m embedding
+        # took 21.7 ms at m = 512).  Same rule as _sweeps.IDENTITY_WHEN_FULL.  Small bonds keep the rank-revealing SVD (structured
+        # circuits -- CX ladders, GHZ -- stay at their true ranks); a large bond that is rank-deficient here is pruned by the next
+        # truncating split, whose solvers drop singular values below rank_tol.
+        eye = torch.eye(m, dtype=F64, device=M.device)
+        return Cx(eye, torch.zeros_like(eye)), m, None, torch.zeros((), dtype=F64, device=M.device)
+    H = matmul(M, M.h())                                         # Hermitian Gram matrix (squared singular values)
     if PURIFY_MIN_N and 2 * m >= PURIFY_MIN_N and cutoff == 0.0 and target < m and ops.dominant_subspace_fused_fits(2 * m, 2 * target):
         # Spectral projection on the INTERLEAVED embedding: the projector is a polynomial of the embedded matrix, hence itself an
         # embedding, and its first 2*target columns are the pairs (P e_j, J P e_j) -- Newton-Schulz keeps that structure, so the even
