@@ -11,6 +11,7 @@ import torch
 from . import ops
 
 F64 = torch.float64
+SMALL_CORE = True                              # shared-MPO-core contractions by the streaming kernel csrc/smallcore.cu (False: GEMMs)
 PROJECTION_BATCHED = True                      # bond problems that fit csrc/purify_batched.cu use it (False: Jacobi only)
 PROJECTION_STATS = {"taken": 0, "fallback": 0}
 
@@ -154,13 +155,22 @@ class BatchedMatrixProductState:
             ops.gemm(X, En, P1, M=a * i, N=r * D, K=b, a_m=b, a_k=1, b_k=r * D, b_n=1, c_m=r * D, c_n=1,
                      batch=B, a_b=a * i * b, b_b=D * D, c_b=a * i * r * D)
             P2 = empty(B, a, l, o, D)
-            # the shared MPO core against ALL (state, a) slices at once: the slice index is the outer level of the column index, so this is
-            # one (l o) x (B a D) x (i r) product instead of B a products with 8 x 8 operands
-            ops.gemm(Wk, P1, P2, M=l * o, N=B * a * D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=(i * r * D, 1, D),
-                     c_m=D, c_n=(l * o * D, 1, D))
+            # the shared MPO core against ALL (state, a) slices: an (l o) x (i r) matrix applied to the middle index of P1 -- pure streaming
+            # (csrc/smallcore.cu); other core sizes: one (l o) x (B a D) x (i r) GEMM with the slice index folded into the column index
+            if SMALL_CORE and ops.small_core_fits(i * r, l * o):
+                ops.apply_small_core(P1, Wk.permute(0, 2, 1, 3).reshape(l * o, i * r).contiguous(), P2, Q=B * a, L=D,
+                                     x_q=i * r * D, x_r=D, x_l=1, y_q=l * o * D, y_ro=(0, D, l * o), y_l=1)
+            else:
+                ops.gemm(Wk, P1, P2, M=l * o, N=B * a * D, K=i * r, a_m=(i * o * r, r, o), a_k=(o * r, 1, r), b_k=D, b_n=(i * r * D, 1, D),
+                         c_m=D, c_n=(l * o * D, 1, D))
             Z = empty(B, a * l, l, i, b)
-            ops.gemm(P2, Wk, Z, M=B * a * l * b, N=l * i, K=o * r, a_m=(o * D, 1, b), a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i),
-                     c_m=(l * i * b, 1, b), c_n=b)                    # likewise: rows (state, a, l', b')
+            if SMALL_CORE and ops.small_core_fits(o * r, l * i):
+                # Z[q = (B, a, l')][(l, i)][b'] = sum_(o, r) W[(l, i), (o, r)] P2[q][(o, r)][b']: the core is read in place (row-major l i x o r)
+                ops.apply_small_core(P2, Wk.contiguous().reshape(l * i, o * r), Z, Q=B * a * l, L=b,
+                                     x_q=o * D, x_r=b, x_l=1, y_q=l * i * b, y_ro=(0, b, l * i), y_l=1)
+            else:
+                ops.gemm(P2, Wk, Z, M=B * a * l * b, N=l * i, K=o * r, a_m=(o * D, 1, b), a_k=(D, b, r), b_k=1, b_n=(i * o * r, o * r, i),
+                         c_m=(l * i * b, 1, b), c_n=b)                    # likewise: rows (state, a, l', b')
             Ek = empty(B, a * l, l * a)
             ops.gemm(Z, X, Ek, M=a * l, N=a, K=i * b, a_m=l * i * b, a_k=1, b_k=1, b_n=i * b, c_m=a * l, c_n=1,
                      batch=B * l, a_b=(a * l * l * i * b, i * b, l), b_b=(a * i * b, 0, l), c_b=(a * l * a * l, a, l))
@@ -176,8 +186,14 @@ class BatchedMatrixProductState:
             ops.gemm(T, X, T1, M=s, N=i * b, K=a, a_m=l * a, a_k=1, b_k=i * b, b_n=1, c_m=l * i * b, c_n=1,
                      batch=B * l, a_b=(s * l * a, a, l), b_b=(a * i * b, 0, l), c_b=(s * l * i * b, i * b, l))
             M = empty(B, s * o, D)
-            ops.gemm(T1, Wk, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
-                     c_m=(o * b * r, r, b), c_n=(b * r, 1, r), batch=B, a_b=s * l * i * b, b_b=0, c_b=s * o * D)
+            if SMALL_CORE and ops.small_core_fits(l * i, o * r):
+                # M[(B, s)][o][b'][r] = sum_(l, i) W[(l, i), (o, r)] T1[(B, s)][(l, i)][b']: the transposed core (o r x l i) as the small matrix,
+                # the output's (o, r) index split around b' by the kernel's two-level index
+                ops.apply_small_core(T1, Wk.reshape(l * i, o * r).t().contiguous(), M, Q=B * s, L=b,
+                                     x_q=l * i * b, x_r=b, x_l=1, y_q=o * D, y_ro=(b * r, 1, r), y_l=r)
+            else:
+                ops.gemm(T1, Wk, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
+                         c_m=(o * b * r, r, b), c_n=(b * r, 1, r), batch=B, a_b=s * l * i * b, b_b=0, c_b=s * o * D)
             if k == n - 1:
                 out.append(M.reshape(B, s, o, D))
                 break

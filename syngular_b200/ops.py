@@ -286,6 +286,22 @@ def dominant_subspace_c128(Hre, Him, k, sp2_max=90, ns_max=60):
     return Ure, Uim, info
 
 
+def small_core_fits(rin, rout):
+    return bool(lib.syn_apply_small_core_fits(_i32(int(rin)), _i32(int(rout))))
+
+
+def apply_small_core(X, Wm, Y, Q, L, x_q, x_r, x_l, y_q, y_ro, y_l):
+    """Y[q][ro][x] = sum_ri Wm[ro][ri] X[q][ri][x] (csrc/smallcore.cu): Wm a small contiguous (rout x rin) matrix, X / Y raw strided views
+    given by element strides; y_ro = (outer, inner, div) two-level index of ro.  Streaming kernel for the shared-MPO-core contractions."""
+    require_cuda_f64(X, Wm, Y)
+    rout, rin = int(Wm.shape[0]), int(Wm.shape[1])
+    assert Wm.is_contiguous()
+    check(lib.syn_apply_small_core_f64(ptr(X), ptr(Wm), ptr(Y), _i64(int(Q)), _i32(rin), _i32(rout), _i32(int(L)), _i64(int(x_q)), _i64(int(x_r)),
+                                       _i64(int(x_l)), _i64(int(y_q)), _i64(int(y_ro[0])), _i64(int(y_ro[1])), _i32(int(y_ro[2])), _i64(int(y_l)),
+                                       stream_ptr()), "syn_apply_small_core_f64")
+    return Y
+
+
 def dominant_subspace_batched_fits(n, ne):
     return bool(lib.syn_dominant_subspace_batched_fits(_i32(int(n)), _i32(int(ne))))
 

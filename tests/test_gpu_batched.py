@@ -127,3 +127,47 @@ def test_batched_apply_round_svd_through_the_projection_kernel():
         dr, dg, dj = R.to_dense(ref), R.to_dense(got), R.to_dense([c[b].cpu().numpy() for c in jac.sites])
         assert np.max(np.abs(dr - dg)) < 1e-10 * np.max(np.abs(dr))
         assert np.max(np.abs(dj - dg)) < 1e-10 * np.max(np.abs(dr))
+
+
+@pytest.mark.parametrize("rin,rout", [(8, 8), (4, 8), (16, 2), (2, 4)])
+def test_small_core_kernel_matches_einsum(rin, rout):
+    """csrc/smallcore.cu: Y[q][ro][x] = sum_ri W[ro][ri] X[q][ri][x] with strided X and a two-level ro index on the output."""
+    from syngular_b200 import ops
+    rng = np.random.default_rng(rin * 17 + rout)
+    Q, L = 37, 50
+    X = rng.normal(size=(Q, rin, L))
+    Wm = rng.normal(size=(rout, rin))
+    ref = np.einsum("or,qrx->qox", Wm, X)
+    Xd, Wd = torch.from_numpy(X).cuda(), torch.from_numpy(Wm).cuda()
+    Y = torch.empty((Q, rout, L), dtype=torch.float64, device="cuda")
+    ops.apply_small_core(Xd, Wd, Y, Q=Q, L=L, x_q=rin * L, x_r=L, x_l=1, y_q=rout * L, y_ro=(0, L, rout), y_l=1)
+    assert np.max(np.abs(Y.cpu().numpy() - ref)) < 1e-13 * np.max(np.abs(ref))
+    # output with ro = (o, r) split around x: Y2[q][o][x][r], r = rout / 2 values innermost
+    ro_r = 2
+    Y2 = torch.empty((Q, rout // ro_r, L, ro_r), dtype=torch.float64, device="cuda")
+    ops.apply_small_core(Xd, Wd, Y2, Q=Q, L=L, x_q=rin * L, x_r=L, x_l=1, y_q=rout * L, y_ro=(L * ro_r, 1, ro_r), y_l=ro_r)
+    want2 = ref.reshape(Q, rout // ro_r, ro_r, L).transpose(0, 1, 3, 2)
+    assert np.max(np.abs(Y2.cpu().numpy() - want2)) < 1e-13 * np.max(np.abs(ref))
+
+
+def test_batched_apply_round_svd_small_core_path_equals_the_gemm_path():
+    """chi_W = 4, d = 2 cores (8 x 8 small matrices) take the streaming kernel; the same sweep with GEMMs must give the same state."""
+    from syngular_b200 import batched
+    from syngular_b200.batched import BatchedMatrixProductState as BMPS
+    from syngular.tensor import _sweeps as sw
+    from oracle import ref_numpy as R
+    rng = np.random.default_rng(28)
+    B, n, d, chi, chiw, target = 3, 10, 2, 16, 4, 12
+    Xs = [rand_chain(rng, n, d, chi) for _ in range(B)]
+    W = rand_chain(rng, n, d, chiw, phys=2)
+    Wd = [sw.as_core(w) for w in W]
+    out = BMPS.from_states(Xs).apply_round_svd(Wd, target)
+    batched.SMALL_CORE = False
+    try:
+        ref = BMPS.from_states(Xs).apply_round_svd(Wd, target)
+    finally:
+        batched.SMALL_CORE = True
+    for b in range(B):
+        dg = R.to_dense([c[b].cpu().numpy() for c in out.sites])
+        dr = R.to_dense([c[b].cpu().numpy() for c in ref.sites])
+        assert np.max(np.abs(dr - dg)) < 1e-11 * np.max(np.abs(dr))
