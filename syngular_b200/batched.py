@@ -100,8 +100,12 @@ class BatchedMatrixProductState:
             ops.gemm(T, X, T1, M=s, N=i * b, K=a, a_m=l * a, a_k=1, b_k=i * b, b_n=1, c_m=l * i * b, c_n=1,
                      batch=B * l, a_b=(s * l * a, a, l), b_b=(a * i * b, 0, l), c_b=(s * l * i * b, i * b, l))
             M = torch.empty((B, s, o, b * r), dtype=F64, device=dev)
-            ops.gemm(T1, Wk, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
-                     c_m=(o * b * r, r, b), c_n=(b * r, 1, r), batch=B, a_b=s * l * i * b, b_b=0, c_b=s * o * b * r)
+            if SMALL_CORE and ops.small_core_fits(l * i, o * r):         # shared small core: streaming kernel (see _apply_round_svd_chunk)
+                ops.apply_small_core(T1, Wk.reshape(l * i, o * r).t().contiguous(), M, Q=B * s, L=b,
+                                     x_q=l * i * b, x_r=b, x_l=1, y_q=o * b * r, y_ro=(b * r, 1, r), y_l=r)
+            else:
+                ops.gemm(T1, Wk, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
+                         c_m=(o * b * r, r, b), c_n=(b * r, 1, r), batch=B, a_b=s * l * i * b, b_b=0, c_b=s * o * b * r)
             if k == n - 1:
                 out.append(M)
                 break
