@@ -46,6 +46,8 @@ static syn_gemm_desc_t pdesc(int M, int N, int K, int batch, int64_t a_m, int64_
 
 __device__ __forceinline__ void block_accumulate(double a, double b, double* out0, double* out1) {
     __shared__ double r0[32], r1[32];
+    __syncthreads();          // warp 0 may still be reading r0 / r1 of a previous call (two calls with no CTA barrier in between: a CTA
+                              // without Gram items goes from the kept-weight sum straight to the trace sum; found by racecheck)
     a = warp_sum(a);
     b = warp_sum(b);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

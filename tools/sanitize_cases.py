@@ -10,7 +10,7 @@ from syngular_b200 import ops
 from syngular.tensor import _sweeps as sw
 import bench
 
-which = sys.argv[1:] or ["gemm", "purify", "ortho", "jacobi", "qr", "chol", "overlap", "sweep", "ttdense", "ttpair", "purifyb"]
+which = sys.argv[1:] or ["gemm", "purify", "ortho", "jacobi", "qr", "chol", "overlap", "sweep", "ttdense", "ttpair", "purifyb", "c128", "smallcore"]
 dev = torch.device("cuda")
 rng = np.random.default_rng(0)
 
@@ -72,5 +72,19 @@ if "purifyb" in which:
     A = torch.stack([spd(64, 32) for _ in range(3)]).contiguous()
     U, info = ops.dominant_subspace_batched(A, 32)
     assert float((U[1].t() @ U[1] - torch.eye(32, dtype=torch.float64, device=dev)).abs().max()) < 1e-10
+if "c128" in which:
+    Z = rng.normal(size=(64, 64)) + 1j * rng.normal(size=(64, 64))
+    Qc, _ = np.linalg.qr(Z)
+    lam = np.concatenate([np.linspace(1.0, 0.5, 32), np.linspace(0.05, 0.001, 32)])
+    H = (Qc * lam) @ Qc.conj().T
+    H = 0.5 * (H + H.conj().T)
+    Ure, Uim, info = ops.dominant_subspace_c128(torch.from_numpy(np.ascontiguousarray(H.real)).to(dev), torch.from_numpy(np.ascontiguousarray(H.imag)).to(dev), 32)
+    U = torch.complex(Ure, Uim)
+    assert float((U.conj().t() @ U - torch.eye(32, dtype=torch.complex128, device=dev)).abs().max()) < 1e-10
+if "smallcore" in which:
+    X = torch.randn((9, 8, 70), dtype=torch.float64, device=dev); Wm = torch.randn((8, 8), dtype=torch.float64, device=dev)
+    Y = torch.empty((9, 8, 70), dtype=torch.float64, device=dev)
+    ops.apply_small_core(X, Wm, Y, Q=9, L=70, x_q=560, x_r=70, x_l=1, y_q=560, y_ro=(0, 70, 8), y_l=1)
+    assert torch.allclose(Y, torch.einsum("or,qrx->qox", Wm, X))
 torch.cuda.synchronize()
 print("sanitize cases ok:", " ".join(which))
