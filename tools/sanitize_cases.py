@@ -26,6 +26,15 @@ if "gemm" in which:
     assert torch.allclose(ops.matmul(a, b), a @ b)
     a = torch.randn(70, 33, dtype=torch.float64, device=dev); b = torch.randn(33, 45, dtype=torch.float64, device=dev)
     assert torch.allclose(ops.matmul(a, b), a @ b)
+    # block-lower output mask (128 x 64 tiles), a skinny and a flat output
+    a = torch.randn(256, 96, dtype=torch.float64, device=dev); b = torch.randn(96, 128, dtype=torch.float64, device=dev)
+    c = torch.zeros(256, 128, dtype=torch.float64, device=dev)
+    ops.gemm(a, b, c, M=256, N=128, K=96, a_m=96, a_k=1, b_k=128, b_n=1, c_m=128, c_n=1, mask=(128, 64))
+    ref = a @ b
+    assert torch.allclose(c[:128, :64], ref[:128, :64]) and torch.allclose(c[128:], ref[128:]) and float(c[:128, 64:].abs().max()) == 0.0
+    a = torch.randn(512, 40, dtype=torch.float64, device=dev); b = torch.randn(40, 16, dtype=torch.float64, device=dev)
+    assert torch.allclose(ops.matmul(a, b), a @ b)
+    assert torch.allclose(ops.matmul(b.t().contiguous(), a.t().contiguous()), b.t() @ a.t())
 if "purify" in which:
     A = spd(128, 64)
     U, info = ops.dominant_subspace(A, 64, 52, 26, sp2_max=90, ns_max=60)
