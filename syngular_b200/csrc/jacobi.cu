@@ -171,8 +171,9 @@ __device__ __forceinline__ int rotate_cached(R (&ra)[NREG], R& na, R* __restrict
         if (FULL || col < n) b[col] = fma(s, x, c * y);
     }
     na = fma(-t, ab, na);
+    __syncwarp();          // every lane has read the cached norm above before lane 0 replaces it (racecheck: intra-warp WAR)
     if (lane == 0) *nb = fma(t, ab, bb);
-    __syncwarp();          // the cached norm is read by every lane of this warp in its next rotation (racecheck: intra-warp RAW)
+    __syncwarp();          // ... and it is read by every lane of this warp in its next rotation (racecheck: intra-warp RAW)
     return kind;
 }
 
