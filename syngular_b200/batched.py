@@ -14,6 +14,18 @@ F64 = torch.float64
 SMALL_CORE = True                              # shared-MPO-core contractions by the streaming kernel csrc/smallcore.cu (False: GEMMs)
 PROJECTION_BATCHED = True                      # bond problems that fit csrc/purify_batched.cu use it (False: Jacobi only)
 PROJECTION_STATS = {"taken": 0, "fallback": 0}
+RANGE_FINDER = True                            # chain-end bonds (kept rank = dimension of the right part): QR of a Gaussian mix of M E
+RANGE_FINDER_STATS = {"bonds": 0}
+_GAUSS = {}
+
+
+def _gauss(D, k, dev):
+    """A fixed (D x k) standard normal matrix per shape and device (seeded: results are reproducible)."""
+    key = (int(D), int(k), str(dev))
+    if key not in _GAUSS:
+        g = torch.Generator(device="cpu").manual_seed(1000003 * int(D) + int(k))
+        _GAUSS[key] = (torch.randn((int(D), int(k)), dtype=F64, generator=g) / float(D) ** 0.5).to(dev)
+    return _GAUSS[key]
 
 
 def _rejected(h, ne, rank_gap):
@@ -219,6 +231,20 @@ class BatchedMatrixProductState:
             ME = empty(B, rows, D)                                     # columns permuted back to (b', r') on the fly
             ops.gemm(M, E[k + 1], ME, M=rows, N=D, K=D, a_m=D, a_k=1, b_k=D, b_n=1, c_m=D, c_n=(1, r, b),
                      batch=B, a_b=rows * D, b_b=D * D, c_b=rows * D)
+            if RANGE_FINDER and keep == right_dim and keep < rows and keep < D:
+                # the cut is the structural rank of the right part (chain end): the kept space is the whole range of A = M E M^T, which is the
+                # column space of M E (rank = keep exactly).  A fixed Gaussian mix of its columns has the same range, and Householder QR of
+                # that (rows x keep) block is an exact basis of it -- no eigen-problem and no squared conditioning (these bonds sit 25-29
+                # doublings deep in the spectrum of A: the projection solver's accuracy guard rejected every member and Jacobi took over).
+                Y = ops.matmul(ME, _gauss(D, keep, dev).expand(B, D, keep))
+                U, _ = ops.qrt(Y, keep, want_S=False)
+                RANGE_FINDER_STATS["bonds"] += 1
+                out.append(U.reshape(B, s, o, keep))
+                Tn = empty(B, keep, r, b)
+                ops.gemm(U, M, Tn, M=keep, N=D, K=rows, a_m=1, a_k=keep, b_k=D, b_n=1, c_m=r * b, c_n=(1, b, r),
+                         batch=B, a_b=rows * keep, b_b=rows * D, c_b=keep * r * b)
+                T = Tn
+                continue
             A = ops.matmul(ME, M.transpose(1, 2))
             U = None
             if PROJECTION_BATCHED and ops.dominant_subspace_batched_fits(rows, keep):
