@@ -69,3 +69,24 @@ def test_brickwall_16_qubits_truncated_to_chi_128_matches_numpy_tebd():
     got = c.get().to_tensor()
     assert np.max(np.abs(got - ref)) < 1e-9 * np.max(np.abs(ref))
     assert abs((st.conj() | st) - np.vdot(ref, ref)) < 1e-9
+
+
+def test_identity_basis_at_untruncated_bonds_gives_the_same_state():
+    """Complex bonds that keep their whole space take the identity basis instead of an eigen-solve (cplx.IDENTITY_MIN_M): the split is exact
+    for any unitary and later truncations only see that unitary on the bond index, so the final (truncated) state is the same."""
+    from syngular.quantum import Circuit
+    from syngular_b200 import cplx
+    rng = np.random.default_rng(21)
+    n, depth, chi = 14, 10, 64
+    structure = [(cc.haar(rng, 4).reshape(2, 2, 2, 2), i) for layer in range(depth) for i in range(layer % 2, n - 1, 2)]
+    saved = cplx.IDENTITY_MIN_M
+    try:
+        cplx.IDENTITY_MIN_M = 16            # bonds of 16 rows and more: many identity splits before the truncating ones
+        a = Circuit(n, structure=structure, chi_max=chi); a.run()
+        cplx.IDENTITY_MIN_M = 0             # every split by an eigen-solve
+        b = Circuit(n, structure=structure, chi_max=chi); b.run()
+    finally:
+        cplx.IDENTITY_MIN_M = saved
+    ta, tb = a.get().to_tensor(), b.get().to_tensor()
+    assert np.linalg.norm(tb) < 1.0 - 1e-6                                  # the run does truncate
+    assert np.max(np.abs(ta - tb)) < 1e-10 * np.max(np.abs(tb))

@@ -175,7 +175,7 @@ def test_relative_cutoff_stays_on_the_projection_solver(n, chi, chiw, cutoff):
         assert abs(disc[k] - discarded[k]) < 1e-10 * float(np.sum(spectra[k] ** 2))
 
 
-@pytest.mark.parametrize("m,k", [(64, 32), (128, 64), (160, 96), (512, 256)])
+@pytest.mark.parametrize("m,k", [(64, 32), (128, 64), (160, 96), (512, 256), (1024, 512)])
 def test_complex_hermitian_projection_solver_matches_eigh(m, k):
     """syn_dominant_subspace_c128: planar complex Hermitian in, planar basis out; the fused kernel forms only the even rows of the embedded
     products.  Projector U U^H against LAPACK's, orthonormality, info doubles in the embedded convention (traces count twice), and the
