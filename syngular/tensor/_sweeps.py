@@ -591,7 +591,11 @@ def _svd_basis(M, chi_max, cutoff, trunc):
         # complex unfolding: eigen-decomposition of the embedded Hermitian Gram matrix (cplx.svd_basis); a tall unfolding is
         # first reduced to its square triangular factor by the complex qrt
         if m > c:
-            Q1, R1 = cplx.qrt(M, c)
+            Q1 = cplx.polar_basis(M)                        # Newton-Schulz polar factor when it applies (large, full column rank)
+            if Q1 is None:
+                Q1, R1 = cplx.qrt(M, c)
+            else:
+                R1 = cplx.matmul(Q1.h(), M)
             U, keep, sigma, disc = cplx.svd_basis(R1, chi_max, cutoff, eigh_gram)
             core2d = cplx.matmul(Q1, U)
         else:

@@ -259,6 +259,25 @@ def qrt(A, q, want_S=True):
     return Q, S
 
 
+POLAR_MIN_ROWS = 128           # tall complex unfoldings with at least this many rows are reduced by the Newton-Schulz kernel (0 = never)
+
+
+def polar_basis(A):
+    """Orthonormal basis Q (m x c planar) of the column space of a tall planar complex matrix A (m > c) as the polar factor
+    A (A^H A)^(-1/2), by the fused Newton-Schulz kernel on the interleaved real embedding (a polynomial in E^T E applied to E is an
+    embedding again, so the even columns are the complex basis).  A 2048 x 1024 embedding takes ~4 ms against 51 ms for the Householder
+    kernel.  Returns None when the sizes do not fit or the iteration did not reach orthonormality (rank-deficient A): the caller then
+    takes qrt."""
+    m, c = A.shape
+    if not (POLAR_MIN_ROWS and m >= POLAR_MIN_ROWS and m > c and ops.orthonormalize_columns_fits(2 * m, 2 * c)):
+        return None
+    Qe, info = ops.orthonormalize_columns(embed(A))
+    h = info.cpu()
+    if not (bool(torch.isfinite(h).all()) and float(h[4]) < 1e-12):
+        return None
+    return polish_columns(unembed_columns(Qe, m, c))
+
+
 def _hermitian_embedding(H):
     """(m x m) Hermitian planar -> (2m x 2m) real symmetric [[Hr, -Hi], [Hi, Hr]] (block layout; symmetrised)."""
     top = torch.cat([H.re, -H.im], dim=1)
