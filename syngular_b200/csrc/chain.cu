@@ -17,6 +17,8 @@
 #include <climits>
 #include <cmath>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace syn {
@@ -53,17 +55,25 @@ static size_t trunc_ws_bytes(int m, int n, int q) {
 // Q (m x kept, contiguous) = orthonormal basis of span(L[:, :q]) (+ completion when q > n); S (kept x n, contiguous) = Q^T L when asked.
 // L: m x n, row stride ldl, unit column stride.  ws: trunc_ws_bytes(m, n, q).
 static int truncation_step(const double* L, int64_t ldl, int m, int n, int q, double* Q, double* S, void* ws, size_t ws_bytes, int* kept_out,
-                           cudaStream_t st) {
+                           cudaStream_t st, double* late_info = nullptr, bool* late_used = nullptr) {
+    // late_info != nullptr: SPECULATIVE step -- the Newton-Schulz route writes its 8 verdict doubles there and the host does not wait for
+    // them (the caller reads the verdicts of all sites once, after the sweep, and repeats the sweep with immediate verdicts if one failed)
     const int kept = std::min(q, m);
     *kept_out = kept;
+    if (late_used) *late_used = false;
     double* info = reinterpret_cast<double*>(static_cast<char*>(ws) + ws_bytes - 256);
     if (ortho_route(m, n, q) && (((uintptr_t)L) & 15) == 0 && (ldl & 1) == 0) {
-        if (int rc = syn_orthonormalize_columns_f64(L, ldl, m, q, ORTHO_NS_MAX, Q, ws, ws_bytes - 256, info, st)) return rc;
-        double h[8];
-        SYN_CUDA(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, st));
-        SYN_CUDA(cudaStreamSynchronize(st));
-        bool ok = h[4] < 1e-12;
-        for (double v : h) ok = ok && std::isfinite(v);
+        if (int rc = syn_orthonormalize_columns_f64(L, ldl, m, q, ORTHO_NS_MAX, Q, ws, ws_bytes - 256, late_info ? late_info : info, st)) return rc;
+        bool ok = true;
+        if (late_info) {
+            if (late_used) *late_used = true;
+        } else {
+            double h[8];
+            SYN_CUDA(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, st));
+            SYN_CUDA(cudaStreamSynchronize(st));
+            ok = h[4] < 1e-12;
+            for (double v : h) ok = ok && std::isfinite(v);
+        }
         if (ok) {
             if (S) {
                 syn_gemm_desc_t d = {kept, n, m, 1, IX(1), IX(kept), IX(0), IX(ldl), IX(1), IX(0), IX(n), IX(1), IX(0), 1.0, 0.0};
@@ -75,6 +85,21 @@ static int truncation_step(const double* L, int64_t ldl, int m, int n, int q, do
     int qk = 0;
     if (int rc = syn_qrt_f64(L, ldl, 1, 0, m, n, q, 1, Q, kept, 1, 0, S, S ? n : 0, S ? 1 : 0, 0, ws, ws_bytes - 256, &qk, st)) return rc;
     SYN_REQUIRE(qk == kept, "chain sweep: truncation step kept %d columns, expected %d", qk, kept);
+    return 0;
+}
+
+// the verdicts of a speculative sweep: one copy and one synchronisation for all sites
+static int late_verdicts(const double* infos, const std::vector<char>& used, int n_sites, bool* all_ok, cudaStream_t st) {
+    std::vector<double> h((size_t)n_sites * 8);
+    SYN_CUDA(cudaMemcpyAsync(h.data(), infos, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    SYN_CUDA(cudaStreamSynchronize(st));
+    *all_ok = true;
+    for (int k = 0; k < n_sites; k++) {
+        if (!used[k]) continue;
+        bool ok = h[(size_t)k * 8 + 4] < 1e-12;
+        for (int e = 0; e < 8; e++) ok = ok && std::isfinite(h[(size_t)k * 8 + e]);
+        if (!ok) *all_ok = false;
+    }
     return 0;
 }
 
@@ -121,8 +146,8 @@ static int plan_apply(int n, const int* xs, const int* wshape, int dim, int* out
     return 0;
 }
 
-static size_t apply_ws_bytes(const ApplyPlan& p) {
-    return 2 * up16(p.t_doubles * 8) + up16(p.t1_doubles * 8) + up16(p.m_doubles * 8) + up16(p.trunc_bytes) + 256;
+static size_t apply_ws_bytes(const ApplyPlan& p, int n_sites) {
+    return 2 * up16(p.t_doubles * 8) + up16(p.t1_doubles * 8) + up16(p.m_doubles * 8) + up16(p.trunc_bytes) + up16((size_t)n_sites * 64) + 256;
 }
 
 }  // namespace chain
@@ -141,24 +166,13 @@ extern "C" size_t syn_apply_round_chain_workspace_f64(int n_sites, const int* xs
     if (n_sites < 1 || !xshape || !wshape || dim < 1) return 0;
     ApplyPlan p;
     if (plan_apply(n_sites, xshape, wshape, dim, nullptr, p)) return 0;
-    return apply_ws_bytes(p);
+    return apply_ws_bytes(p, n_sites);
 }
 
-extern "C" int syn_apply_round_chain_f64(int n_sites, const double* const* X, const int* xshape, const double* const* W, const int* wshape, int dim,
-                                         double* const* out, void* ws, size_t ws_bytes, void* stream) {
-    SYN_REQUIRE(n_sites >= 1 && X && xshape && W && wshape && out && ws && dim >= 1, "syn_apply_round_chain_f64: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    ApplyPlan p;
-    if (int rc = plan_apply(n_sites, xshape, wshape, dim, nullptr, p)) return rc;
-    SYN_REQUIRE(ws_bytes >= apply_ws_bytes(p), "syn_apply_round_chain_f64: workspace too small (%zu < %zu bytes)", ws_bytes, apply_ws_bytes(p));
-    SYN_REQUIRE((((uintptr_t)ws) & 255) == 0, "syn_apply_round_chain_f64: the workspace must be 256-byte aligned");
-    char* base = static_cast<char*>(ws);
-    double* T = reinterpret_cast<double*>(base);            base += up16(p.t_doubles * 8);
-    double* Tn = reinterpret_cast<double*>(base);           base += up16(p.t_doubles * 8);
-    double* T1 = reinterpret_cast<double*>(base);           base += up16(p.t1_doubles * 8);
-    double* M = reinterpret_cast<double*>(base);            base += up16(p.m_doubles * 8);
-    void* tws = base;
-    const size_t tws_bytes = up16(p.trunc_bytes);
+// one left-to-right pass; speculative: no host wait per site, verdict slots of all sites in `infos`
+static int apply_round_pass(int n_sites, const double* const* X, const int* xshape, const double* const* W, const int* wshape, int dim,
+                            double* const* out, double* T, double* Tn, double* T1, double* M, void* tws, size_t tws_bytes, double* infos,
+                            bool speculative, std::vector<char>& used, cudaStream_t st) {
     const double one = 1.0;
     SYN_CUDA(cudaMemcpyAsync(T, &one, sizeof(double), cudaMemcpyHostToDevice, st));
     int s = 1;
@@ -170,7 +184,11 @@ extern "C" int syn_apply_round_chain_f64(int n_sites, const double* const* X, co
         if (int rc = contract_carry(T, s, X[k], a, i, b, W[k], l, o, r, T1, M, st)) return rc;
         const int rows = s * o, cols = b * r;
         int kept = 0;
-        if (int rc = truncation_step(M, cols, rows, cols, dim, out[k], nullptr, tws, tws_bytes, &kept, st)) return rc;
+        bool late = false;
+        if (int rc = truncation_step(M, cols, rows, cols, dim, out[k], nullptr, tws, tws_bytes, &kept, st, speculative ? infos + (size_t)k * 8 : nullptr,
+                                     &late))
+            return rc;
+        used[k] = late ? 1 : 0;
         // T_next[kept, r, b] = Q^T L with the columns of L (b major) re-ordered to (r, b) on the fly
         syn_gemm_desc_t dc = {kept, cols, rows, 1, IX(1), IX(kept), IX(0), IX(cols), IX(1), IX(0), IX((int64_t)r * b), IX2(1, b, r), IX(0), 1.0, 0.0};
         if (int rc = gemm_f64(dc, out[k], M, Tn, st)) return rc;
@@ -178,6 +196,37 @@ extern "C" int syn_apply_round_chain_f64(int n_sites, const double* const* X, co
         s = kept;
     }
     return 0;
+}
+
+extern "C" int syn_apply_round_chain_f64(int n_sites, const double* const* X, const int* xshape, const double* const* W, const int* wshape, int dim,
+                                         double* const* out, void* ws, size_t ws_bytes, void* stream) {
+    SYN_REQUIRE(n_sites >= 1 && X && xshape && W && wshape && out && ws && dim >= 1, "syn_apply_round_chain_f64: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    ApplyPlan p;
+    if (int rc = plan_apply(n_sites, xshape, wshape, dim, nullptr, p)) return rc;
+    SYN_REQUIRE(ws_bytes >= apply_ws_bytes(p, n_sites), "syn_apply_round_chain_f64: workspace too small (%zu < %zu bytes)", ws_bytes,
+                apply_ws_bytes(p, n_sites));
+    SYN_REQUIRE((((uintptr_t)ws) & 255) == 0, "syn_apply_round_chain_f64: the workspace must be 256-byte aligned");
+    char* base = static_cast<char*>(ws);
+    double* T = reinterpret_cast<double*>(base);            base += up16(p.t_doubles * 8);
+    double* Tn = reinterpret_cast<double*>(base);           base += up16(p.t_doubles * 8);
+    double* T1 = reinterpret_cast<double*>(base);           base += up16(p.t1_doubles * 8);
+    double* M = reinterpret_cast<double*>(base);            base += up16(p.m_doubles * 8);
+    void* tws = base;
+    const size_t tws_bytes = up16(p.trunc_bytes);           base += tws_bytes;
+    double* infos = reinterpret_cast<double*>(base);
+    // Speculative pass: the Newton-Schulz steps are queued without waiting for their verdicts (the host wait per site left the GPU idle for
+    // a launch latency 63 times a sweep); the verdicts of all sites are read once at the end.  A rejected site (dependent columns: the
+    // iteration did not reach orthonormality) repeats the sweep with immediate verdicts and the Householder fallback.
+    std::vector<char> used((size_t)n_sites, 0);
+    if (int rc = apply_round_pass(n_sites, X, xshape, W, wshape, dim, out, T, Tn, T1, M, tws, tws_bytes, infos, true, used, st)) return rc;
+    bool any = false;
+    for (char u : used) any = any || u;
+    if (!any) return 0;
+    bool all_ok = true;
+    if (int rc = late_verdicts(infos, used, n_sites, &all_ok, st)) return rc;
+    if (all_ok) return 0;
+    return apply_round_pass(n_sites, X, xshape, W, wshape, dim, out, T, Tn, T1, M, tws, tws_bytes, infos, false, used, st);
 }
 
 // ---- `>>` on a chain of cores (l, d, r), physical legs flattened ----------------------------------------------------------------------
@@ -215,23 +264,11 @@ extern "C" size_t syn_round_chain_workspace_f64(int n_sites, const int* shape, i
     if (n_sites < 1 || !shape || dim < 1) return 0;
     size_t c, t;
     if (plan_round(n_sites, shape, dim, nullptr, c, t)) return 0;
-    return 3 * up16(c * 8) + up16(t) + 256;
+    return 3 * up16(c * 8) + up16(t) + up16((size_t)n_sites * 64) + 256;
 }
 
-extern "C" int syn_round_chain_f64(int n_sites, const double* const* cores, const int* shape, int dim, double* const* out, void* ws, size_t ws_bytes,
-                                   void* stream) {
-    SYN_REQUIRE(n_sites >= 1 && cores && shape && out && ws && dim >= 1, "syn_round_chain_f64: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    size_t cd, tb;
-    if (int rc = plan_round(n_sites, shape, dim, nullptr, cd, tb)) return rc;
-    SYN_REQUIRE(ws_bytes >= 3 * up16(cd * 8) + up16(tb) + 256, "syn_round_chain_f64: workspace too small");
-    SYN_REQUIRE((((uintptr_t)ws) & 255) == 0, "syn_round_chain_f64: the workspace must be 256-byte aligned");
-    char* base = static_cast<char*>(ws);
-    double* S = reinterpret_cast<double*>(base);            base += up16(cd * 8);
-    double* Ca = reinterpret_cast<double*>(base);           base += up16(cd * 8);      // current core with the carry absorbed (ping)
-    double* Cb = reinterpret_cast<double*>(base);           base += up16(cd * 8);      // (pong)
-    void* tws = base;
-    const size_t tws_bytes = up16(tb);
+static int round_pass(int n_sites, const double* const* cores, const int* shape, int dim, double* const* out, double* S, double* Ca, double* Cb,
+                      void* tws, size_t tws_bytes, double* infos, bool speculative, std::vector<char>& used, cudaStream_t st) {
     const double* cur = cores[0];                   // (s * d) x r unfolding of the current core, contiguous
     int s = shape[0];
     for (int k = 0; k < n_sites; k++) {
@@ -243,7 +280,10 @@ extern "C" int syn_round_chain_f64(int n_sites, const double* const* cores, cons
         }
         const int rows = s * d;
         int kept = 0;
-        if (int rc = truncation_step(cur, r, rows, r, dim, out[k], S, tws, tws_bytes, &kept, st)) return rc;
+        bool late = false;
+        if (int rc = truncation_step(cur, r, rows, r, dim, out[k], S, tws, tws_bytes, &kept, st, speculative ? infos + (size_t)k * 8 : nullptr, &late))
+            return rc;
+        used[k] = late ? 1 : 0;
         // next core <- S (kept x r) @ next.reshape(r, d' r')
         const int dn = shape[3 * k + 4], rn = shape[3 * k + 5];
         double* nxt = (cur == Ca) ? Cb : Ca;
@@ -253,4 +293,30 @@ extern "C" int syn_round_chain_f64(int n_sites, const double* const* cores, cons
         s = kept;
     }
     return 0;
+}
+
+extern "C" int syn_round_chain_f64(int n_sites, const double* const* cores, const int* shape, int dim, double* const* out, void* ws, size_t ws_bytes,
+                                   void* stream) {
+    SYN_REQUIRE(n_sites >= 1 && cores && shape && out && ws && dim >= 1, "syn_round_chain_f64: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t cd, tb;
+    if (int rc = plan_round(n_sites, shape, dim, nullptr, cd, tb)) return rc;
+    SYN_REQUIRE(ws_bytes >= 3 * up16(cd * 8) + up16(tb) + up16((size_t)n_sites * 64) + 256, "syn_round_chain_f64: workspace too small");
+    SYN_REQUIRE((((uintptr_t)ws) & 255) == 0, "syn_round_chain_f64: the workspace must be 256-byte aligned");
+    char* base = static_cast<char*>(ws);
+    double* S = reinterpret_cast<double*>(base);            base += up16(cd * 8);
+    double* Ca = reinterpret_cast<double*>(base);           base += up16(cd * 8);      // current core with the carry absorbed (ping)
+    double* Cb = reinterpret_cast<double*>(base);           base += up16(cd * 8);      // (pong)
+    void* tws = base;
+    const size_t tws_bytes = up16(tb);                      base += tws_bytes;
+    double* infos = reinterpret_cast<double*>(base);
+    std::vector<char> used((size_t)n_sites, 0);             // speculative pass first, see syn_apply_round_chain_f64
+    if (int rc = round_pass(n_sites, cores, shape, dim, out, S, Ca, Cb, tws, tws_bytes, infos, true, used, st)) return rc;
+    bool any = false;
+    for (char u : used) any = any || u;
+    if (!any) return 0;
+    bool all_ok = true;
+    if (int rc = late_verdicts(infos, used, n_sites, &all_ok, st)) return rc;
+    if (all_ok) return 0;
+    return round_pass(n_sites, cores, shape, dim, out, S, Ca, Cb, tws, tws_bytes, infos, false, used, st);
 }

@@ -74,3 +74,29 @@ def test_chain_entry_points_reject_bad_arguments():
     W = [torch.randn(1, 2, 2, 2, dtype=torch.float64, device="cuda"), torch.randn(2, 2, 2, 1, dtype=torch.float64, device="cuda")]
     with pytest.raises(SynError):
         ops.apply_round_chain(X, W, 4)
+
+
+def test_chain_call_repeats_the_sweep_when_a_speculative_step_is_rejected():
+    """The chain call queues its Newton-Schulz truncation steps without waiting for their verdicts and reads them once at the end.  A plateau
+    site whose leading columns are dependent (a duplicated bond column) fails that iteration: the call must notice it afterwards, repeat
+    the sweep with immediate verdicts (Householder at that site) and return what the site-by-site sweep returns."""
+    from syngular.tensor import _sweeps as sw
+    import bench
+    X, W = bench.make_chain(2)
+    X = [np.array(c, copy=True) for c in X[:13]] + [np.array(X[13][:, :, :1], copy=True)]
+    Ws = [sw.as_core(c) for c in W[:13]] + [sw.as_core(W[13][:, :, :, :1])]
+    X[10][:, :, 1] = X[10][:, :, 0]                     # site 10 (256 x 2 x 256): bond column 1 duplicates column 0
+    Xs = [sw.as_core(c) for c in X]
+    one = sw.apply_round_qr(Xs, Ws, 256)
+    steps = sw.apply_round_qr_steps(Xs, Ws, 256)
+    for k, (a, b) in enumerate(zip(one, steps)):
+        assert a.shape == b.shape and bool(torch.isfinite(a).all())
+        if k < 10:                                      # before the deficient site both sweeps are the same kernels on the same data
+            assert float((a - b).abs().max().item()) < 1e-10, k
+    # at the deficient site the 16 dependent columns are replaced by completion directions, which are as arbitrary as LAPACK's in the
+    # reference (the two Householder kernels complete differently): the columns that ARE determined agree, every core is left-orthonormal
+    a, b = one[10].reshape(-1, 256), steps[10].reshape(-1, 256)
+    assert float((a[:, :16] - b[:, :16]).abs().max().item()) < 1e-10
+    for k in range(13):
+        L = one[k].reshape(-1, one[k].shape[-1])
+        assert float((L.t() @ L - torch.eye(L.shape[1], dtype=torch.float64, device=L.device)).abs().max()) < 1e-12, k
