@@ -276,6 +276,14 @@ int dominant_subspace_f64(const double* A, int n, int ne, int sp2_iters, int ns_
 // iteration counts adapt to the spectrum with no host round trip: SP2 stops two steps after tr(X - X^2) < 1e-11 ne, Newton-Schulz when
 // max |U^T U - I| < 1e-13.  While the smallest singular value of U is still far from 1 the steeper map 2x - x^3 replaces 1.5x - 0.5x^3.
 constexpr int PF_THREADS = 256, PF_BK = 128, PF_STAGES = 3, PF_LD = PF_BK + 4, PF_T = 32, PF_STEEP = 8;
+constexpr bool PF_SCALED_NS = true;
+#ifndef SYN_PF_L0_ORTHO_INV
+#define SYN_PF_L0_ORTHO_INV 32.0
+#endif
+#ifndef SYN_PF_L0_PROJ_INV
+#define SYN_PF_L0_PROJ_INV 512.0
+#endif
+constexpr double PF_L0_ORTHO = 1.0 / SYN_PF_L0_ORTHO_INV, PF_L0_PROJ = 1.0 / SYN_PF_L0_PROJ_INV;
 constexpr size_t PF_SMEM = (size_t)PF_STAGES * 2 * PF_T * PF_LD * sizeof(double);
 
 struct PurifyArgs {
@@ -575,6 +583,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
     int ns = 0;
     double dev = 0.0, dev0 = 0.0;
     int steep_steps = PF_STEEP;
+    double lo = 1.0;                     // running lower bound (estimate) of the singular values of the iterate, see the scaled step below
     bool last_steep = true;              // the map that produced the current iterate (the start counts as "not yet standard")
     double* Gc = a.G;
     for (;; ++ns) {
@@ -673,13 +682,31 @@ __global__ void __launch_bounds__(PF_THREADS, 1) purify_fused_kernel(const Purif
                 steep_steps = PF_STEEP - cut < 2 ? 2 : PF_STEEP - cut;
             }
         }
+        if (ns == 0) lo = dev0 > 0.5 ? (a.ns_only ? PF_L0_ORTHO : PF_L0_PROJ) : 1.0;
         if (ns >= 1 && !last_steep && fabs((double)ne - tr) < 8e-13) break;
         if (ns >= a.ns_max) break;
         // U' = ca U + cb U G   (G symmetric: rows of G are its columns), V' = U'^T
-        // the first steps use x -> 2x - x^3 (slope 2 at 0 instead of 1.5; values near 1 stay within [0.88, 1.09]): the smallest
-        // singular values of P[:, :ne] (1e-3 .. 1e-1 on the C2 chain) reach the quadratic region in half the steps
-        const bool steep = ns < steep_steps && dev0 > 0.5;
-        const double ca = (steep ? 2.0 : 1.5) * gamma, cb = (steep ? -1.0 : -0.5) * gamma * gamma * gamma;
+        bool steep;
+        double ca, cb;
+        if (PF_SCALED_NS) {
+            // Scaled Newton-Schulz: with the singular values in [lo, 1] the cubic x -> g x (3 - g^2 x^2) / 2, g^2 = 3 / (1 + lo + lo^2), maps
+            // both ends to the same value and its maximum to exactly 1 -- the best cubic for that interval (the small end grows ~2.5x per
+            // step instead of 2x for the fixed steep map 2x - x^3, and nothing ever exceeds 1, so tr G bounds every 1 - sigma^2 after any
+            // step).  lo is only an estimate (1/32 for the blocks of the QR sweep, whose condition numbers are 12-23; 1/512 for the
+            // leading columns of a projector): tracked through the maps it reaches 1, where the map is the standard 1.5 x - 0.5 x^3; a
+            // smaller true minimum just finishes with standard steps.
+            const double g2 = 3.0 / (1.0 + lo + lo * lo), g = sqrt(g2);
+            ca = 1.5 * g * gamma;
+            cb = -0.5 * g * g2 * gamma * gamma * gamma;
+            lo = fmin(1.0, 0.5 * g * lo * (3.0 - g2 * lo * lo));
+            steep = false;
+        } else {
+            // the first steps use x -> 2x - x^3 (slope 2 at 0 instead of 1.5; values near 1 stay within [0.88, 1.09]): the smallest
+            // singular values of P[:, :ne] (1e-3 .. 1e-1 on the C2 chain) reach the quadratic region in half the steps
+            steep = ns < steep_steps && dev0 > 0.5;
+            ca = (steep ? 2.0 : 1.5) * gamma;
+            cb = (steep ? -1.0 : -0.5) * gamma * gamma * gamma;
+        }
         if (a.cx) {
             for (int tile = blockIdx.x; tile < (n / 64) * TG; tile += gridDim.x) {
                 const int I = tile / TG, J = tile - I * TG;
