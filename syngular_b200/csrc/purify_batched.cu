@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const Pur
         pb_sum2(kept, unused, red);
         // ---- Newton-Schulz on U = P[:, :ne], in place ------------------------------------------------------------------------------------
         int ns = 0;
-        double dev0 = 0.0;
+        double dev0 = 0.0, lo = 1.0;
         bool last_steep = true;
         for (;; ++ns) {
             double gacc[gmt][gnt][2];
@@ -182,8 +182,12 @@ __global__ void __launch_bounds__(PB_THREADS, 1) purify_batched_kernel(const Pur
             if (ns == 0) dev0 = pb_max(dmax, red);             // how far the start is from orthonormal decides whether the steep map is used
             if (ns >= 1 && !last_steep && fabs(dne - trg) < 8e-13) break;
             if (ns >= a.ns_max) break;
-            const bool steep = ns < 8 && dev0 > 0.5;
-            const double ca = steep ? 2.0 : 1.5, cb = steep ? -1.0 : -0.5;
+            // scaled Newton-Schulz (see purify.cu): the best cubic for singular values in [lo, 1], lo an estimate tracked through the maps
+            if (ns == 0) lo = dev0 > 0.5 ? 1.0 / 512.0 : 1.0;
+            const double g2 = 3.0 / (1.0 + lo + lo * lo), gs = sqrt(g2);
+            const double ca = 1.5 * gs, cb = -0.5 * gs * g2;
+            lo = fmin(1.0, 0.5 * gs * lo * (3.0 - g2 * lo * lo));
+            const bool steep = false;
             double acc[mt][gnt][2];
             pb_mma<mt, gnt, LD, 1, LDG, 1, ne>(acc, X + i0 * LD, G + gj0 * LDG);   // U G (G symmetric: its rows are its columns)
             __syncthreads();                                   // every warp has read the old U
