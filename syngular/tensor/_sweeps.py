@@ -35,7 +35,9 @@ def as_core(x):
     if t.dtype not in (F64, C128):
         t = t.to(C128 if t.is_complex() else F64)
     if not t.is_cuda:
-        t = t.to(device())
+        # pinned host tensors upload asynchronously on the current stream (the kernels that read them are queued behind the copy; as with
+        # any non_blocking copy the caller must not overwrite the pinned buffer before the stream has passed it); pageable memory blocks
+        t = t.to(device(), non_blocking=t.is_pinned())
     return t.contiguous()
 
 
