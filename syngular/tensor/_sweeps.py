@@ -802,7 +802,39 @@ class _AsyncVerdict:
         return self.host.numpy().copy()
 
 
-def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None):
+class HostStreamer:
+    """Result cores leave the device while the sweep is still running: a core is copied to its pinned host buffer on a side stream as soon
+    as it is final (its projection verdict has been accepted), the caller's stream waits for the last copy at the end.  `bufs`: one pinned
+    1-D float64 host tensor per site, at least as long as the core."""
+
+    def __init__(self, bufs):
+        self.bufs, self.copied = list(bufs), 0
+        self.stream = torch.cuda.Stream(device())
+
+    def push(self, out, upto):
+        if upto <= self.copied:
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                   # everything that produces out[:upto] is queued before this point
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            for idx in range(self.copied, upto):
+                c = out[idx]
+                self.bufs[idx][: c.numel()].copy_(c.reshape(-1), non_blocking=True)
+        self.copied = upto
+
+    def finish(self, out):
+        self.push(out, len(out))
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def copy_to_host(sites, bufs):
+    """Plain (un-overlapped) form of HostStreamer for the routes that do not stream."""
+    h = HostStreamer(bufs)
+    h.finish(list(sites))
+
+
+def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None, host_out=None):
     """`W @ X` + optimal (SVD) rounding by the density-matrix algorithm: right environments, then a left-to-right sweep that finds the
     dominant eigenspace of M E M^T at every bond -- mathematically the truncation of round_svd(site_mpo_mps(...)) but every matrix
     stays <= (chi d) x D.  Eigenvalues are squared singular values, so values below ~1e-8 sigma_0 are noise: rank_tol.
@@ -818,7 +850,11 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None):
 
     `capture` (tests only): a dict {site: None}; the Gram matrix of that bond and the basis the solver kept are stored in it."""
     if 0.0 < cutoff < rank_tol:
-        return round_svd([site_mpo_mps(x, w) for x, w in zip(X, W)], chi_max, cutoff)
+        res = round_svd([site_mpo_mps(x, w) for x, w in zip(X, W)], chi_max, cutoff)
+        if host_out is not None:
+            copy_to_host(res[0], host_out)
+        return res
+    streamer = HostStreamer(host_out) if host_out is not None else None
     n = len(X)
     E = right_environments(X, W)
     trunc = Truncation()
@@ -905,5 +941,9 @@ def apply_round_dm(X, W, chi_max, cutoff=0.0, rank_tol=3.2e-7, capture=None):
                 k = pk + 1
                 queued = None
         pending = queued
+        if streamer is not None:                       # cores before the one still awaiting its verdict are final
+            streamer.push(out, queued[5] if queued is not None else len(out))
     out.append(contract_carry(T, X[-1], W[-1]))
+    if streamer is not None:
+        streamer.finish(out)
     return out, trunc

@@ -151,7 +151,7 @@ class MatrixProductOperator(_MatrixProduct):
         raise NotImplementedError("empty stub in the reference (MPO:653-655)")
 
 
-def _apply_to_state(W, X, min_bond, rounding=None, guard=True):
+def _apply_to_state(W, X, min_bond, rounding=None, guard=True, host_out=None):
     """MPO x MPS then `>> min_bond` (MPO:181-192).  The guard of `>>` is evaluated on the bonds the product WOULD have
     (from_sites metadata: products of the actual bonds), exactly like the reference's from_sites + compress."""
     prod_bonds = tuple(x.shape[2] * w.shape[3] for x, w in zip(X.sites[:-1], W.sites[:-1]))
@@ -174,7 +174,8 @@ def _apply_to_state(W, X, min_bond, rounding=None, guard=True):
     out.orthonormalized = None
     out.real_parameters_number = None
     if rounding == "svd":
-        out.sites, out.truncation = sw.apply_round_dm(X.sites, W.sites, min_bond, MatrixProductState.SVD_CUTOFF)
+        out.sites, out.truncation = sw.apply_round_dm(X.sites, W.sites, min_bond, MatrixProductState.SVD_CUTOFF, host_out=host_out)
+        out._streamed = host_out is not None          # the result cores were copied to the host from inside the sweep
     else:
         out.sites = sw.apply_round_qr(X.sites, W.sites, min_bond)
     out._refresh_from_cores(bonds=False)

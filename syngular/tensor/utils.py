@@ -4,11 +4,24 @@ from syngular.tensor.matrix_product_operator import MatrixProductOperator, _appl
 from syngular.tensor.matrix_product_state import MatrixProductState
 
 
-def mul(op1, op2, mode="standard", bond=None):
+def mul(op1, op2, mode="standard", bond=None, host_out=None):
     """mode="standard": the reference's path (contraction + `>> min_bond`, QR truncation unless set_rounding("svd")).
     mode="optimized": the density-matrix algorithm the reference sketched but never finished (MPO:193-260, utils.py:84-91):
     MPO x MPS with optimal (SVD) truncation, product cores never formed.
-    `bond` (extension): target bond dimension; defaults to the reference's min_bond rule."""
+    `bond` (extension): target bond dimension; defaults to the reference's min_bond rule.
+    `host_out` (extension, MPO x MPS only): one pinned 1-D float64 host tensor per site; the result cores are also copied into them --
+    from inside the sweep, overlapped with it, on the optimized route (a host-resident caller gets its arrays back without a
+    separate download phase); the returned chain still holds the device cores."""
+    res = _mul(op1, op2, mode, bond, host_out)
+    if host_out is not None:
+        if not isinstance(res, MatrixProductState) or any(not isinstance(c, sw.torch.Tensor) or c.is_complex() for c in res.sites):
+            raise Exception("host_out needs a real MPO x MPS product")
+        if not getattr(res, "_streamed", False):
+            sw.copy_to_host(res.sites, host_out)
+    return res
+
+
+def _mul(op1, op2, mode, bond, host_out):
     n, m = op1.sites_number, op2.sites_number
     min_bond = min(min(op1.bond_shape), min(op2.bond_shape))                 # utils.py:12
     guard = bond is None
@@ -25,7 +38,7 @@ def mul(op1, op2, mode="standard", bond=None):
             raise Exception("`syn.mul` mode 'optimized' needs one MatrixProductOperator and one MatrixProductState")
         if not op1.decomposed or not op2.decomposed:
             raise Exception("Operators and States must be decomposed")
-        return _apply_to_state(op1, op2, min_bond, rounding="svd", guard=guard)
+        return _apply_to_state(op1, op2, min_bond, rounding="svd", guard=guard, host_out=host_out)
     if mode == "standard":
         if isinstance(op1, MatrixProductState) and isinstance(op2, MatrixProductOperator):
             if not op1.decomposed or not op2.decomposed:

@@ -221,3 +221,19 @@ def test_apply_round_dm_with_a_cutoff_below_the_gram_resolution_follows_the_text
     # default cutoff: the density-matrix mode declares the 1e-9 part noise
     out0, _ = sw.apply_round_dm(Xd, Wd, 64)
     assert out0[n // 2 - 1].shape[-1] == 6
+
+
+def test_syn_mul_host_out_streams_the_result_cores():
+    """syn.mul(..., host_out=pinned buffers): the cores are copied to the host from inside the sweep (overlapped with it on the optimized
+    route, plainly on the standard route); the buffers must hold exactly the cores the call returns."""
+    import torch
+    import syngular as syn
+    from syngular.tensor import MatrixProductState as MPS, MatrixProductOperator as MPO
+    import bench
+    X, W = bench.make_chain(5, n=16, chi=64, chiw=8)
+    for mode, bond in (("optimized", 64), ("standard", 32)):
+        bufs = [torch.zeros(64 * 2 * 64, dtype=torch.float64).pin_memory() for _ in range(16)]
+        Y = syn.mul(MPO.from_sites(W), MPS.from_sites(X), mode=mode, bond=bond, host_out=bufs)
+        torch.cuda.synchronize()
+        for k, c in enumerate(Y.sites):
+            assert torch.equal(bufs[k][: c.numel()], c.reshape(-1).cpu()), (mode, k)
