@@ -177,13 +177,17 @@ int syn_dominant_subspace_c128(const double* Hre, const double* Him, int m, int 
 int syn_dominant_subspace_batched_fits(int n, int ne);
 int syn_dominant_subspace_batched_f64(const double* A, int batch, int n, int ne, int sp2_max, int ns_max, double* U, double* info, void* stream);
 
-/* Y[q][ro][x] = sum_ri W[ro][ri] X[q][ri][x]: a small matrix (rin, rout in {2, 4, 8, 16}; W row-major contiguous) applied to the middle index
+/* Y[q][ro][x] = sum_ri W[ro][ri] X[q][ri][x]: a small matrix (rin, rout in {2, 4, 8, 16}; W row-major contiguous, or strided in the
+ * _strided form: element (ro, ri) at W[ro * w_ro + ri * w_ri], e.g. an MPO core read in place) applied to the middle index
  * of a large tensor -- the contractions of a BATCH of chains with one shared MPO core (the per-site einsum of MPO:181-192 looped over states),
  * which are pure streaming (csrc/smallcore.cu).  X strides (x_q, x_r, x_l), Y strides (y_q, y_l) and a two-level ro index
  * ((ro / y_ro_div) * y_ro_outer + (ro % y_ro_div) * y_ro_inner), all in elements; x should be the unit-stride index of X. */
 int syn_apply_small_core_fits(int rin, int rout);
 int syn_apply_small_core_f64(const double* X, const double* W, double* Y, int64_t Q, int rin, int rout, int L, int64_t x_q, int64_t x_r,
                              int64_t x_l, int64_t y_q, int64_t y_ro_outer, int64_t y_ro_inner, int y_ro_div, int64_t y_l, void* stream);
+int syn_apply_small_core_strided_f64(const double* X, const double* W, int64_t w_ro, int64_t w_ri, double* Y, int64_t Q, int rin, int rout, int L,
+                                     int64_t x_q, int64_t x_r, int64_t x_l, int64_t y_q, int64_t y_ro_outer, int64_t y_ro_inner, int y_ro_div,
+                                     int64_t y_l, void* stream);
 
 /* out[i] = sum_p parts[p * part_stride + i], i < count: the reduction after a split-K syn_gemm_f64 (partials as the batch index). */
 int syn_sum_parts_f64(const double* parts, int64_t part_stride, int nparts, double* out, int64_t count, void* stream);

@@ -495,6 +495,9 @@ def decompose_right(T, shapes):
 # ---------------------------------------------------------------------------------------------------------
 # fused MPO x MPS application: the product core (a*l, o, b*r) is never materialised
 # ---------------------------------------------------------------------------------------------------------
+SMALL_CORE = True      # the carry x MPO-core contraction on the streaming kernel when the core is at most 16 x 16 (False: GEMM)
+
+
 def contract_carry(T, X, W):
     """M[s, o, (b,r)] = sum_{a,l,i} T[s,l,a] X[a,i,b] W[l,i,o,r].
     `T` is the carry of the sweep, stored (s, l, a) -- MPO bond major -- so that both GEMMs read unit-stride operands;
@@ -509,8 +512,14 @@ def contract_carry(T, X, W):
              batch=l, a_b=a, b_b=0, c_b=i * b)
     M = empty(s, o, b * r)
     # M[(s,b),(o,r)] = sum_{(l,i)} T1[s,(l,i),b] W[(l,i),(o,r)]
-    ops.gemm(T1, W, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
-             c_m=(o * b * r, r, b), c_n=(b * r, 1, r))
+    if SMALL_CORE and ops.small_core_fits(l * i, o * r) and W.is_contiguous() and s * b >= 4096:
+        # an MPO core of at most 16 x 16 against s b columns: streaming kernel, the core read in place as its transpose (csrc/smallcore.cu;
+        # at 32 x 32 -- the C2 chain -- the DMMA GEMM is faster: 22 vs 40 us)
+        ops.apply_small_core(T1, W, M, Q=s, L=b, x_q=l * i * b, x_r=b, x_l=1, y_q=o * b * r, y_ro=(b * r, 1, r), y_l=r,
+                             w=(o * r, l * i, 1, o * r))
+    else:
+        ops.gemm(T1, W, M, M=s * b, N=o * r, K=l * i, a_m=(l * i * b, 1, b), a_k=b, b_k=o * r, b_n=1,
+                 c_m=(o * b * r, r, b), c_n=(b * r, 1, r))
     return M
 
 

@@ -24,6 +24,9 @@
 namespace syn {
 
 int gemm_f64(const syn_gemm_desc_t& d, const double* A, const double* B, double* C, cudaStream_t st);
+int apply_small_core(const double* X, const double* W, int64_t w_ro, int64_t w_ri, double* Y, int64_t Q, int rin, int rout, int L, int64_t x_q,
+                     int64_t x_r, int64_t x_l, int64_t y_q, int64_t y_ro_outer, int64_t y_ro_inner, int y_ro_div, int64_t y_l, cudaStream_t stream);
+bool small_core_fits(int rin, int rout);
 
 namespace chain {
 
@@ -110,6 +113,9 @@ static int contract_carry(const double* T, int s, const double* X, int a, int i,
     syn_gemm_desc_t d1 = {s, i * b, a, l, IX((int64_t)l * a), IX(1), IX(a), IX((int64_t)i * b), IX(1), IX(0), IX((int64_t)l * i * b), IX(1),
                           IX((int64_t)i * b), 1.0, 0.0};
     if (int rc = gemm_f64(d1, T, X, T1, st)) return rc;
+    if (small_core_fits(l * i, o * r) && (int64_t)s * b >= 4096)
+        // an MPO core of at most 16 x 16 against s b columns: pure streaming (smallcore.cu), the core read in place as its transpose
+        return apply_small_core(T1, W, 1, (int64_t)o * r, M, s, l * i, o * r, b, (int64_t)l * i * b, b, 1, (int64_t)o * b * r, (int64_t)b * r, 1, r, r, st);
     syn_gemm_desc_t d2 = {s * b, o * r, l * i, 1, IX2((int64_t)l * i * b, 1, b), IX(b), IX(0), IX((int64_t)o * r), IX(1), IX(0),
                           IX2((int64_t)o * b * r, r, b), IX2((int64_t)b * r, 1, r), IX(0), 1.0, 0.0};
     return gemm_f64(d2, T1, W, M, st);

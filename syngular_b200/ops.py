@@ -290,15 +290,20 @@ def small_core_fits(rin, rout):
     return bool(lib.syn_apply_small_core_fits(_i32(int(rin)), _i32(int(rout))))
 
 
-def apply_small_core(X, Wm, Y, Q, L, x_q, x_r, x_l, y_q, y_ro, y_l):
-    """Y[q][ro][x] = sum_ri Wm[ro][ri] X[q][ri][x] (csrc/smallcore.cu): Wm a small contiguous (rout x rin) matrix, X / Y raw strided views
-    given by element strides; y_ro = (outer, inner, div) two-level index of ro.  Streaming kernel for the shared-MPO-core contractions."""
+def apply_small_core(X, Wm, Y, Q, L, x_q, x_r, x_l, y_q, y_ro, y_l, w=None):
+    """Y[q][ro][x] = sum_ri Wm[ro][ri] X[q][ri][x] (csrc/smallcore.cu): Wm a small contiguous (rout x rin) matrix -- or, with
+    w = (rout, rin, stride_ro, stride_ri), any tensor read in place as that strided matrix -- X / Y raw strided views given by element
+    strides; y_ro = (outer, inner, div) two-level index of ro.  Streaming kernel for the shared-MPO-core contractions."""
     require_cuda_f64(X, Wm, Y)
-    rout, rin = int(Wm.shape[0]), int(Wm.shape[1])
-    assert Wm.is_contiguous()
-    check(lib.syn_apply_small_core_f64(ptr(X), ptr(Wm), ptr(Y), _i64(int(Q)), _i32(rin), _i32(rout), _i32(int(L)), _i64(int(x_q)), _i64(int(x_r)),
-                                       _i64(int(x_l)), _i64(int(y_q)), _i64(int(y_ro[0])), _i64(int(y_ro[1])), _i32(int(y_ro[2])), _i64(int(y_l)),
-                                       stream_ptr()), "syn_apply_small_core_f64")
+    if w is None:
+        rout, rin = int(Wm.shape[0]), int(Wm.shape[1])
+        assert Wm.is_contiguous()
+        w_ro, w_ri = rin, 1
+    else:
+        rout, rin, w_ro, w_ri = (int(v) for v in w)
+    check(lib.syn_apply_small_core_strided_f64(ptr(X), ptr(Wm), _i64(w_ro), _i64(w_ri), ptr(Y), _i64(int(Q)), _i32(rin), _i32(rout), _i32(int(L)),
+                                               _i64(int(x_q)), _i64(int(x_r)), _i64(int(x_l)), _i64(int(y_q)), _i64(int(y_ro[0])), _i64(int(y_ro[1])),
+                                               _i32(int(y_ro[2])), _i64(int(y_l)), stream_ptr()), "syn_apply_small_core_f64")
     return Y
 
 

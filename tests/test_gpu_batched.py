@@ -129,7 +129,7 @@ def test_batched_apply_round_svd_through_the_projection_kernel():
         assert np.max(np.abs(dj - dg)) < 1e-10 * np.max(np.abs(dr))
 
 
-@pytest.mark.parametrize("rin,rout", [(8, 8), (4, 8), (16, 2), (2, 4)])
+@pytest.mark.parametrize("rin,rout", [(8, 8), (4, 8), (16, 2), (2, 4), (16, 16)])
 def test_small_core_kernel_matches_einsum(rin, rout):
     """csrc/smallcore.cu: Y[q][ro][x] = sum_ri W[ro][ri] X[q][ri][x] with strided X and a two-level ro index on the output."""
     from syngular_b200 import ops
@@ -148,6 +148,11 @@ def test_small_core_kernel_matches_einsum(rin, rout):
     ops.apply_small_core(Xd, Wd, Y2, Q=Q, L=L, x_q=rin * L, x_r=L, x_l=1, y_q=rout * L, y_ro=(L * ro_r, 1, ro_r), y_l=ro_r)
     want2 = ref.reshape(Q, rout // ro_r, ro_r, L).transpose(0, 1, 3, 2)
     assert np.max(np.abs(Y2.cpu().numpy() - want2)) < 1e-13 * np.max(np.abs(ref))
+    # the small matrix read in place as the transpose of a (rin x rout) tensor
+    Wt = torch.from_numpy(np.ascontiguousarray(Wm.T)).cuda()
+    Y3 = torch.empty((Q, rout, L), dtype=torch.float64, device="cuda")
+    ops.apply_small_core(Xd, Wt, Y3, Q=Q, L=L, x_q=rin * L, x_r=L, x_l=1, y_q=rout * L, y_ro=(0, L, rout), y_l=1, w=(rout, rin, 1, rout))
+    assert np.max(np.abs(Y3.cpu().numpy() - ref)) < 1e-13 * np.max(np.abs(ref))
 
 
 def test_batched_apply_round_svd_small_core_path_equals_the_gemm_path():

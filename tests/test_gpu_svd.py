@@ -237,3 +237,30 @@ def test_syn_mul_host_out_streams_the_result_cores():
         torch.cuda.synchronize()
         for k, c in enumerate(Y.sites):
             assert torch.equal(bufs[k][: c.numel()], c.reshape(-1).cpu()), (mode, k)
+
+
+def test_contract_carry_small_core_path_equals_the_gemm_path():
+    """chi_W = 8, d = 2: the carry x MPO-core contraction (16 x 16 core against s b >= 4096 columns) takes the streaming kernel, in the
+    Python-driven sweeps and in the C chain call; same results as the GEMM route."""
+    import torch
+    from syngular.tensor import _sweeps as sw
+    import bench
+    X, W = bench.make_chain(9, n=14, chi=64, chiw=8)
+    Xd, Wd = [sw.as_core(x) for x in X], [sw.as_core(w) for w in W]
+    T = torch.randn(64, 8, 64, dtype=torch.float64, device="cuda")
+    a = sw.contract_carry(T, Xd[7], Wd[7])
+    sw.SMALL_CORE = False
+    try:
+        b = sw.contract_carry(T, Xd[7], Wd[7])
+        ref_svd, _ = sw.apply_round_dm(Xd, Wd, 64)
+        ref_qr = sw.apply_round_qr_steps(Xd, Wd, 64)
+    finally:
+        sw.SMALL_CORE = True
+    assert float((a - b).abs().max()) < 1e-13 * float(b.abs().max())
+    got_svd, _ = sw.apply_round_dm(Xd, Wd, 64)
+    got_qr = sw.apply_round_qr(Xd, Wd, 64)                     # the C chain call
+    for x, y in zip(got_qr, ref_qr):
+        assert float((x - y).abs().max()) < 1e-10
+    n2 = float(sw.overlap(ref_svd, ref_svd).item())
+    d2 = n2 + float(sw.overlap(got_svd, got_svd).item()) - 2 * float(sw.overlap(got_svd, ref_svd).item())
+    assert abs(d2) < 1e-12 * n2
