@@ -205,3 +205,26 @@ def test_complex_hermitian_projection_solver_matches_eigh(m, k):
     Ue = Ue.re.cpu().numpy() + 1j * Ue.im.cpu().numpy()
     assert np.max(np.abs(Ue @ Ue.conj().T - U @ U.conj().T)) < 1e-10
     assert int(info_e.cpu()[7]) % 1000 == int(h[7]) % 1000           # the same number of SP2 steps: the iterates agree
+
+
+def test_host_streaming_survives_a_rolled_back_site():
+    """A steeply decaying spectrum (chi_W = 2) makes the accuracy guard reject projection results one site late: the sweep rolls back and
+    re-solves those sites with Jacobi.  Cores are streamed to the host only once their verdict is in, so the host buffers must still hold
+    exactly the cores the sweep returns."""
+    import bench
+    from syngular.tensor import _sweeps as sw
+    X, W = bench.make_chain(5, n=16, chi=64, chiw=2)
+    Xd, Wd = [sw.as_core(c) for c in X], [sw.as_core(c) for c in W]
+    bufs = [torch.zeros(64 * 2 * 64, dtype=torch.float64).pin_memory() for _ in range(16)]
+    saved = sw.PURIFY_MIN_N
+    try:
+        sw.PURIFY_MIN_N = 64
+        sw.PURIFY_STATS.update(taken=0, fallback=0)
+        out, _ = sw.apply_round_dm(Xd, Wd, 64, host_out=bufs)
+        fallbacks = sw.PURIFY_STATS["fallback"]
+    finally:
+        sw.PURIFY_MIN_N = saved
+    torch.cuda.synchronize()
+    assert fallbacks >= 1
+    for k, c in enumerate(out):
+        assert torch.equal(bufs[k][: c.numel()], c.reshape(-1).cpu()), k
